@@ -1,0 +1,188 @@
+/* lcx_b200.h -- C ABI of the B200-native Linear CorEx fit-loop library (liblcx_b200.so).
+ *
+ * This is the drop-in boundary for the hot path of gregversteeg/LinearCorex
+ * (linearcorex/linearcorex.py, class Corex).  The reference has no FFI of its own: its only
+ * accelerator seam is the `if self.gpu:` cudamat branch (cm.CUDAMatrix / cm.dot / .asarray at
+ * linearcorex.py:199-208, :217-223, :240-256, :340-352, :427-428), which ships Y and X^T Y back to
+ * the host after every GEMM.  The entry points below replace that seam one level up -- the array
+ * math of _calculate_moments_{ns,syn}, _sig, _norm, _update_{ns,syn}, preprocess, transform and
+ * get_covariance -- and are what a ctypes binding inside the reference would call.
+ *
+ * Conventions
+ *   - Every function returns an int: 0 = ok, LCX_QUICK_FAIL (1) = "max uj >= 1" (the reference's
+ *     `return False`, linearcorex.py:250-251), negative = error; lcx_last_error() gives the text.
+ *     No exception ever crosses this boundary.
+ *   - The library owns no array memory.  X~, the workspace and every output are device pointers
+ *     supplied by the caller (torch tensors in the shipped host code) with explicit sizes and
+ *     leading dimensions.  The session holds only launch state, a stream, a small pinned mailbox
+ *     for the O(1) scalars that gate host control flow, and pointers into the caller's workspace.
+ *   - All work is enqueued on the session's stream.  A call synchronises that stream only when it
+ *     returns host scalars (TC, max uj, tangent).
+ *   - Factor-major arrays (W, rho, ...) are m x n row-major with leading dimension lcx_ld(n)
+ *     (n rounded up to 16); the n x m arrays of the reference (X_i Y_j, X_i Z_j) are stored
+ *     transposed in that same layout.
+ *   - Sessions are not thread-safe; one host thread per GPU (one process per GPU under torchrun).
+ *   - Rows of X may be sharded across ranks: lcx_set_allreduce() installs the hook the library
+ *     calls wherever the reference's single-process sum over samples must become a sum over ranks.
+ */
+#ifndef LCX_B200_H
+#define LCX_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LCX_OK 0
+#define LCX_QUICK_FAIL 1
+#define LCX_ERR_ARG (-1)
+#define LCX_ERR_CUDA (-2)
+#define LCX_ERR_STATE (-3)
+
+/* precision modes */
+#define LCX_PRECISION_FP64 0   /* DMMA (mma.sync m8n8k4 f64) contractions, everything in binary64 */
+#define LCX_PRECISION_FAST 1   /* fp32-equivalent 3xTF32 tcgen05 contractions for the two X passes  */
+
+/* input dtypes of raw X */
+#define LCX_F32 0
+#define LCX_F64 1
+
+/* gaussianize modes (linearcorex.py:407-423) */
+#define LCX_GAUSS_STANDARD 0
+#define LCX_GAUSS_OUTLIERS 1
+#define LCX_GAUSS_NONE 2
+
+/* workspace arrays addressable through lcx_array_info(); "set" 0 = current moments, 1 = trial */
+enum lcx_array {
+    LCX_A_W = 0,        /* m x ld   weights `ws`                                   (set) */
+    LCX_A_RHO,          /* m x ld   moments['rho']                                 (set) */
+    LCX_A_INVRHO,       /* m x ld   moments['invrho']                              (set) */
+    LCX_A_RHOINVRHO,    /* m x ld   moments['rhoinvrho']                           (set) */
+    LCX_A_QIJ,          /* m x ld   moments['Qij']                                 (set) */
+    LCX_A_SI,           /* ld       moments['Si']                                  (set) */
+    LCX_A_QISI2,        /* ld       moments['Qi-Si^2'] (ns) / moments['Qi'] (syn)  (set) */
+    LCX_A_RY,           /* m x ldm  moments['ry']                                  (set) */
+    LCX_A_UJ,           /* m        moments['uj']                                  (set) */
+    LCX_A_GRAD,         /* m x ld   grad of _update_ns (:296-300)                        */
+    LCX_A_UPDATE,       /* m x ld   update (:303)                                        */
+    LCX_A_RDIR,         /* m x ld   _sig(update)                                         */
+    LCX_A_D,            /* m x ld (+ m) all-reduce buffer: X~^T(X~ A^T) then sum Y^2     */
+    LCX_A_MI,           /* m x ld   moments['MI']                                        */
+    LCX_A_XZ,           /* m x ld   moments['X_i Z_j']^T                                 */
+    LCX_A_XY,           /* m x ld   moments['X_i Y_j']^T                                 */
+    LCX_A_X2Y,          /* ld       moments['X_i^2 | Y']                                 */
+    LCX_A_IXY,          /* ld       moments['I(X_i ; Y)']                                */
+    LCX_A_YJ2,          /* m        moments['Y_j^2']                                     */
+    LCX_A_IYX,          /* m        moments['I(Y_j ; X)']                                */
+    LCX_A_TCS,          /* m        moments['TCs']                                       */
+    LCX_A_TCDIRECT,     /* m        moments['TC_direct']                                 */
+    LCX_A_CY,           /* m x ldm  moments['cy'] (syn)                                  */
+    LCX_A_Y,            /* N_local x ldy   Y = X~ A^T of the last projection             */
+    LCX_A_SCALARS,      /* 16       [0] TC [1] max uj [2] tangent [4] TC_no_overlap [5] sum I(X_i;Y)
+                                    [6] additivity [7] sum I(Y_j;X)                      */
+    LCX_A_COUNT
+};
+
+typedef struct lcx_session lcx_session;
+
+/* Sum `count` doubles at workspace offset `offset` (in doubles) over all ranks, in place, ordered
+ * on the session stream.  Installed by multi-GPU callers; NULL (default) = single rank. */
+typedef int (*lcx_allreduce_fn)(void* user, long long offset, long long count);
+
+/* ---- lifecycle ------------------------------------------------------------------------------ */
+int lcx_version(void);
+const char* lcx_last_error(void);
+int lcx_session_create(lcx_session** out, int device, int precision);
+int lcx_session_destroy(lcx_session* s);
+int lcx_set_stream(lcx_session* s, void* cuda_stream);
+int lcx_set_allreduce(lcx_session* s, lcx_allreduce_fn fn, void* user);
+int lcx_launch_count(lcx_session* s, long long* launches);   /* kernels launched so far by this session */
+
+/* ---- layout --------------------------------------------------------------------------------- */
+long long lcx_ld(int n_vars);                       /* leading dimension of m x n arrays */
+long long lcx_ldy(int n_factors);                   /* leading dimension of Y            */
+/* Doubles the caller must provide to lcx_bind for a problem of this size. */
+long long lcx_workspace_doubles(long long n_rows_local, int n_vars, int n_factors);
+/* Bind a preprocessed data block X~ (n_rows_local x n_vars, fp64, ld = ldx) and a workspace.
+ * n_rows_total = sum of n_rows_local over ranks (the reference's n_samples, :110). */
+int lcx_bind(lcx_session* s, const double* xt, long long n_rows_local, long long n_rows_total, int n_vars,
+             long long ldx, int n_factors, double* workspace, long long workspace_doubles);
+/* Offset (in doubles, from the workspace base), rows, cols and leading dimension of an array. */
+int lcx_array_info(lcx_session* s, int array_id, int set, long long* offset, long long* rows, long long* cols,
+                   long long* ld);
+
+/* ---- preprocessing: linearcorex.py:397-429 (preprocess), :497-510 (mean_impute), :483-487 (g) --- */
+/* pass 1: per-column sum and count of observed entries -> sum[n], cnt[n] (device).  scratch: slab partials */
+int lcx_colstats_sum(lcx_session* s, const void* x, int dtype, long long n_rows, int n_vars, long long ldx,
+                     int has_marker, double marker, double* sum, double* cnt, double* scratch,
+                     long long scratch_doubles);
+/* mean = sum / cnt  (after the caller all-reduced sum and cnt) */
+int lcx_colstats_mean(lcx_session* s, const double* sum, const double* cnt, double* mean, int n_vars);
+/* pass 2: per-column sum of squared deviations of observed entries -> sq[n] */
+int lcx_colstats_sqdev(lcx_session* s, const void* x, int dtype, long long n_rows, int n_vars, long long ldx,
+                       int has_marker, double marker, const double* mean, double* sq, double* scratch,
+                       long long scratch_doubles);
+/* std = clip(sqrt(sq / (use_nobs ? cnt : n_rows_total)), 1e-10)   (:413 vs :421) */
+int lcx_colstats_std(lcx_session* s, const double* sq, const double* cnt, double n_rows_total, int use_nobs,
+                     double* sd, int n_vars);
+/* X~ = g?((impute(x) - mean) / std), fp64, ld = ldo (columns >= n_vars zero-filled).  Missing entries
+ * take impute[i] -- the column mean of the data being preprocessed (mean_impute runs on transform()
+ * inputs too, :389/:404), which differs from theta's mean outside fit. */
+int lcx_standardize(lcx_session* s, const void* x, int dtype, long long n_rows, int n_vars, long long ldx,
+                    int has_marker, double marker, int gauss_mode, const double* impute, const double* mean,
+                    const double* sd, double* out, long long ldo);
+long long lcx_colstats_scratch_doubles(long long n_rows, int n_vars);
+
+/* ---- the two X contractions ----------------------------------------------------------------- */
+/* Y = X~ A^T  (:247, :210, :226, :394) and optionally colsq[j] = sum_l Y_lj^2 (:248, :227).
+ * Free-standing (no bound problem needed): used by transform().  scratch >= lcx_project_scratch_doubles. */
+int lcx_project(lcx_session* s, const double* xt, long long n_rows, int n_vars, long long ldx, const double* a,
+                long long lda, int n_factors, double* y, long long ldy, double* colsq, double* scratch,
+                long long scratch_doubles);
+long long lcx_project_scratch_doubles(long long n_rows, int n_factors);
+/* _sig (:196-213) on the bound X~: out = (1-eps^2) (X~^T (X~ u^T))^T / N + eps^2 u, all m x ld device arrays */
+int lcx_sig(lcx_session* s, const double* u, double eps, double* out);
+
+/* ---- fit-loop steps on the bound problem ----------------------------------------------------- */
+int lcx_set_w(lcx_session* s, const double* host_w, long long host_ld);          /* upload ws (m x n) into set 0 */
+int lcx_get_w(lcx_session* s, double* host_w, long long host_ld);                /* download set 0 ws           */
+int lcx_init_scale(lcx_session* s, double eps);                                  /* ws /= 10 _norm(x, ws)  (:117) */
+int lcx_stage_rescale(lcx_session* s, double eps, double eps_prev);              /* :130-133                      */
+int lcx_permute_rows(lcx_session* s, const int* host_order);                     /* ws = ws[order]         (:162) */
+/* _calculate_moments_ns(x, ws, quick=True) from X~ for set 0 (:236-276).  Returns LCX_QUICK_FAIL when
+ * max uj >= 1 and check_uj != 0.  tc / max_uj are host outputs. */
+int lcx_moments_ns(lcx_session* s, double eps, int check_uj, double* tc, double* max_uj);
+/* the quick=False extras (:277-287) for set 0; host outputs: TC_no_overlap, additivity */
+int lcx_details_ns(lcx_session* s, double* tc_no_overlap, double* additivity);
+/* search direction of _update_ns (:292-305); host output: update_tangent */
+int lcx_direction_ns(lcx_session* s, double eps, double* tangent);
+/* one backtracking trial (:320-321): set 1 <- moments of ws + eta*update.
+ * exact = 0: through the linearity of _sig (no pass over X);  exact = 1: from X~ like the reference. */
+int lcx_trial_ns(lcx_session* s, double eps, double eta, int exact, double* tc, double* max_uj);
+int lcx_accept_trial(lcx_session* s);                                            /* set 0 <-> set 1 (:333-334)   */
+/* _calculate_moments_syn (:336-373) for set 0; host output TC */
+int lcx_moments_syn(lcx_session* s, double* tc, double* additivity);
+/* _update_syn (:375-384): ws <- (1-eta) ws + eta (R - H ws), then moments_syn */
+int lcx_update_syn(lcx_session* s, double eta, double* tc, double* additivity);
+
+/* ---- get_covariance (:443-455) ---------------------------------------------------------------- */
+/* rows [row0, row0+rows) of the n x n covariance into out (rows x ldc, device).  synergy = 0: ns formula
+ * with eps; synergy = 1: X_i Z_j X_i Y_j^T.  sd = theta[1] (device, n). */
+int lcx_get_covariance(lcx_session* s, int synergy, double eps, const double* sd, int row0, int rows, double* out,
+                       long long ldc);
+
+/* ---- raw FP64 tensor-core GEMM (unit tests / building block) ----------------------------------- */
+/* layout: 0 = A[M][K], B[N][K];  1 = A[K][M], B[K][N];  2 = A[M][K], B[K][N].  C = A*B (+ cadd), optionally
+ * stored transposed.  scratch holds split-K partials (may be NULL with max_splits <= 1). */
+int lcx_gemm_f64(lcx_session* s, int layout, int M, int N, int K, const double* a, long long lda, const double* b,
+                 long long ldb, double* c, long long ldc, int trans_out, const double* cadd, int max_splits,
+                 double* scratch, long long scratch_doubles);
+/* out = inverse(a) for an m x m device matrix; aug >= 2*m*m doubles of scratch */
+int lcx_inverse(lcx_session* s, const double* a, long long lda, int m, double* out, long long ldo, double* aug);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LCX_B200_H */

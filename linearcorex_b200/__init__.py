@@ -1,0 +1,5 @@
+"""linearcorex_b200: B200-native Linear CorEx fit loop behind the `linearcorex.Corex` API."""
+from .corex import Corex  # noqa: F401
+from .sharding import Reducer, shard_rows  # noqa: F401
+
+__all__ = ["Corex", "Reducer", "shard_rows"]

@@ -1,0 +1,570 @@
+"""`Corex`: the sklearn-style Linear CorEx model of gregversteeg/LinearCorex, B200-native.
+
+Drop-in for `linearcorex.Corex` (reference linearcorex/linearcorex.py:22-455): same constructor
+keywords and defaults (:72-74), `fit` / `fit_transform` / `transform` / `predict` / `invert` /
+`get_covariance` / `clusters()` / `tc` / `tcs` / `mis`, attributes `ws`, `moments`, `theta`,
+`history`, `eps`, `m`, `n_samples`, `nv`, `n_obs`, global-RNG seeding (:89, :116) and warm start
+(:114).  This file is host control flow only: every array operation runs in liblcx_b200.so
+(hand-written sm_100a CUDA behind the C ABI of include/lcx_b200.h); torch owns the device
+buffers and, for multi-GPU runs, supplies `torch.distributed`.  Only O(1) scalars (TC, max uj,
+update_tangent) cross to the host inside the loop, at the points where the reference branches
+on them (:250, :306, :327, :144, :152).
+
+There is no CPU fallback.  If the CUDA library or a CUDA device is missing, construction of the
+device session raises.
+
+Extensions over the reference signature (all keyword-only in spirit, defaults keep reference
+behaviour):
+  eliminate_synergy   README/docstring name of `discourage_overlap` (README.md:32)
+  precision           'fp64' (default): all arithmetic binary64, parity target = the reference's
+                      numpy float64 path.  'fast': 3xTF32 tensor-core X contractions.
+  exact_trials        False (default): backtracking trials are evaluated through the linearity of
+                      `_sig` (rho(W + eta U) = rho(W) + eta _sig(U)) -- one pass pair over X per
+                      iteration instead of one per trial.  True: every trial
+                      re-reads X exactly like linearcorex.py:321.
+  input_dtype         'float64' (default) keeps the input as given (the float64 reference path);
+                      'float32' reproduces the reference's cast at :108 and :116.
+  comm                None, or a torch.distributed process group / True for the default group:
+                      `fit(x)` then takes this rank's row block of X (sample sharding).
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from .sharding import Reducer
+
+ANNEAL_SCHEDULE = [0.6 ** k for k in range(1, 7)] + [0]  # linearcorex.py:119
+
+
+def _torch():
+    import torch
+    return torch
+
+
+class _DeviceSession(object):
+    """Owns the lcx_session handle, the bound X~ block and the torch workspace."""
+
+    def __init__(self, precision, device=None):
+        torch = _torch()
+        self.lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise _lib.LcxError("no CUDA device: linearcorex_b200 has no CPU path")
+        self.device = torch.device("cuda", torch.cuda.current_device() if device is None else device)
+        torch.cuda.set_device(self.device)
+        h = C.c_void_p()
+        _lib.check(self.lib.lcx_session_create(C.byref(h), self.device.index, precision), "lcx_session_create")
+        self.h = h
+        self.stream = torch.cuda.current_stream(self.device)
+        _lib.check(self.lib.lcx_set_stream(self.h, C.c_void_p(self.stream.cuda_stream)), "lcx_set_stream")
+        self.xt = None
+        self.ws = None
+        self._hook = None
+        self.n = self.m = 0
+
+    def close(self):
+        if getattr(self, "h", None) is not None and self.h:
+            self.lib.lcx_session_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- plumbing ----------------------------------------------------------------------------
+    def launches(self):
+        v = C.c_longlong(0)
+        _lib.check(self.lib.lcx_launch_count(self.h, C.byref(v)))
+        return v.value
+
+    def bind(self, xt, n_rows_total, n_vars, n_factors, reducer):
+        torch = _torch()
+        n_local = xt.shape[0]
+        need = self.lib.lcx_workspace_doubles(n_local, n_vars, n_factors)
+        if need <= 0:
+            raise _lib.LcxError("bad problem shape")
+        self.ws = torch.zeros(need, dtype=torch.float64, device=self.device)
+        self.xt = xt
+        self.n, self.m = n_vars, n_factors
+        _lib.check(self.lib.lcx_bind(self.h, xt.data_ptr(), n_local, n_rows_total, n_vars, xt.stride(0), n_factors,
+                                     self.ws.data_ptr(), need), "lcx_bind")
+        if reducer is not None and reducer.world > 1:
+            ws = self.ws
+
+            def hook(_user, offset, count):
+                try:
+                    reducer.sum_(ws[offset:offset + count])
+                    return 0
+                except Exception:  # never let an exception unwind through the C frame
+                    return 1
+            self._hook = _lib.ALLREDUCE_FN(hook)
+            _lib.check(self.lib.lcx_set_allreduce(self.h, self._hook, None), "lcx_set_allreduce")
+        else:
+            self._hook = None
+            _lib.check(self.lib.lcx_set_allreduce(self.h, C.cast(None, _lib.ALLREDUCE_FN), None), "lcx_set_allreduce")
+
+    def view(self, array_id, which=0):
+        off, rows, cols, ld = (C.c_longlong() for _ in range(4))
+        _lib.check(self.lib.lcx_array_info(self.h, array_id, which, C.byref(off), C.byref(rows), C.byref(cols),
+                                           C.byref(ld)), "lcx_array_info")
+        flat = self.ws[off.value: off.value + rows.value * ld.value]
+        return flat.view(rows.value, ld.value)[:, :cols.value]
+
+    def host(self, array_id, which=0, squeeze=False):
+        a = self.view(array_id, which).cpu().numpy().copy()
+        return a[0] if squeeze else a
+
+
+class Corex(object):
+    """Linear Total Correlation Explanation on B200 (see module docstring)."""
+
+    def __init__(self, n_hidden=10, max_iter=10000, tol=1e-5, anneal=True, missing_values=None,
+                 discourage_overlap=True, gaussianize='standard', gpu=True, verbose=False, seed=None,
+                 eliminate_synergy=None, precision='fp64', exact_trials=False, input_dtype='float64',
+                 comm=None, device=None):
+        self.m = n_hidden
+        self.max_iter = max_iter
+        self.tol = tol
+        self.anneal = anneal
+        self.eps = 0
+        self.missing_values = missing_values
+        if eliminate_synergy is not None:
+            discourage_overlap = bool(eliminate_synergy)
+        self.discourage_overlap = discourage_overlap
+        self.gaussianize = gaussianize
+        self.gpu = True  # kept for signature compatibility; the device path is the only path
+        self.yscale = 1.
+        if gaussianize not in ('standard', 'outliers', 'none'):
+            raise ValueError("gaussianize must be 'standard', 'outliers' or 'none' "
+                             "('empirical' is not supported: the reference itself cannot invert it, :425)")
+        if precision not in ('fp64', 'fast'):
+            raise ValueError("precision must be 'fp64' or 'fast'")
+        if input_dtype not in ('float64', 'float32'):
+            raise ValueError("input_dtype must be 'float64' or 'float32'")
+        self.precision = precision
+        self.exact_trials = bool(exact_trials)
+        self.input_dtype = input_dtype
+        np.random.seed(seed)  # :89 -- the reference seeds the *global* legacy RNG at construction
+        self.verbose = verbose
+        if verbose:
+            np.set_printoptions(precision=3, suppress=True, linewidth=160)
+            print('Linear CorEx with {:d} latent factors'.format(n_hidden))
+        self.n_samples, self.nv = 0, 0
+        self.ws = np.zeros((0, 0))
+        self.moments = {}
+        self.theta = None
+        self.n_obs = 0
+        self.history = {}
+        self.trace = []          # per-iteration: eps, eta, trials, quick_fails, tangent, TC
+        self._comm = comm
+        self._device = device
+        self._sess = None
+        self._theta_dev = None
+
+    # ------------------------------------------------------------------------------------------
+    # pickling (vis_corex.py:549): host state only
+    # ------------------------------------------------------------------------------------------
+    def __getstate__(self):
+        d = dict(self.__dict__)
+        for k in ("_sess", "_theta_dev", "_comm"):
+            d[k] = None
+        return d
+
+    # ------------------------------------------------------------------------------------------
+    # properties of the reference (:177-194)
+    # ------------------------------------------------------------------------------------------
+    @property
+    def tc(self):
+        return self.moments["TC"]
+
+    @property
+    def tcs(self):
+        return self.moments["TCs"]
+
+    @property
+    def mis(self):
+        return - 0.5 * np.log1p(-self.moments["rho"] ** 2)
+
+    def clusters(self):
+        return np.argmax(np.abs(self.ws), axis=0)
+
+    # ------------------------------------------------------------------------------------------
+    # device helpers
+    # ------------------------------------------------------------------------------------------
+    def _session(self):
+        if self._sess is None:
+            prec = _lib.PRECISION_FP64 if self.precision == 'fp64' else _lib.PRECISION_FAST
+            self._sess = _DeviceSession(prec, self._device)
+        return self._sess
+
+    def _reducer(self):
+        return Reducer(self._comm)
+
+    def _upload(self, x):
+        """Host array -> device tensor (float32 or float64), through pinned staging in row chunks."""
+        torch = _torch()
+        sess = self._session()
+        x = np.ascontiguousarray(x)
+        out = torch.empty(x.shape, dtype=torch.float32 if x.dtype == np.float32 else torch.float64, device=sess.device)
+        rows = max(1, int((256 << 20) // max(1, x.shape[1] * x.itemsize)))
+        stage = None
+        for lo in range(0, x.shape[0], rows):
+            hi = min(x.shape[0], lo + rows)
+            src = torch.from_numpy(x[lo:hi])
+            if x.shape[0] > rows:  # large input: pinned double-buffer-free staging
+                if stage is None:
+                    stage = torch.empty((rows, x.shape[1]), dtype=src.dtype).pin_memory()
+                stage[:hi - lo].copy_(src)
+                out[lo:hi].copy_(stage[:hi - lo], non_blocking=True)
+                torch.cuda.current_stream().synchronize()
+            else:
+                out[lo:hi].copy_(src)
+        return out
+
+    def _as_input(self, x):
+        """Device tensors pass through (row block already resident); host data is cast like :108."""
+        torch = _torch()
+        if isinstance(x, torch.Tensor) and x.is_cuda:
+            if x.dtype not in (torch.float32, torch.float64):
+                x = x.double()
+            if self.input_dtype == 'float32' and x.dtype != torch.float32:
+                x = x.float()
+            return x.contiguous()
+        want = np.float32 if self.input_dtype == 'float32' else np.float64
+        x = np.asarray(x)
+        if x.dtype == np.float32 and want == np.float64:
+            return self._upload(x)  # float32 values are exact in float64: keep the narrow upload
+        return self._upload(np.asarray(x, dtype=want))
+
+    def preprocess(self, x, fit=False):
+        """Device preprocessing (:397-429).  Returns the fp64 X~ tensor (N x ld)."""
+        torch = _torch()
+        sess = self._session()
+        lib = sess.lib
+        red = self._reducer()
+        xd = self._as_input(x)
+        N, n = xd.shape
+        dt = _lib.F32 if xd.dtype == torch.float32 else _lib.F64
+        ldo = lib.lcx_ld(n)
+        out = torch.empty((N, ldo), dtype=torch.float64, device=sess.device)
+        has_marker = self.missing_values is not None
+        marker = float(self.missing_values) if has_marker else 0.0
+        mode = _lib.GAUSS[self.gaussianize]
+        vec = lambda: torch.zeros(n, dtype=torch.float64, device=sess.device)
+        nscr = lib.lcx_colstats_scratch_doubles(N, n)
+        scratch = torch.empty(nscr, dtype=torch.float64, device=sess.device)
+        impute = mean = sd = None
+        n_total = red.sum_scalar(N)
+        if has_marker or (fit and mode != _lib.GAUSS['none']):
+            ssum, cnt = vec(), vec()
+            _lib.check(lib.lcx_colstats_sum(sess.h, xd.data_ptr(), dt, N, n, xd.stride(0), int(has_marker), marker,
+                                            ssum.data_ptr(), cnt.data_ptr(), scratch.data_ptr(), nscr), "lcx_colstats_sum")
+            red.sum_(ssum)
+            red.sum_(cnt)
+            impute = vec()
+            _lib.check(lib.lcx_colstats_mean(sess.h, ssum.data_ptr(), cnt.data_ptr(), impute.data_ptr(), n))
+            self.n_obs = cnt.cpu().numpy().astype(np.int64) if has_marker else int(n_total)
+        else:
+            self.n_obs = int(n_total)
+        if mode != _lib.GAUSS['none']:
+            if fit:
+                mean = impute
+                sq, sd = vec(), vec()
+                _lib.check(lib.lcx_colstats_sqdev(sess.h, xd.data_ptr(), dt, N, n, xd.stride(0), int(has_marker), marker,
+                                                  mean.data_ptr(), sq.data_ptr(), scratch.data_ptr(), nscr),
+                           "lcx_colstats_sqdev")
+                red.sum_(sq)
+                _lib.check(lib.lcx_colstats_std(sess.h, sq.data_ptr(), cnt.data_ptr(), float(n_total),
+                                                int(self.gaussianize == 'standard'), sd.data_ptr(), n))
+                self._theta_dev = (mean, sd)
+                self.theta = (mean.cpu().numpy().copy(), sd.cpu().numpy().copy())
+            else:
+                if self._theta_dev is None:  # e.g. after unpickling
+                    self._theta_dev = tuple(torch.as_tensor(np.asarray(t, dtype=np.float64), device=sess.device)
+                                            for t in self.theta)
+                mean, sd = self._theta_dev
+        p = lambda t: t.data_ptr() if t is not None else None
+        _lib.check(lib.lcx_standardize(sess.h, xd.data_ptr(), dt, N, n, xd.stride(0), int(has_marker), marker, mode,
+                                       p(impute), p(mean), p(sd), out.data_ptr(), ldo), "lcx_standardize")
+        return out
+
+    # ------------------------------------------------------------------------------------------
+    # fit (:107-164)
+    # ------------------------------------------------------------------------------------------
+    def fit(self, x):
+        sess = self._session()
+        lib = sess.lib
+        red = self._reducer()
+        xt = self.preprocess(x, fit=True)
+        n_local, self.nv = xt.shape[0], int(np.shape(x)[1])
+        self.n_samples = int(red.sum_scalar(n_local))
+        if self.m is None:
+            raise ValueError("n_hidden=None (pick_n_hidden) is not supported: the reference helper is broken (:458-480)")
+        sess.bind(xt, self.n_samples, self.nv, self.m, red)
+        tcv, muj, tang, addv = (C.c_double() for _ in range(4))
+
+        schedule = [0.]
+        if self.ws.size == 0:  # :114-121
+            if self.discourage_overlap:
+                w0 = np.random.randn(self.m, self.nv)
+                if self.input_dtype == 'float32':
+                    w0 = w0.astype(np.float32)
+                self._set_w(w0)
+                _lib.check(lib.lcx_init_scale(sess.h, float(self.eps)), "lcx_init_scale")
+                if self.anneal:
+                    schedule = list(ANNEAL_SCHEDULE)
+            else:
+                self._set_w(np.random.randn(self.m, self.nv) * self.yscale ** 2 / np.sqrt(self.nv))
+        else:
+            self._set_w(self.ws)
+
+        def moments_from_x():
+            if self.discourage_overlap:
+                _lib.check(lib.lcx_moments_ns(sess.h, float(self.eps), 0, C.byref(tcv), C.byref(muj)), "lcx_moments_ns")
+            else:
+                _lib.check(lib.lcx_moments_syn(sess.h, C.byref(tcv), C.byref(addv)), "lcx_moments_syn")
+            return tcv.value
+
+        self.moments = {"TC": moments_from_x()}  # :122
+        early_exit = False
+        for i_eps, eps in enumerate(schedule):
+            eps0, self.eps = self.eps, eps
+            if i_eps > 0:  # :129-133
+                _lib.check(lib.lcx_stage_rescale(sess.h, float(eps), float(eps0)), "lcx_stage_rescale")
+            self.moments = {"TC": moments_from_x()}  # :134
+            delta = 0.0
+            for i_loop in range(self.max_iter):
+                last_tc = self.tc
+                rec = {"eps": eps}
+                if self.discourage_overlap:
+                    ok = self._update_ns(rec)
+                else:
+                    _lib.check(lib.lcx_update_syn(sess.h, 0.1, C.byref(tcv), C.byref(addv)), "lcx_update_syn")
+                    self.moments = {"TC": tcv.value, "additivity": addv.value}
+                    ok = True
+                if not ok or not np.isfinite(self.tc):  # :144-149
+                    if not ok:
+                        print("Error... updates giving invalid solutions?")
+                        early_exit = True
+                        break
+                    print("Error: TC is no longer finite: {}".format(self.tc))
+                delta = np.abs(self.tc - last_tc)
+                rec["TC"] = self.tc
+                self.trace.append(rec)
+                self.history["TC"] = self.history.get("TC", []) + [self.tc]
+                if self.verbose > 1:
+                    print("TC={:.3f}\tadd={:.3f}\tdelta={:.6f}".format(self.tc, self.moments.get("additivity", 0), delta))
+                if delta < self.tol:
+                    if self.verbose:
+                        print('{:d} iterations to tol: {:f}, TC={:f}'.format(i_loop, self.tol, self.tc))
+                    break
+            else:
+                if self.verbose:
+                    print("Warning: Convergence not achieved in {:d} iterations. Final delta: {:f}".format(
+                        self.max_iter, float(delta)))
+            if early_exit:
+                break
+        if early_exit:  # the reference returns from inside the loop (:149) without the final sort
+            self.ws = self._get_w()
+            return self
+        # :160-163 full moments, sort factors by TCs (descending), full moments again
+        self._full_moments()
+        order = np.argsort(-self.moments["TCs"])
+        _lib.check(lib.lcx_permute_rows(sess.h, (C.c_int * self.m)(*[int(o) for o in order])), "lcx_permute_rows")
+        self._full_moments()
+        self.ws = self._get_w()
+        return self
+
+    def fit_transform(self, x):
+        self.fit(x)
+        return self.transform(x)
+
+    def _set_w(self, w):
+        sess = self._session()
+        w = np.ascontiguousarray(w, dtype=np.float64)
+        _lib.check(sess.lib.lcx_set_w(sess.h, w.ctypes.data_as(C.c_void_p), w.shape[1]), "lcx_set_w")
+
+    def _get_w(self):
+        sess = self._session()
+        w = np.empty((self.m, self.nv), dtype=np.float64)
+        _lib.check(sess.lib.lcx_get_w(sess.h, w.ctypes.data_as(C.c_void_p), self.nv), "lcx_get_w")
+        return w
+
+    def _update_ns(self, rec):
+        """Host control flow of _update_ns (:290-334).  Returns False when the reference would hand
+        back `False` moments (step too small right after a uj >= 1 rejection)."""
+        sess = self._sess
+        lib = sess.lib
+        tcv, muj, tang = C.c_double(), C.c_double(), C.c_double()
+        _lib.check(lib.lcx_direction_ns(sess.h, float(self.eps), C.byref(tang)), "lcx_direction_ns")
+        tangent = tang.value
+        rec.update(tangent=tangent, eta=0.0, trials=0, quick_fails=0)
+        if tangent >= 0:  # :306-311
+            print('Warning: covariance is nearly singular and this causes a loss of numerical precision.'
+                  'For this reason, we can no longer find an update that increases the objective. '
+                  'Hopefully this is a good solution. If not, this is caused by having many variables that are '
+                  'near duplicates. You could try again with the duplicates removed to look for other structure.')
+            return True
+        tc_now = self.tc
+        eta = 1.
+        last_rc = None
+        while True:
+            if eta < min(self.tol, 1e-10):  # :316-319
+                if self.verbose:
+                    print('Warning: step size becoming too small')
+                break
+            rc = _lib.check(lib.lcx_trial_ns(sess.h, float(self.eps), eta, int(self.exact_trials), C.byref(tcv),
+                                             C.byref(muj)), "lcx_trial_ns")
+            last_rc = rc
+            rec["trials"] += 1
+            if rc == _lib.QUICK_FAIL:  # TEST 1 (:322-326)
+                rec["quick_fails"] += 1
+                eta *= 0.5
+                if self.verbose > 1:
+                    print('back:{:.7f}'.format(eta))
+                continue
+            if not (-tcv.value <= -tc_now + 0.1 * eta * tangent):  # TEST 2, first Wolfe condition (:327-332)
+                eta *= 0.5
+                if self.verbose > 1:
+                    print('wolfe1:{:.7f}'.format(eta))
+                continue
+            break
+        rec["eta"] = eta
+        if last_rc is None or last_rc == _lib.QUICK_FAIL:
+            return False
+        _lib.check(lib.lcx_accept_trial(sess.h), "lcx_accept_trial")
+        self.moments = {"TC": tcv.value}
+        return True
+
+    # ------------------------------------------------------------------------------------------
+    # moments export
+    # ------------------------------------------------------------------------------------------
+    def _full_moments(self):
+        """`_calculate_moments(x, ws, quick=False)` from X~, then pull every key to the host."""
+        sess = self._sess
+        lib = sess.lib
+        tcv, muj, a, b = (C.c_double() for _ in range(4))
+        if self.discourage_overlap:
+            _lib.check(lib.lcx_moments_ns(sess.h, float(self.eps), 0, C.byref(tcv), C.byref(muj)), "lcx_moments_ns")
+            _lib.check(lib.lcx_details_ns(sess.h, C.byref(a), C.byref(b)), "lcx_details_ns")
+        else:
+            _lib.check(lib.lcx_moments_syn(sess.h, C.byref(tcv), C.byref(b)), "lcx_moments_syn")
+        self.moments = self._export_moments(sess, tcv.value)
+
+    def _export_moments(self, sess, tc):
+        L = _lib
+        m = {}
+        sc = sess.host(L.A_SCALARS, squeeze=True)
+        if self.discourage_overlap:  # key set of _calculate_moments_ns (:236-288)
+            m["uj"] = sess.host(L.A_UJ, squeeze=True)
+            m["rho"] = sess.host(L.A_RHO)
+            m["ry"] = sess.host(L.A_RY)
+            m["Y_j^2"] = sess.host(L.A_YJ2, squeeze=True)
+            m["invrho"] = sess.host(L.A_INVRHO)
+            m["rhoinvrho"] = sess.host(L.A_RHOINVRHO)
+            m["Qij"] = sess.host(L.A_QIJ)
+            m["Si"] = sess.host(L.A_SI, squeeze=True)
+            m["Qi-Si^2"] = sess.host(L.A_QISI2, squeeze=True)
+            m["TC"] = tc
+            m["MI"] = sess.host(L.A_MI)
+            m["X_i Y_j"] = np.ascontiguousarray(sess.host(L.A_XY).T)
+            m["X_i Z_j"] = np.ascontiguousarray(sess.host(L.A_XZ).T)
+            m["X_i^2 | Y"] = sess.host(L.A_X2Y, squeeze=True)
+            m["I(Y_j ; X)"] = sess.host(L.A_IYX, squeeze=True)
+            m["I(X_i ; Y)"] = sess.host(L.A_IXY, squeeze=True)
+            m["TCs"] = sess.host(L.A_TCS, squeeze=True)
+            m["TC_no_overlap"] = float(sc[4])
+            m["TC_direct"] = sess.host(L.A_TCDIRECT, squeeze=True)
+            m["additivity"] = float(sc[6])
+        else:  # key set of _calculate_moments_syn (:336-373)
+            m["X_i Y_j"] = np.ascontiguousarray(sess.host(L.A_XY).T)
+            m["cy"] = sess.host(L.A_CY)
+            m["Y_j^2"] = sess.host(L.A_YJ2, squeeze=True)
+            m["ry"] = sess.host(L.A_RY)
+            m["rho"] = sess.host(L.A_RHO)
+            m["invrho"] = sess.host(L.A_INVRHO)
+            m["rhoinvrho"] = sess.host(L.A_RHOINVRHO)
+            m["Qij"] = sess.host(L.A_QIJ)
+            m["Qi"] = sess.host(L.A_QISI2, squeeze=True)
+            m["Si"] = sess.host(L.A_SI, squeeze=True)
+            m["MI"] = sess.host(L.A_MI)
+            m["X_i Z_j"] = np.ascontiguousarray(sess.host(L.A_XZ).T)
+            m["X_i^2 | Y"] = sess.host(L.A_X2Y, squeeze=True)
+            m["TCs"] = sess.host(L.A_TCS, squeeze=True)
+            m["additivity"] = float(sc[6])
+            m["TC"] = tc
+        return m
+
+    # ------------------------------------------------------------------------------------------
+    # transform / invert / predict / get_covariance (:386-395, :431-455)
+    # ------------------------------------------------------------------------------------------
+    def transform(self, x, details=False):
+        """Y = preprocess(x) . ws^T (:386-395).  Returns an (N, m) float64 ndarray; with
+        `details=True` also the full moments of `x` under the fitted weights."""
+        torch = _torch()
+        sess = self._session()
+        lib = sess.lib
+        xt = self.preprocess(x)
+        ns, nv = xt.shape[0], int(np.shape(x)[1])
+        assert self.nv == nv, "Incorrect number of variables in input, %d instead of %d" % (nv, self.nv)
+        w = np.ascontiguousarray(self.ws, dtype=np.float64)
+        ld = lib.lcx_ld(nv)
+        wd = torch.zeros((self.m, ld), dtype=torch.float64, device=sess.device)
+        wd[:, :nv].copy_(torch.from_numpy(w))
+        ldy = lib.lcx_ldy(self.m)
+        y = torch.empty((ns, ldy), dtype=torch.float64, device=sess.device)
+        _lib.check(lib.lcx_project(sess.h, xt.data_ptr(), ns, nv, xt.stride(0), wd.data_ptr(), ld, self.m, y.data_ptr(),
+                                   ldy, None, None, 0), "lcx_project")
+        y_host = y[:, :self.m].cpu().numpy().copy()
+        if details:
+            other = _DeviceSession(_lib.PRECISION_FP64 if self.precision == 'fp64' else _lib.PRECISION_FAST, self._device)
+            red = self._reducer()
+            other.bind(xt, int(red.sum_scalar(ns)), nv, self.m, red)
+            _lib.check(lib.lcx_set_w(other.h, w.ctypes.data_as(C.c_void_p), nv), "lcx_set_w")
+            tcv, muj, a, b = (C.c_double() for _ in range(4))
+            if self.discourage_overlap:
+                _lib.check(lib.lcx_moments_ns(other.h, float(self.eps), 0, C.byref(tcv), C.byref(muj)))
+                _lib.check(lib.lcx_details_ns(other.h, C.byref(a), C.byref(b)))
+            else:
+                _lib.check(lib.lcx_moments_syn(other.h, C.byref(tcv), C.byref(b)))
+            moments = self._export_moments(other, tcv.value)
+            other.close()
+            return y_host, moments
+        return y_host
+
+    def invert(self, x):
+        """Undo the preprocessing (:431-438); O(N n) host arithmetic on user-supplied arrays."""
+        if self.gaussianize == 'standard':
+            return self.theta[1] * x + self.theta[0]
+        if self.gaussianize == 'outliers':
+            core = np.clip(x, -4, 4)
+            return self.theta[1] * (core + np.arctanh(np.clip(x - core, -1 + 1e-10, 1 - 1e-10))) + self.theta[0]
+        return x
+
+    def predict(self, y):
+        return self.invert(np.dot(self.moments["X_i Z_j"], np.asarray(y).T).T)  # :440-441
+
+    def get_covariance(self, block_rows=4096):
+        """n x n covariance estimate (:443-455), computed on the device in row blocks."""
+        torch = _torch()
+        sess = self._session()
+        lib = sess.lib
+        if sess.ws is None:
+            raise _lib.LcxError("get_covariance needs the fitted device state (call fit in this process)")
+        n = self.nv
+        if self.theta is None:
+            raise ValueError("get_covariance needs theta (gaussianize='none' has none, like the reference)")
+        sd = torch.as_tensor(np.asarray(self.theta[1], dtype=np.float64), device=sess.device)
+        ldc = lib.lcx_ld(n)
+        block_rows = max(2, min(block_rows, n + (n % 2)))
+        block_rows -= block_rows % 2
+        buf = torch.empty((block_rows, ldc), dtype=torch.float64, device=sess.device)
+        out = np.empty((n, n), dtype=np.float64)
+        for r0 in range(0, n, block_rows):
+            rows = min(block_rows, n - r0)
+            _lib.check(lib.lcx_get_covariance(sess.h, int(not self.discourage_overlap), float(self.eps), sd.data_ptr(),
+                                              r0, rows, buf.data_ptr(), ldc), "lcx_get_covariance")
+            out[r0:r0 + rows] = buf[:rows, :n].cpu().numpy()
+        return out

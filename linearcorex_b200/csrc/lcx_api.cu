@@ -1,0 +1,907 @@
+// C ABI of liblcx_b200.so -- see include/lcx_b200.h for the contract and the reference lines each
+// entry point replaces.  Host orchestration only; the arithmetic lives in dgemm_mma.cuh,
+// corex_kernels.cuh and preprocess_kernels.cuh.
+#include "../../include/lcx_b200.h"
+
+#include <math.h>
+
+#include "common.cuh"
+#include "corex_kernels.cuh"
+#include "dgemm_mma.cuh"
+#include "preprocess_kernels.cuh"
+
+namespace lcx {
+thread_local char g_err[512] = "";
+constexpr int kSMs = 148;  // B200; plans (and therefore workspace sizes) are fixed for this part
+constexpr int kMaxSplitsX = 32;
+constexpr int kMaxSplitsSmall = 148;
+
+__global__ void axpy_kernel(const double* __restrict__ W, const double* __restrict__ U, double eta, double* __restrict__ W2,
+                            int m, int n, long long ld) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y;
+    if (i < n && j < m) W2[(long long)j * ld + i] = W[(long long)j * ld + i] + eta * U[(long long)j * ld + i];
+}
+
+// out = c1 * D + e2 * u     (_sig, linearcorex.py:212)
+__global__ void sig_finish_kernel(const double* __restrict__ D, const double* __restrict__ u, double c1, double e2,
+                                  double* __restrict__ out, int m, int n, long long ld) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y;
+    if (i < n && j < m) out[(long long)j * ld + i] = c1 * D[(long long)j * ld + i] + e2 * u[(long long)j * ld + i];
+}
+}  // namespace lcx
+
+using namespace lcx;
+
+// internal (non-exported) workspace slots appended after the public enum
+enum {
+    I_T = LCX_A_COUNT,  // m x ld   rinv/(1+Qi-Si^2), also z of get_covariance and R of _update_syn
+    I_PART,             // split-K partials
+    I_COLSQ,            // K1 per-CTA column-sum-of-squares partials
+    I_SPART,            // scalar partials
+    I_W2,               // m   sum_i W^2
+    I_BJ,               // m
+    I_F,                // m   row scale factors
+    I_UJDIAG,           // m   diag(W rho^T)
+    I_ROWMI,            // m
+    I_SQRTY,            // m
+    I_RYINV,            // m x ldm
+    I_AUG,              // m x 2m
+    I_STATUS,           // 2 doubles (int status of the inverse)
+    I_COUNT
+};
+
+struct Slot {
+    long long off, rows, cols, ld;
+};
+
+struct Layout {
+    Slot slot[I_COUNT][2];
+    long long total;
+    long long ld, ldm, ldy;
+    GemmPlan plan_k1, plan_k2, plan_mm, plan_mn;  // K1, K2, (m x m over n), (m x n over m)
+    int nstrips;
+};
+
+static long long align16(long long v) { return round_up(v, 16); }
+
+static Layout make_layout(long long Nl, int n, int m) {
+    Layout L;
+    memset(&L, 0, sizeof(L));
+    L.ld = round_up(n, 16);
+    L.ldm = round_up(m, 16);
+    L.ldy = round_up(m, 8);
+    L.plan_k1 = plan_gemm((int)Nl, m, n, kSMs, 1, false);
+    L.plan_k2 = plan_gemm(n, m, (int)Nl, kSMs, kMaxSplitsX, true);
+    L.plan_mm = plan_gemm(m, m, n, kSMs, kMaxSplitsSmall, true);
+    L.plan_mn = plan_gemm(m, n, m, kSMs, 1, false);
+    L.nstrips = cdiv(n, kStripCols);
+    long long cur = 0;
+    auto put = [&](int id, int set, long long rows, long long cols, long long ld) {
+        L.slot[id][set] = Slot{cur, rows, cols, ld};
+        cur = align16(cur + rows * ld);
+    };
+    const long long mn = m;
+    for (int set = 0; set < 2; ++set) {
+        put(LCX_A_W, set, mn, n, L.ld);
+        put(LCX_A_RHO, set, mn, n, L.ld);
+        put(LCX_A_INVRHO, set, mn, n, L.ld);
+        put(LCX_A_RHOINVRHO, set, mn, n, L.ld);
+        put(LCX_A_QIJ, set, mn, n, L.ld);
+        put(LCX_A_SI, set, 1, n, L.ld);
+        put(LCX_A_QISI2, set, 1, n, L.ld);
+        put(LCX_A_RY, set, mn, m, L.ldm);
+        put(LCX_A_UJ, set, 1, m, L.ldm);
+    }
+    auto put1 = [&](int id, long long rows, long long cols, long long ld) {
+        put(id, 0, rows, cols, ld);
+        L.slot[id][1] = L.slot[id][0];
+    };
+    put1(LCX_A_GRAD, mn, n, L.ld);
+    put1(LCX_A_UPDATE, mn, n, L.ld);
+    put1(LCX_A_RDIR, mn, n, L.ld);
+    put1(LCX_A_D, mn + cdiv(m, L.ld), n, L.ld);  // D (m x ld) immediately followed by s (m values)
+    put1(LCX_A_MI, mn, n, L.ld);
+    put1(LCX_A_XZ, mn, n, L.ld);
+    put1(LCX_A_XY, mn, n, L.ld);
+    put1(LCX_A_X2Y, 1, n, L.ld);
+    put1(LCX_A_IXY, 1, n, L.ld);
+    put1(LCX_A_YJ2, 1, m, L.ldm);
+    put1(LCX_A_IYX, 1, m, L.ldm);
+    put1(LCX_A_TCS, 1, m, L.ldm);
+    put1(LCX_A_TCDIRECT, 1, m, L.ldm);
+    put1(LCX_A_CY, mn, m, L.ldm);
+    put1(LCX_A_Y, Nl, m, L.ldy);
+    put1(LCX_A_SCALARS, 1, 16, 16);
+    put1(I_T, mn, n, L.ld);
+    long long part = 0;
+    if (L.plan_k2.splits > 1) part = max(part, (long long)L.plan_k2.splits * mn * L.ld);
+    if (L.plan_mm.splits > 1) part = max(part, (long long)L.plan_mm.splits * mn * L.ldm);
+    put1(I_PART, 1, max(part, 16LL), max(part, 16LL));
+    put1(I_COLSQ, L.plan_k1.grid.x, m, L.ldy);
+    const long long spart = max(3LL * L.nstrips, (long long)m * cdiv(n, 256));
+    put1(I_SPART, 1, spart, spart);
+    put1(I_W2, 1, m, L.ldm);
+    put1(I_BJ, 1, m, L.ldm);
+    put1(I_F, 1, m, L.ldm);
+    put1(I_UJDIAG, 1, m, L.ldm);
+    put1(I_ROWMI, 1, m, L.ldm);
+    put1(I_SQRTY, 1, m, L.ldm);
+    put1(I_RYINV, mn, m, L.ldm);
+    put1(I_AUG, mn, 2 * mn, 2 * mn);
+    put1(I_STATUS, 1, 2, 2);
+    L.total = cur;
+    return L;
+}
+
+struct lcx_session {
+    int device, precision;
+    cudaStream_t stream;
+    lcx_allreduce_fn hook;
+    void* hook_user;
+    long long launches;
+    double* mailbox;  // pinned host, 16 doubles
+    bool bound;
+    const double* xt;
+    long long Nl, Nt, ldx;
+    int n, m;
+    double* ws;
+    Layout L;
+    int cur;  // which physical set is "set 0" (current)
+
+    double* ptr(int id, int set = 0) const {
+        const int phys = (id <= LCX_A_UJ) ? (set ^ cur) : 0;
+        return ws + L.slot[id][phys].off;
+    }
+    long long off(int id, int set = 0) const {
+        const int phys = (id <= LCX_A_UJ) ? (set ^ cur) : 0;
+        return L.slot[id][phys].off;
+    }
+};
+
+#define S_REQUIRE_BOUND(s)                                                        \
+    do {                                                                          \
+        if (!(s)) return fail(LCX_ERR_ARG, "session", "null session");            \
+        if (!(s)->bound) return fail(LCX_ERR_STATE, "session", "no bound problem"); \
+        LCX_CUDA(cudaSetDevice((s)->device));                                     \
+    } while (0)
+
+#define LAUNCHED(s) ((s)->launches++)
+
+static dim3 grid_mn(int m, int n) { return dim3(cdiv(n, 256), m); }
+
+// ---- lifecycle ---------------------------------------------------------------------------------
+extern "C" int lcx_version(void) { return 100; }
+extern "C" const char* lcx_last_error(void) { return g_err; }
+
+extern "C" int lcx_session_create(lcx_session** out, int device, int precision) {
+    LCX_REQUIRE(out != nullptr, "out is null");
+    LCX_REQUIRE(precision == LCX_PRECISION_FP64 || precision == LCX_PRECISION_FAST, "unknown precision mode");
+    LCX_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    LCX_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) return fail(LCX_ERR_STATE, "lcx_session_create", "this library is built for sm_100a (B200) only");
+    lcx_session* s = new lcx_session();
+    memset(s, 0, sizeof(*s));
+    s->device = device;
+    s->precision = precision;
+    s->stream = 0;
+    LCX_CUDA(cudaHostAlloc((void**)&s->mailbox, 16 * sizeof(double), cudaHostAllocDefault));
+    *out = s;
+    return 0;
+}
+
+extern "C" int lcx_session_destroy(lcx_session* s) {
+    if (!s) return 0;
+    if (s->mailbox) cudaFreeHost(s->mailbox);
+    delete s;
+    return 0;
+}
+
+extern "C" int lcx_set_stream(lcx_session* s, void* cuda_stream) {
+    LCX_REQUIRE(s != nullptr, "null session");
+    s->stream = (cudaStream_t)cuda_stream;
+    return 0;
+}
+
+extern "C" int lcx_set_allreduce(lcx_session* s, lcx_allreduce_fn fn, void* user) {
+    LCX_REQUIRE(s != nullptr, "null session");
+    s->hook = fn;
+    s->hook_user = user;
+    return 0;
+}
+
+extern "C" int lcx_launch_count(lcx_session* s, long long* launches) {
+    LCX_REQUIRE(s != nullptr && launches != nullptr, "null argument");
+    *launches = s->launches;
+    return 0;
+}
+
+// ---- layout ------------------------------------------------------------------------------------
+extern "C" long long lcx_ld(int n_vars) { return round_up(n_vars, 16); }
+extern "C" long long lcx_ldy(int n_factors) { return round_up(n_factors, 8); }
+
+extern "C" long long lcx_workspace_doubles(long long n_rows_local, int n_vars, int n_factors) {
+    if (n_rows_local < 0 || n_vars <= 0 || n_factors <= 0) return -1;
+    return make_layout(n_rows_local, n_vars, n_factors).total;
+}
+
+extern "C" int lcx_bind(lcx_session* s, const double* xt, long long n_rows_local, long long n_rows_total, int n_vars,
+                        long long ldx, int n_factors, double* workspace, long long workspace_doubles) {
+    LCX_REQUIRE(s != nullptr, "null session");
+    LCX_REQUIRE(xt != nullptr && workspace != nullptr, "null device pointer");
+    LCX_REQUIRE(n_rows_local > 0 && n_rows_local < (1LL << 31) && n_rows_total >= n_rows_local, "bad row counts");
+    LCX_REQUIRE(n_vars > 0 && n_factors > 0, "bad shape");
+    LCX_REQUIRE(ldx >= n_vars && ldx % 2 == 0, "ldx must be even and >= n_vars");
+    LCX_REQUIRE(((uintptr_t)xt % 16 == 0) && ((uintptr_t)workspace % 128 == 0), "misaligned device pointer");
+    Layout L = make_layout(n_rows_local, n_vars, n_factors);
+    LCX_REQUIRE(workspace_doubles >= L.total, "workspace too small (see lcx_workspace_doubles)");
+    LCX_CUDA(cudaSetDevice(s->device));
+    s->xt = xt;
+    s->Nl = n_rows_local;
+    s->Nt = n_rows_total;
+    s->ldx = ldx;
+    s->n = n_vars;
+    s->m = n_factors;
+    s->ws = workspace;
+    s->L = L;
+    s->cur = 0;
+    s->bound = true;
+    // everything except Y starts at zero so padding never carries NaNs into an all-reduce
+    const long long y_off = L.slot[LCX_A_Y][0].off;
+    LCX_CUDA(cudaMemsetAsync(workspace, 0, (size_t)y_off * sizeof(double), s->stream));
+    const long long y_end = align16(y_off + n_rows_local * L.ldy);
+    LCX_CUDA(cudaMemsetAsync(workspace + y_end, 0, (size_t)(L.total - y_end) * sizeof(double), s->stream));
+    return 0;
+}
+
+extern "C" int lcx_array_info(lcx_session* s, int array_id, int set, long long* offset, long long* rows, long long* cols,
+                              long long* ld) {
+    S_REQUIRE_BOUND(s);
+    LCX_REQUIRE(array_id >= 0 && array_id < LCX_A_COUNT && (set == 0 || set == 1), "bad array id / set");
+    const int phys = (array_id <= LCX_A_UJ) ? (set ^ s->cur) : 0;
+    const Slot& sl = s->L.slot[array_id][phys];
+    if (offset) *offset = sl.off;
+    if (rows) *rows = (array_id == LCX_A_D) ? s->m : sl.rows;
+    if (cols) *cols = sl.cols;
+    if (ld) *ld = sl.ld;
+    return 0;
+}
+
+// ---- preprocessing -----------------------------------------------------------------------------
+static const int kSlabRows = 4096;
+
+extern "C" long long lcx_colstats_scratch_doubles(long long n_rows, int n_vars) {
+    return 2LL * cdiv(n_rows, kSlabRows) * round_up(n_vars, 16) + 32;
+}
+
+template <typename T>
+static int colstats_sum_t(lcx_session* s, const T* x, long long N, int n, long long ldx, int has_marker, double marker,
+                          double* sum, double* cnt, double* scratch) {
+    const int slabs = cdiv(N, kSlabRows);
+    const long long ldp = round_up(n, 16);
+    double* ps = scratch;
+    double* pc = scratch + (long long)slabs * ldp;
+    dim3 grid(cdiv(n, 32), slabs), block(32, 8);
+    colstats_sum_kernel<T><<<grid, block, 0, s->stream>>>(x, N, n, ldx, kSlabRows, has_marker, marker, marker != marker, ps,
+                                                        pc, ldp);
+    LAUNCHED(s);
+    combine_slabs_kernel<<<cdiv(n, 256), 256, 0, s->stream>>>(ps, slabs, ldp, sum, n);
+    LAUNCHED(s);
+    combine_slabs_kernel<<<cdiv(n, 256), 256, 0, s->stream>>>(pc, slabs, ldp, cnt, n);
+    LAUNCHED(s);
+    LCX_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int lcx_colstats_sum(lcx_session* s, const void* x, int dtype, long long n_rows, int n_vars, long long ldx,
+                                int has_marker, double marker, double* sum, double* cnt, double* scratch,
+                                long long scratch_doubles) {
+    LCX_REQUIRE(s && x && sum && cnt && scratch, "null argument");
+    LCX_REQUIRE(n_rows > 0 && n_vars > 0 && ldx >= n_vars, "bad shape");
+    LCX_REQUIRE(scratch_doubles >= lcx_colstats_scratch_doubles(n_rows, n_vars), "scratch too small");
+    LCX_CUDA(cudaSetDevice(s->device));
+    if (dtype == LCX_F32) return colstats_sum_t<float>(s, (const float*)x, n_rows, n_vars, ldx, has_marker, marker, sum, cnt, scratch);
+    if (dtype == LCX_F64) return colstats_sum_t<double>(s, (const double*)x, n_rows, n_vars, ldx, has_marker, marker, sum, cnt, scratch);
+    return fail(LCX_ERR_ARG, "lcx_colstats_sum", "unknown dtype");
+}
+
+extern "C" int lcx_colstats_mean(lcx_session* s, const double* sum, const double* cnt, double* mean, int n_vars) {
+    LCX_REQUIRE(s && sum && cnt && mean && n_vars > 0, "bad argument");
+    LCX_CUDA(cudaSetDevice(s->device));
+    finish_mean_kernel<<<cdiv(n_vars, 256), 256, 0, s->stream>>>(sum, cnt, mean, n_vars);
+    LAUNCHED(s);
+    LCX_CUDA(cudaGetLastError());
+    return 0;
+}
+
+template <typename T>
+static int colstats_sqdev_t(lcx_session* s, const T* x, long long N, int n, long long ldx, int has_marker, double marker,
+                            const double* mean, double* sq, double* scratch) {
+    const int slabs = cdiv(N, kSlabRows);
+    const long long ldp = round_up(n, 16);
+    dim3 grid(cdiv(n, 32), slabs), block(32, 8);
+    colstats_sqdev_kernel<T><<<grid, block, 0, s->stream>>>(x, N, n, ldx, kSlabRows, has_marker, marker, marker != marker,
+                                                          mean, scratch, ldp);
+    LAUNCHED(s);
+    combine_slabs_kernel<<<cdiv(n, 256), 256, 0, s->stream>>>(scratch, slabs, ldp, sq, n);
+    LAUNCHED(s);
+    LCX_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int lcx_colstats_sqdev(lcx_session* s, const void* x, int dtype, long long n_rows, int n_vars, long long ldx,
+                                  int has_marker, double marker, const double* mean, double* sq, double* scratch,
+                                  long long scratch_doubles) {
+    LCX_REQUIRE(s && x && mean && sq && scratch, "null argument");
+    LCX_REQUIRE(n_rows > 0 && n_vars > 0 && ldx >= n_vars, "bad shape");
+    LCX_REQUIRE(scratch_doubles >= lcx_colstats_scratch_doubles(n_rows, n_vars), "scratch too small");
+    LCX_CUDA(cudaSetDevice(s->device));
+    if (dtype == LCX_F32) return colstats_sqdev_t<float>(s, (const float*)x, n_rows, n_vars, ldx, has_marker, marker, mean, sq, scratch);
+    if (dtype == LCX_F64) return colstats_sqdev_t<double>(s, (const double*)x, n_rows, n_vars, ldx, has_marker, marker, mean, sq, scratch);
+    return fail(LCX_ERR_ARG, "lcx_colstats_sqdev", "unknown dtype");
+}
+
+extern "C" int lcx_colstats_std(lcx_session* s, const double* sq, const double* cnt, double n_rows_total, int use_nobs,
+                                double* sd, int n_vars) {
+    LCX_REQUIRE(s && sq && cnt && sd && n_vars > 0, "bad argument");
+    LCX_CUDA(cudaSetDevice(s->device));
+    finish_std_kernel<<<cdiv(n_vars, 256), 256, 0, s->stream>>>(sq, cnt, n_rows_total, use_nobs, sd, n_vars);
+    LAUNCHED(s);
+    LCX_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int lcx_standardize(lcx_session* s, const void* x, int dtype, long long n_rows, int n_vars, long long ldx,
+                               int has_marker, double marker, int gauss_mode, const double* impute, const double* mean,
+                               const double* sd, double* out, long long ldo) {
+    LCX_REQUIRE(s && x && out, "null argument");
+    LCX_REQUIRE(gauss_mode == LCX_GAUSS_NONE || (mean && sd), "mean/std required");
+    LCX_REQUIRE(has_marker == 0 || impute != nullptr, "imputation means required when a missing marker is set");
+    LCX_REQUIRE(n_rows > 0 && n_vars > 0 && ldx >= n_vars && ldo >= n_vars, "bad shape");
+    LCX_CUDA(cudaSetDevice(s->device));
+    dim3 grid((unsigned)n_rows, cdiv(ldo, 256));
+    const int nan_marker = marker != marker;
+    if (dtype == LCX_F32)
+        standardize_kernel<float><<<grid, 256, 0, s->stream>>>((const float*)x, n_rows, n_vars, ldx, has_marker, marker,
+                                                             nan_marker, gauss_mode, impute, mean, sd, out, ldo);
+    else if (dtype == LCX_F64)
+        standardize_kernel<double><<<grid, 256, 0, s->stream>>>((const double*)x, n_rows, n_vars, ldx, has_marker, marker,
+                                                              nan_marker, gauss_mode, impute, mean, sd, out, ldo);
+    else
+        return fail(LCX_ERR_ARG, "lcx_standardize", "unknown dtype");
+    LAUNCHED(s);
+    LCX_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ---- GEMM plumbing -----------------------------------------------------------------------------
+static int run_gemm(lcx_session* s, GemmLayout lay, const GemmPlan& pl, GemmArgs a, double* part, long long out_count) {
+    // out_count = number of doubles of one full output (rows * ldc) -- the split stride
+    if (pl.splits > 1) {
+        double* final_c = a.C;
+        const double* cadd = a.Cadd;
+        LCX_REQUIRE(cadd == nullptr, "split-K with Cadd is not supported");
+        a.C = part;
+        a.c_split_stride = out_count;
+        LCX_TRY(launch_gemm(lay, pl, a, s->stream));
+        LAUNCHED(s);
+        LCX_TRY(launch_reduce_splits(part, pl.splits, out_count, final_c, out_count, s->stream));
+        LAUNCHED(s);
+    } else {
+        a.c_split_stride = 0;
+        LCX_TRY(launch_gemm(lay, pl, a, s->stream));
+        LAUNCHED(s);
+    }
+    return 0;
+}
+
+// Y = X~ A^T (+ colsq into D's tail), D = X~^T Y summed over splits, then the rank all-reduce.
+static int xpair(lcx_session* s, const double* A, bool want_colsq) {
+    const Layout& L = s->L;
+    const int m = s->m, n = s->n;
+    double* Y = s->ptr(LCX_A_Y);
+    double* D = s->ptr(LCX_A_D);
+    double* svec = D + (long long)m * L.ld;
+    {   // K1
+        GemmArgs a;
+        memset(&a, 0, sizeof(a));
+        a.A = s->xt; a.B = A; a.C = Y;
+        a.M = (int)s->Nl; a.N = m; a.K = n;
+        a.lda = s->ldx; a.ldb = L.ld; a.ldc = L.ldy;
+        a.colsq_part = want_colsq ? s->ptr(I_COLSQ) : nullptr;
+        a.ld_colsq = (int)L.ldy;
+        LCX_TRY(run_gemm(s, kLayoutKK, L.plan_k1, a, nullptr, 0));
+        if (want_colsq) {
+            reduce_colsq_kernel<<<cdiv(m, 128), 128, 0, s->stream>>>(s->ptr(I_COLSQ), L.plan_k1.grid.x, (int)L.ldy, svec, m);
+            LAUNCHED(s);
+        }
+    }
+    {   // K2: (X~^T Y)^T written factor-major
+        GemmArgs a;
+        memset(&a, 0, sizeof(a));
+        a.A = s->xt; a.B = Y; a.C = D;
+        a.M = n; a.N = m; a.K = (int)s->Nl;
+        a.lda = s->ldx; a.ldb = L.ldy; a.ldc = L.ld;
+        a.trans_out = 1;
+        LCX_TRY(run_gemm(s, kLayoutMN, L.plan_k2, a, s->ptr(I_PART), (long long)m * L.ld));
+    }
+    LCX_CUDA(cudaGetLastError());
+    if (s->hook) {
+        const int rc = s->hook(s->hook_user, s->off(LCX_A_D), (long long)m * L.ld + (want_colsq ? m : 0));
+        if (rc != 0) return fail(LCX_ERR_STATE, "allreduce hook", "hook reported failure");
+    }
+    return 0;
+}
+
+static int read_mailbox(lcx_session* s) {
+    LCX_CUDA(cudaMemcpyAsync(s->mailbox, s->ptr(LCX_A_SCALARS), 16 * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    LCX_CUDA(cudaStreamSynchronize(s->stream));
+    return 0;
+}
+
+// ry, Qij, Qi-Si^2, TC, uj for `set`, given rho/invrho/rinv/Si (and W) of that set.
+static int moments_tail(lcx_session* s, int set, double c1, double e2, int uj_mode) {
+    const Layout& L = s->L;
+    const int m = s->m, n = s->n;
+    double* W = s->ptr(LCX_A_W, set);
+    double* rho = s->ptr(LCX_A_RHO, set);
+    double* rinv = s->ptr(LCX_A_RHOINVRHO, set);
+    double* ry = s->ptr(LCX_A_RY, set);
+    double* Qij = s->ptr(LCX_A_QIJ, set);
+    {   // ry = W rho^T  (:261), diag -> 1 (:263); the diagonal before the fill is uj by linearity
+        GemmArgs a;
+        memset(&a, 0, sizeof(a));
+        a.A = W; a.B = rho; a.C = ry;
+        a.M = m; a.N = m; a.K = n;
+        a.lda = L.ld; a.ldb = L.ld; a.ldc = L.ldm;
+        LCX_TRY(run_gemm(s, kLayoutKK, L.plan_mm, a, s->ptr(I_PART), (long long)m * L.ldm));
+        diag_fix_kernel<<<cdiv(m, 128), 128, 0, s->stream>>>(ry, L.ldm, m, 1.0, s->ptr(I_UJDIAG));
+        LAUNCHED(s);
+    }
+    {   // Qij = ry rinv  (:266)
+        GemmArgs a;
+        memset(&a, 0, sizeof(a));
+        a.A = ry; a.B = rinv; a.C = Qij;
+        a.M = m; a.N = n; a.K = m;
+        a.lda = L.ldm; a.ldb = L.ld; a.ldc = L.ld;
+        LCX_TRY(run_gemm(s, kLayoutKN, L.plan_mn, a, nullptr, 0));
+    }
+    moments_stage2_kernel<<<L.nstrips, dim3(kStripCols, kStripRows), 0, s->stream>>>(
+        rho, rinv, Qij, s->ptr(LCX_A_SI, set), s->ptr(LCX_A_QISI2, set), s->ptr(I_SPART), m, n, L.ld);
+    LAUNCHED(s);
+    moments_finish_kernel<<<1, 256, 0, s->stream>>>(s->ptr(I_SPART), L.nstrips, uj_mode,
+                                                   s->ptr(LCX_A_D) + (long long)m * L.ld, s->ptr(I_W2), s->ptr(I_UJDIAG), c1,
+                                                   e2, s->ptr(LCX_A_UJ, set), m, s->ptr(LCX_A_SCALARS));
+    LAUNCHED(s);
+    LCX_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// full from-X moment evaluation of W(set) into `set`
+static int moments_from_x(lcx_session* s, int set, double eps) {
+    const Layout& L = s->L;
+    const int m = s->m, n = s->n;
+    const double c1 = (1.0 - eps * eps) / (double)s->Nt, e2 = eps * eps;
+    double* W = s->ptr(LCX_A_W, set);
+    LCX_TRY(xpair(s, W, true));
+    row_dot_kernel<<<m, 256, 0, s->stream>>>(W, W, s->ptr(I_W2), n, L.ld);
+    LAUNCHED(s);
+    moments_stage1_kernel<true><<<L.nstrips, dim3(kStripCols, kStripRows), 0, s->stream>>>(
+        s->ptr(LCX_A_D), W, nullptr, nullptr, nullptr, 0.0, c1, e2, nullptr, s->ptr(LCX_A_RHO, set),
+        s->ptr(LCX_A_INVRHO, set), s->ptr(LCX_A_RHOINVRHO, set), s->ptr(LCX_A_SI, set), m, n, L.ld);
+    LAUNCHED(s);
+    return moments_tail(s, set, c1, e2, 0);
+}
+
+// ---- exported steps ----------------------------------------------------------------------------
+extern "C" long long lcx_project_scratch_doubles(long long n_rows, int n_factors) {
+    return (long long)cdiv(n_rows, 128) * round_up(n_factors, 8) + 16;
+}
+
+extern "C" int lcx_project(lcx_session* s, const double* xt, long long n_rows, int n_vars, long long ldx, const double* a,
+                           long long lda, int n_factors, double* y, long long ldy, double* colsq, double* scratch,
+                           long long scratch_doubles) {
+    LCX_REQUIRE(s && xt && a && y, "null argument");
+    LCX_REQUIRE(n_rows > 0 && n_rows < (1LL << 31) && n_vars > 0 && n_factors > 0, "bad shape");
+    LCX_REQUIRE(colsq == nullptr || (scratch != nullptr && scratch_doubles >= lcx_project_scratch_doubles(n_rows, n_factors)),
+                "scratch too small for the column sums");
+    LCX_CUDA(cudaSetDevice(s->device));
+    GemmPlan pl = plan_gemm((int)n_rows, n_factors, n_vars, kSMs, 1, false);
+    GemmArgs g;
+    memset(&g, 0, sizeof(g));
+    g.A = xt; g.B = a; g.C = y;
+    g.M = (int)n_rows; g.N = n_factors; g.K = n_vars;
+    g.lda = ldx; g.ldb = lda; g.ldc = ldy;
+    const int ldp = (int)round_up(n_factors, 8);
+    g.colsq_part = colsq ? scratch : nullptr;
+    g.ld_colsq = ldp;
+    LCX_TRY(launch_gemm(kLayoutKK, pl, g, s->stream));
+    LAUNCHED(s);
+    if (colsq) {
+        reduce_colsq_kernel<<<cdiv(n_factors, 128), 128, 0, s->stream>>>(scratch, pl.grid.x, ldp, colsq, n_factors);
+        LAUNCHED(s);
+    }
+    LCX_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int lcx_sig(lcx_session* s, const double* u, double eps, double* out) {
+    S_REQUIRE_BOUND(s);
+    LCX_REQUIRE(u && out, "null argument");
+    LCX_TRY(xpair(s, u, false));
+    const double c1 = (1.0 - eps * eps) / (double)s->Nt, e2 = eps * eps;
+    sig_finish_kernel<<<grid_mn(s->m, s->n), 256, 0, s->stream>>>(s->ptr(LCX_A_D), u, c1, e2, out, s->m, s->n, s->L.ld);
+    LAUNCHED(s);
+    LCX_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int lcx_set_w(lcx_session* s, const double* host_w, long long host_ld) {
+    S_REQUIRE_BOUND(s);
+    LCX_REQUIRE(host_w && host_ld >= s->n, "bad host array");
+    LCX_CUDA(cudaMemcpy2DAsync(s->ptr(LCX_A_W), s->L.ld * sizeof(double), host_w, host_ld * sizeof(double),
+                               (size_t)s->n * sizeof(double), s->m, cudaMemcpyHostToDevice, s->stream));
+    LCX_CUDA(cudaStreamSynchronize(s->stream));
+    return 0;
+}
+
+extern "C" int lcx_get_w(lcx_session* s, double* host_w, long long host_ld) {
+    S_REQUIRE_BOUND(s);
+    LCX_REQUIRE(host_w && host_ld >= s->n, "bad host array");
+    LCX_CUDA(cudaMemcpy2DAsync(host_w, host_ld * sizeof(double), s->ptr(LCX_A_W), s->L.ld * sizeof(double),
+                               (size_t)s->n * sizeof(double), s->m, cudaMemcpyDeviceToHost, s->stream));
+    LCX_CUDA(cudaStreamSynchronize(s->stream));
+    return 0;
+}
+
+extern "C" int lcx_init_scale(lcx_session* s, double eps) {
+    S_REQUIRE_BOUND(s);
+    const Layout& L = s->L;
+    const int m = s->m, n = s->n;
+    double* W = s->ptr(LCX_A_W);
+    double* svec = s->ptr(LCX_A_D) + (long long)m * L.ld;
+    LCX_TRY(lcx_project(s, s->xt, s->Nl, n, s->ldx, W, L.ld, m, s->ptr(LCX_A_Y), L.ldy, svec, s->ptr(I_COLSQ),
+                        lcx_project_scratch_doubles(s->Nl, m)));
+    if (s->hook) {
+        if (s->hook(s->hook_user, s->off(LCX_A_D) + (long long)m * L.ld, m) != 0)
+            return fail(LCX_ERR_STATE, "allreduce hook", "hook reported failure");
+    }
+    row_dot_kernel<<<m, 256, 0, s->stream>>>(W, W, s->ptr(I_W2), n, L.ld);
+    LAUNCHED(s);
+    const double c1 = (1.0 - eps * eps) / (double)s->Nt, e2 = eps * eps;
+    init_scale_kernel<<<cdiv(m, 128), 128, 0, s->stream>>>(svec, s->ptr(I_W2), c1, e2, s->ptr(I_F), m);
+    LAUNCHED(s);
+    scale_rows_kernel<<<grid_mn(m, n), 256, 0, s->stream>>>(W, s->ptr(I_F), m, n, L.ld);
+    LAUNCHED(s);
+    LCX_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int lcx_stage_rescale(lcx_session* s, double eps, double eps_prev) {
+    S_REQUIRE_BOUND(s);
+    const Layout& L = s->L;
+    const int m = s->m, n = s->n;
+    double* W = s->ptr(LCX_A_W);
+    row_dot_kernel<<<m, 256, 0, s->stream>>>(W, W, s->ptr(I_W2), n, L.ld);
+    LAUNCHED(s);
+    stage_scale_kernel<<<cdiv(m, 128), 128, 0, s->stream>>>(s->ptr(I_W2), s->ptr(LCX_A_UJ), eps, eps_prev, s->ptr(I_F), m);
+    LAUNCHED(s);
+    scale_rows_kernel<<<grid_mn(m, n), 256, 0, s->stream>>>(W, s->ptr(I_F), m, n, L.ld);
+    LAUNCHED(s);
+    LCX_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int lcx_permute_rows(lcx_session* s, const int* host_order) {
+    S_REQUIRE_BOUND(s);
+    LCX_REQUIRE(host_order != nullptr, "null order");
+    const Layout& L = s->L;
+    double* W = s->ptr(LCX_A_W);
+    double* tmp = s->ptr(LCX_A_GRAD);
+    for (int j = 0; j < s->m; ++j) {
+        LCX_REQUIRE(host_order[j] >= 0 && host_order[j] < s->m, "order out of range");
+        LCX_CUDA(cudaMemcpyAsync(tmp + (long long)j * L.ld, W + (long long)host_order[j] * L.ld, L.ld * sizeof(double),
+                                 cudaMemcpyDeviceToDevice, s->stream));
+    }
+    LCX_CUDA(cudaMemcpyAsync(W, tmp, (size_t)s->m * L.ld * sizeof(double), cudaMemcpyDeviceToDevice, s->stream));
+    return 0;
+}
+
+extern "C" int lcx_moments_ns(lcx_session* s, double eps, int check_uj, double* tc, double* max_uj) {
+    S_REQUIRE_BOUND(s);
+    LCX_TRY(moments_from_x(s, 0, eps));
+    LCX_TRY(read_mailbox(s));
+    if (tc) *tc = s->mailbox[0];
+    if (max_uj) *max_uj = s->mailbox[1];
+    return (check_uj && s->mailbox[1] >= 1.0) ? LCX_QUICK_FAIL : LCX_OK;
+}
+
+extern "C" int lcx_direction_ns(lcx_session* s, double eps, double* tangent) {
+    S_REQUIRE_BOUND(s);
+    const Layout& L = s->L;
+    const int m = s->m, n = s->n;
+    const double c1 = (1.0 - eps * eps) / (double)s->Nt, e2 = eps * eps;
+    double* W = s->ptr(LCX_A_W);
+    double* rho = s->ptr(LCX_A_RHO);
+    double* rinv = s->ptr(LCX_A_RHOINVRHO);
+    double* G = s->ptr(LCX_A_GRAD);
+    double* T = s->ptr(I_T);
+    double* H = s->ptr(I_RYINV);  // m x ldm scratch (the inverse buffer is idle outside the details path)
+    direction_stage1_kernel<<<grid_mn(m, n), 256, 0, s->stream>>>(W, rho, s->ptr(LCX_A_INVRHO), rinv, s->ptr(LCX_A_QIJ),
+                                                                s->ptr(LCX_A_SI), s->ptr(LCX_A_QISI2), s->ptr(LCX_A_UJ), T, G,
+                                                                m, n, L.ld);
+    LAUNCHED(s);
+    {   // H = T rinv^T, diag -> 0 (:294-295)
+        GemmArgs a;
+        memset(&a, 0, sizeof(a));
+        a.A = T; a.B = rinv; a.C = H;
+        a.M = m; a.N = m; a.K = n;
+        a.lda = L.ld; a.ldb = L.ld; a.ldc = L.ldm;
+        LCX_TRY(run_gemm(s, kLayoutKK, L.plan_mm, a, s->ptr(I_PART), (long long)m * L.ldm));
+        diag_fix_kernel<<<cdiv(m, 128), 128, 0, s->stream>>>(H, L.ldm, m, 0.0, nullptr);
+        LAUNCHED(s);
+    }
+    {   // grad = G0 + H W (:300), in place over G0
+        GemmArgs a;
+        memset(&a, 0, sizeof(a));
+        a.A = H; a.B = W; a.C = G; a.Cadd = G;
+        a.M = m; a.N = n; a.K = m;
+        a.lda = L.ldm; a.ldb = L.ld; a.ldc = L.ld;
+        LCX_TRY(run_gemm(s, kLayoutKN, L.plan_mn, a, nullptr, 0));
+    }
+    LCX_TRY(xpair(s, G, false));  // X~^T (X~ grad^T): the one pass over X of this iteration (:301)
+    row_dot_kernel<<<m, 256, 0, s->stream>>>(rho, G, s->ptr(I_BJ), n, L.ld);  // Bj (:302)
+    LAUNCHED(s);
+    const dim3 g2(cdiv(n, 256), m);
+    direction_stage2_kernel<<<g2, 256, 0, s->stream>>>(W, rho, G, s->ptr(LCX_A_D), s->ptr(LCX_A_UJ), s->ptr(I_BJ), c1, e2,
+                                                     s->ptr(LCX_A_UPDATE), s->ptr(LCX_A_RDIR), s->ptr(I_SPART), m, n, L.ld);
+    LAUNCHED(s);
+    sum_partials_kernel<<<1, 256, 0, s->stream>>>(s->ptr(I_SPART), (int)(g2.x * g2.y), s->ptr(LCX_A_SCALARS) + 2);
+    LAUNCHED(s);
+    LCX_CUDA(cudaGetLastError());
+    LCX_TRY(read_mailbox(s));
+    if (tangent) *tangent = s->mailbox[2];
+    return 0;
+}
+
+extern "C" int lcx_trial_ns(lcx_session* s, double eps, double eta, int exact, double* tc, double* max_uj) {
+    S_REQUIRE_BOUND(s);
+    const Layout& L = s->L;
+    const int m = s->m, n = s->n;
+    const double c1 = (1.0 - eps * eps) / (double)s->Nt, e2 = eps * eps;
+    if (exact) {
+        axpy_kernel<<<grid_mn(m, n), 256, 0, s->stream>>>(s->ptr(LCX_A_W), s->ptr(LCX_A_UPDATE), eta, s->ptr(LCX_A_W, 1), m, n,
+                                                        L.ld);
+        LAUNCHED(s);
+        LCX_TRY(moments_from_x(s, 1, eps));
+    } else {
+        moments_stage1_kernel<false><<<L.nstrips, dim3(kStripCols, kStripRows), 0, s->stream>>>(
+            nullptr, s->ptr(LCX_A_W), s->ptr(LCX_A_UPDATE), s->ptr(LCX_A_RHO), s->ptr(LCX_A_RDIR), eta, c1, e2,
+            s->ptr(LCX_A_W, 1), s->ptr(LCX_A_RHO, 1), s->ptr(LCX_A_INVRHO, 1), s->ptr(LCX_A_RHOINVRHO, 1),
+            s->ptr(LCX_A_SI, 1), m, n, L.ld);
+        LAUNCHED(s);
+        LCX_TRY(moments_tail(s, 1, c1, e2, 1));
+    }
+    LCX_TRY(read_mailbox(s));
+    if (tc) *tc = s->mailbox[0];
+    if (max_uj) *max_uj = s->mailbox[1];
+    return (s->mailbox[1] >= 1.0) ? LCX_QUICK_FAIL : LCX_OK;
+}
+
+extern "C" int lcx_accept_trial(lcx_session* s) {
+    S_REQUIRE_BOUND(s);
+    s->cur ^= 1;
+    return 0;
+}
+
+static int run_inverse(lcx_session* s, const double* a, long long lda, int m, double* out, long long ldo, double* aug,
+                       int* status) {
+    gauss_jordan_inverse_kernel<<<1, 1024, 0, s->stream>>>(a, lda, m, aug, out, ldo, status);
+    LAUNCHED(s);
+    LCX_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// shared tail of the details computations: MI, X_i^2|Y, I(X_i;Y), TCs, TC_no_overlap, TC_direct, additivity
+static int details_tail(lcx_session* s, const double* other, const double* yj2_in) {
+    const Layout& L = s->L;
+    const int m = s->m, n = s->n;
+    details_cols_kernel<<<L.nstrips, dim3(kStripCols, kStripRows), 0, s->stream>>>(
+        s->ptr(LCX_A_RHO), s->ptr(LCX_A_XZ), other, s->ptr(LCX_A_MI), s->ptr(LCX_A_X2Y), s->ptr(LCX_A_IXY), s->ptr(I_SPART),
+        m, n, L.ld);
+    LAUNCHED(s);
+    row_dot_kernel<<<m, 256, 0, s->stream>>>(s->ptr(LCX_A_MI), nullptr, s->ptr(I_ROWMI), n, L.ld);
+    LAUNCHED(s);
+    details_finish_kernel<<<1, 256, 0, s->stream>>>(s->ptr(I_SPART), L.nstrips, s->ptr(LCX_A_UJ), yj2_in, s->ptr(I_ROWMI),
+                                                   s->ptr(LCX_A_YJ2), s->ptr(LCX_A_IYX), s->ptr(LCX_A_TCS),
+                                                   s->ptr(LCX_A_TCDIRECT), s->ptr(I_SQRTY), m, s->ptr(LCX_A_SCALARS) + 4);
+    LAUNCHED(s);
+    LCX_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int lcx_details_ns(lcx_session* s, double* tc_no_overlap, double* additivity) {
+    S_REQUIRE_BOUND(s);
+    const Layout& L = s->L;
+    const int m = s->m, n = s->n;
+    double* rho = s->ptr(LCX_A_RHO);
+    // X_i Z_j = solve(ry, rho)^T (:280) as ry^-1 rho
+    LCX_TRY(run_inverse(s, s->ptr(LCX_A_RY), L.ldm, m, s->ptr(I_RYINV), L.ldm, s->ptr(I_AUG), (int*)s->ptr(I_STATUS)));
+    {
+        GemmArgs a;
+        memset(&a, 0, sizeof(a));
+        a.A = s->ptr(I_RYINV); a.B = rho; a.C = s->ptr(LCX_A_XZ);
+        a.M = m; a.N = n; a.K = m;
+        a.lda = L.ldm; a.ldb = L.ld; a.ldc = L.ld;
+        LCX_TRY(run_gemm(s, kLayoutKN, L.plan_mn, a, nullptr, 0));
+    }
+    LCX_TRY(details_tail(s, rho, nullptr));
+    // X_i Y_j = rho^T sqrt(Y_j^2) (:279)
+    scale_rows_out_kernel<<<grid_mn(m, n), 256, 0, s->stream>>>(rho, s->ptr(I_SQRTY), s->ptr(LCX_A_XY), m, n, L.ld);
+    LAUNCHED(s);
+    LCX_CUDA(cudaGetLastError());
+    LCX_TRY(read_mailbox(s));
+    if (tc_no_overlap) *tc_no_overlap = s->mailbox[4];
+    if (additivity) *additivity = s->mailbox[6];
+    return 0;
+}
+
+extern "C" int lcx_moments_syn(lcx_session* s, double* tc, double* additivity) {
+    S_REQUIRE_BOUND(s);
+    const Layout& L = s->L;
+    const int m = s->m, n = s->n;
+    double* W = s->ptr(LCX_A_W);
+    double* XY = s->ptr(LCX_A_XY);
+    double* cy = s->ptr(LCX_A_CY);
+    double* rinv = s->ptr(LCX_A_RHOINVRHO);
+    LCX_TRY(xpair(s, W, false));
+    // X_i Y_j = X~^T Y / N (:354)
+    sig_finish_kernel<<<grid_mn(m, n), 256, 0, s->stream>>>(s->ptr(LCX_A_D), s->ptr(LCX_A_D), 1.0 / (double)s->Nt, 0.0, XY, m, n,
+                                                          L.ld);
+    LAUNCHED(s);
+    {   // cy = W XY + yscale^2 I (:355)
+        GemmArgs a;
+        memset(&a, 0, sizeof(a));
+        a.A = W; a.B = XY; a.C = cy;
+        a.M = m; a.N = m; a.K = n;
+        a.lda = L.ld; a.ldb = L.ld; a.ldc = L.ldm;
+        LCX_TRY(run_gemm(s, kLayoutKK, L.plan_mm, a, s->ptr(I_PART), (long long)m * L.ldm));
+        diag_add_kernel<<<cdiv(m, 128), 128, 0, s->stream>>>(cy, L.ldm, m, 1.0);
+        LAUNCHED(s);
+    }
+    syn_ry_kernel<<<dim3(cdiv(m, 128), m), 128, 0, s->stream>>>(cy, L.ldm, m, s->ptr(LCX_A_RY), s->ptr(LCX_A_YJ2),
+                                                              s->ptr(I_SQRTY));
+    LAUNCHED(s);
+    syn_stage1_kernel<<<L.nstrips, dim3(kStripCols, kStripRows), 0, s->stream>>>(
+        XY, s->ptr(I_SQRTY), s->ptr(LCX_A_RHO), s->ptr(LCX_A_INVRHO), rinv, s->ptr(LCX_A_SI), m, n, L.ld);
+    LAUNCHED(s);
+    {   // Qij = ry rinv (:361)
+        GemmArgs a;
+        memset(&a, 0, sizeof(a));
+        a.A = s->ptr(LCX_A_RY); a.B = rinv; a.C = s->ptr(LCX_A_QIJ);
+        a.M = m; a.N = n; a.K = m;
+        a.lda = L.ldm; a.ldb = L.ld; a.ldc = L.ld;
+        LCX_TRY(run_gemm(s, kLayoutKN, L.plan_mn, a, nullptr, 0));
+    }
+    syn_qi_kernel<<<L.nstrips, dim3(kStripCols, kStripRows), 0, s->stream>>>(rinv, s->ptr(LCX_A_QIJ), s->ptr(LCX_A_QISI2), m, n,
+                                                                           L.ld);
+    LAUNCHED(s);
+    // X_i Z_j = solve(cy, XY^T)^T (:366) as cy^-1 XY
+    LCX_TRY(run_inverse(s, cy, L.ldm, m, s->ptr(I_RYINV), L.ldm, s->ptr(I_AUG), (int*)s->ptr(I_STATUS)));
+    {
+        GemmArgs a;
+        memset(&a, 0, sizeof(a));
+        a.A = s->ptr(I_RYINV); a.B = XY; a.C = s->ptr(LCX_A_XZ);
+        a.M = m; a.N = n; a.K = m;
+        a.lda = L.ldm; a.ldb = L.ld; a.ldc = L.ld;
+        LCX_TRY(run_gemm(s, kLayoutKN, L.plan_mn, a, nullptr, 0));
+    }
+    // sqrtY currently holds sqrt(Yj2); details_finish rewrites it with the same values
+    LCX_TRY(details_tail(s, XY, s->ptr(LCX_A_YJ2)));
+    syn_tc_kernel<<<1, 32, 0, s->stream>>>(s->ptr(LCX_A_SCALARS) + 4, s->ptr(LCX_A_SCALARS));
+    LAUNCHED(s);
+    LCX_CUDA(cudaGetLastError());
+    LCX_TRY(read_mailbox(s));
+    if (tc) *tc = s->mailbox[0];
+    if (additivity) *additivity = s->mailbox[6];
+    return 0;
+}
+
+extern "C" int lcx_update_syn(lcx_session* s, double eta, double* tc, double* additivity) {
+    S_REQUIRE_BOUND(s);
+    const Layout& L = s->L;
+    const int m = s->m, n = s->n;
+    double* W = s->ptr(LCX_A_W);
+    double* Rm = s->ptr(I_T);
+    double* H = s->ptr(LCX_A_CY);       // rebuilt by moments_syn below
+    double* Sm = s->ptr(LCX_A_GRAD);
+    syn_colscale_kernel<<<grid_mn(m, n), 256, 0, s->stream>>>(s->ptr(LCX_A_XZ), s->ptr(LCX_A_X2Y), Rm, m, n, L.ld);
+    LAUNCHED(s);
+    {   // H = (XZ^T / X2Y) XZ, diag -> 0 (:378-379)
+        GemmArgs a;
+        memset(&a, 0, sizeof(a));
+        a.A = Rm; a.B = s->ptr(LCX_A_XZ); a.C = H;
+        a.M = m; a.N = m; a.K = n;
+        a.lda = L.ld; a.ldb = L.ld; a.ldc = L.ldm;
+        LCX_TRY(run_gemm(s, kLayoutKK, L.plan_mm, a, s->ptr(I_PART), (long long)m * L.ldm));
+        diag_fix_kernel<<<cdiv(m, 128), 128, 0, s->stream>>>(H, L.ldm, m, 0.0, nullptr);
+        LAUNCHED(s);
+    }
+    {   // S = H W (:381)
+        GemmArgs a;
+        memset(&a, 0, sizeof(a));
+        a.A = H; a.B = W; a.C = Sm;
+        a.M = m; a.N = n; a.K = m;
+        a.lda = L.ldm; a.ldb = L.ld; a.ldc = L.ld;
+        LCX_TRY(run_gemm(s, kLayoutKN, L.plan_mn, a, nullptr, 0));
+    }
+    syn_mix_kernel<<<grid_mn(m, n), 256, 0, s->stream>>>(W, Rm, Sm, eta, W, m, n, L.ld);
+    LAUNCHED(s);
+    LCX_CUDA(cudaGetLastError());
+    return lcx_moments_syn(s, tc, additivity);
+}
+
+extern "C" int lcx_get_covariance(lcx_session* s, int synergy, double eps, const double* sd, int row0, int rows, double* out,
+                                  long long ldc) {
+    S_REQUIRE_BOUND(s);
+    const Layout& L = s->L;
+    const int m = s->m, n = s->n;
+    LCX_REQUIRE(sd && out, "null argument");
+    LCX_REQUIRE(row0 >= 0 && rows > 0 && row0 + rows <= n && row0 % 2 == 0, "bad row block (row0 must be even)");
+    LCX_REQUIRE(ldc >= n && ldc % 2 == 0, "ldc must be even and >= n");
+    const double* left;
+    const double* right;
+    if (!synergy) {
+        double* z = s->ptr(I_T);
+        cov_z_kernel<<<grid_mn(m, n), 256, 0, s->stream>>>(s->ptr(LCX_A_RHOINVRHO), s->ptr(LCX_A_SI), z, m, n, L.ld);
+        LAUNCHED(s);
+        left = z;
+        right = z;
+    } else {
+        left = s->ptr(LCX_A_XZ);
+        right = s->ptr(LCX_A_XY);
+    }
+    GemmPlan pl = plan_gemm(rows, n, m, kSMs, 1, false);
+    GemmArgs a;
+    memset(&a, 0, sizeof(a));
+    a.A = left + row0; a.B = right; a.C = out;
+    a.M = rows; a.N = n; a.K = m;
+    a.lda = L.ld; a.ldb = L.ld; a.ldc = ldc;
+    LCX_TRY(launch_gemm(kLayoutMN, pl, a, s->stream));
+    LAUNCHED(s);
+    cov_finish_kernel<<<dim3(cdiv(n, 256), rows), 256, 0, s->stream>>>(out, ldc, row0, rows, n,
+                                                                     synergy ? 1.0 : (1.0 - eps * eps), sd);
+    LAUNCHED(s);
+    LCX_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int lcx_gemm_f64(lcx_session* s, int layout, int M, int N, int K, const double* a, long long lda, const double* b,
+                            long long ldb, double* c, long long ldc, int trans_out, const double* cadd, int max_splits,
+                            double* scratch, long long scratch_doubles) {
+    LCX_REQUIRE(s && a && b && c, "null argument");
+    LCX_REQUIRE(layout >= 0 && layout <= 2 && M > 0 && N > 0 && K > 0, "bad shape/layout");
+    LCX_CUDA(cudaSetDevice(s->device));
+    const long long out_rows = trans_out ? N : M;
+    const long long out_count = out_rows * ldc;
+    int ms = max_splits;
+    if (scratch == nullptr || cadd != nullptr) ms = 1;
+    if (ms > 1 && out_count > 0) ms = (int)min((long long)ms, scratch_doubles / out_count);
+    if (ms < 1) ms = 1;
+    GemmPlan pl = plan_gemm(M, N, K, kSMs, ms, ms > 1);
+    GemmArgs g;
+    memset(&g, 0, sizeof(g));
+    g.A = a; g.B = b; g.C = c; g.Cadd = cadd;
+    g.M = M; g.N = N; g.K = K;
+    g.lda = lda; g.ldb = ldb; g.ldc = ldc;
+    g.trans_out = trans_out;
+    return run_gemm(s, (GemmLayout)layout, pl, g, scratch, out_count);
+}
+
+extern "C" int lcx_inverse(lcx_session* s, const double* a, long long lda, int m, double* out, long long ldo, double* aug) {
+    LCX_REQUIRE(s && a && out && aug && m > 0, "bad argument");
+    LCX_CUDA(cudaSetDevice(s->device));
+    return run_inverse(s, a, lda, m, out, ldo, aug, (int*)(aug + 2LL * m * m));
+}

@@ -1,0 +1,134 @@
+"""GPU unit parity: each C-ABI building block against numpy float64 on seeded operands.
+All calls go through liblcx_b200.so (ctypes); nothing here touches /root/reference."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    import torch
+    from linearcorex_b200 import _lib
+    from linearcorex_b200.corex import _DeviceSession
+    sess = _DeviceSession(_lib.PRECISION_FP64)
+    yield sess, _lib, torch
+    sess.close()
+
+
+def _dev_mat(torch, a, ld=None):
+    """numpy (r x c) -> device tensor with even leading dimension ld >= c (padding filled with NaN on purpose:
+    the kernels must never read it)."""
+    r, c = a.shape
+    ld = ld or (c + (c % 2) + 2)
+    t = torch.full((r, ld), float("nan"), dtype=torch.float64, device="cuda")
+    t[:, :c] = torch.from_numpy(np.ascontiguousarray(a))
+    return t
+
+
+GEMM_SHAPES = [(128, 104, 160), (1, 1, 1), (5, 3, 7), (257, 100, 333), (300, 13, 50), (100, 100, 1000),
+               (130, 260, 40), (64, 500, 96), (1000, 5, 50), (37, 30, 4100)]
+
+
+@pytest.mark.parametrize("layout", [0, 1, 2])
+@pytest.mark.parametrize("M,N,K", GEMM_SHAPES)
+@pytest.mark.parametrize("variant", ["plain", "trans", "cadd", "split"])
+def test_dgemm_matches_numpy(dev, layout, M, N, K, variant):
+    sess, L, torch = dev
+    rng = np.random.RandomState(M * 131 + N * 17 + K + layout)
+    A = rng.randn(M, K)
+    B = rng.randn(K, N)
+    want = A @ B
+    a_store = A if layout in (0, 2) else A.T            # [M][K] or [K][M]
+    b_store = B.T if layout == 0 else B                 # [N][K] or [K][N]
+    ad, bd = _dev_mat(torch, a_store), _dev_mat(torch, b_store)
+    trans = variant == "trans"
+    out_shape = (N, M) if trans else (M, N)
+    cd = torch.full((out_shape[0], out_shape[1] + (out_shape[1] % 2) + 2), float("nan"), dtype=torch.float64, device="cuda")
+    cadd = None
+    if variant == "cadd":
+        cadd0 = rng.randn(*out_shape)
+        cadd = _dev_mat(torch, cadd0, ld=cd.shape[1])
+        want = want + cadd0
+    max_splits, scratch, nscr = 1, None, 0
+    if variant == "split":
+        max_splits = 7
+        nscr = 7 * cd.numel()
+        scratch = torch.empty(nscr, dtype=torch.float64, device="cuda")
+    rc = sess.lib.lcx_gemm_f64(sess.h, layout, M, N, K, ad.data_ptr(), ad.stride(0), bd.data_ptr(), bd.stride(0),
+                               cd.data_ptr(), cd.stride(0), int(trans), cadd.data_ptr() if cadd is not None else None,
+                               max_splits, scratch.data_ptr() if scratch is not None else None, nscr)
+    L.check(rc, "lcx_gemm_f64")
+    torch.cuda.synchronize()
+    got = cd[:, :out_shape[1]].cpu().numpy()
+    if trans:
+        got = got.T
+    scale = np.abs(A) @ np.abs(B)
+    assert np.all(np.abs(got - want) <= 1e-14 * scale + 1e-300), np.abs(got - want).max()
+    assert torch.isnan(cd[:, out_shape[1]:]).all()  # padding untouched
+
+
+@pytest.mark.parametrize("m", [1, 2, 5, 30, 100, 257])
+def test_inverse_matches_numpy(dev, m):
+    sess, L, torch = dev
+    rng = np.random.RandomState(m)
+    Wm = rng.randn(m, 3 * m + 5)
+    A = Wm @ Wm.T / (3 * m + 5) + 0.05 * rng.randn(m, m) / max(1, m)  # well conditioned, not symmetric
+    np.fill_diagonal(A, 1.0)
+    ad = _dev_mat(torch, A)
+    od = torch.zeros((m, m + (m % 2) + 2), dtype=torch.float64, device="cuda")
+    aug = torch.empty(2 * m * m + 16, dtype=torch.float64, device="cuda")
+    L.check(sess.lib.lcx_inverse(sess.h, ad.data_ptr(), ad.stride(0), m, od.data_ptr(), od.stride(0), aug.data_ptr()))
+    torch.cuda.synchronize()
+    got = od[:, :m].cpu().numpy()
+    want = np.linalg.inv(A)
+    np.testing.assert_allclose(got, want, rtol=1e-9, atol=1e-11 * np.abs(want).max())
+
+
+@pytest.mark.parametrize("N,n,m", [(400, 300, 10), (1000, 50, 5), (77, 513, 30), (2000, 5, 1), (130, 1000, 100)])
+def test_project_and_colsq(dev, N, n, m):
+    sess, L, torch = dev
+    rng = np.random.RandomState(N + n + m)
+    X = rng.randn(N, n)
+    W = rng.randn(m, n) / np.sqrt(n)
+    ld = sess.lib.lcx_ld(n)
+    xd, wd = _dev_mat(torch, X, ld=ld), _dev_mat(torch, W, ld=ld)
+    ldy = sess.lib.lcx_ldy(m)
+    y = torch.full((N, ldy), float("nan"), dtype=torch.float64, device="cuda")
+    s = torch.zeros(m, dtype=torch.float64, device="cuda")
+    nscr = sess.lib.lcx_project_scratch_doubles(N, m)
+    scr = torch.empty(nscr, dtype=torch.float64, device="cuda")
+    L.check(sess.lib.lcx_project(sess.h, xd.data_ptr(), N, n, ld, wd.data_ptr(), ld, m, y.data_ptr(), ldy, s.data_ptr(),
+                                 scr.data_ptr(), nscr))
+    torch.cuda.synchronize()
+    Y = X @ W.T
+    np.testing.assert_allclose(y[:, :m].cpu().numpy(), Y, rtol=1e-12, atol=1e-13)
+    np.testing.assert_allclose(s.cpu().numpy(), (Y * Y).sum(0), rtol=1e-12)
+
+
+@pytest.mark.parametrize("dtype", ["float32", "float64"])
+@pytest.mark.parametrize("mode", ["standard", "outliers"])
+@pytest.mark.parametrize("missing", [None, -1e6, float("nan")])
+def test_preprocess_matches_oracle(dev, dtype, mode, missing):
+    import corex_oracle as oc
+    from linearcorex_b200 import Corex
+    rng = np.random.RandomState(11)
+    x = (rng.randn(9000, 37) * rng.uniform(0.5, 30, size=37) + rng.uniform(-50, 50, size=37))
+    x[:, 3] = np.sign(x[:, 3]) * np.abs(x[:, 3]) ** 2.5
+    x = x.astype(dtype)
+    if missing is not None:
+        x = np.where(rng.rand(*x.shape) < 0.05, missing, x).astype(dtype)
+    mdl = Corex(n_hidden=2, gaussianize=mode, missing_values=missing, input_dtype="float64")
+    xt = mdl.preprocess(x, fit=True)[:, :37].cpu().numpy()
+    want, theta, n_obs = oc.standardize(x.astype(np.float64), mode, missing)
+    np.testing.assert_allclose(mdl.theta[0], theta[0], rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(mdl.theta[1], theta[1], rtol=1e-12)
+    np.testing.assert_array_equal(np.asarray(mdl.n_obs), np.asarray(n_obs))
+    np.testing.assert_allclose(xt, want, rtol=1e-10, atol=1e-11)
+    # transform-time preprocessing imputes with the *new* data's column means but keeps theta (:389, :404)
+    x2 = x[:1234]
+    xt2 = mdl.preprocess(x2)[:, :37].cpu().numpy()
+    want2, _, _ = oc.standardize(x2.astype(np.float64), mode, missing, theta=theta)
+    np.testing.assert_allclose(xt2, want2, rtol=1e-10, atol=1e-11)
