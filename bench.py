@@ -1,0 +1,367 @@
+#!/usr/bin/env python
+"""bench.py -- Linear CorEx fit-loop throughput on B200 (the driver's measurement contract).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on the host cores
+
+A "step" is one fit iteration = one `_update_ns` (reference linearcorex.py:290-334): search direction, one
+pass pair over X, backtracking line search, accept.  The workload is BASELINE.json configs[2] -- synthetic
+Gaussian latent-factor data, N=100 000 samples x n=10 000 variables, m=100 factors, FP64 mode -- the
+configuration the metric is quoted on (configs[0..1] are the reference's CPU-scale parity cases).  With
+--gpus N>1 the same N x n problem is row-sharded over the ranks (strong scaling; one all-reduce of the
+m*n + m moment partials per pass pair), launched under torchrun, one rank per GPU.
+
+One JSON line on stdout (rank 0).  `value` = fit iterations per second with X~ resident in HBM, timed with
+CUDA events around exactly K iterations, max over ranks.  `e2e` = the same metric through the public API
+(`Corex(...).fit(x_host)`) with the host->device copy of X, preprocessing, the fit, the final moment export
+and the device->host copies all inside the timed region.  `roofline` is for the dominant kernel (the two
+FP64 tensor-core contractions, >97 % of a step), timed live by CUDA events on the launching stream.
+`cpu_baseline` / `--impl reference` time oracle/corex_oracle.py (the numpy restatement of the reference;
+/root/reference does not exist on the GPU box) on a bounded row subsample with all host threads.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (N samples, n variables, m factors)
+    "config3": (100000, 10000, 100),     # BASELINE.json configs[2]
+    "config4": (1000, 50000, 500),       # configs[3] (gaussianize='outliers')
+    "target8": (1000000, 20000, 100),    # BASELINE.json target shape: needs >= 2 GPUs in FP64 mode
+    "small": (4000, 2000, 20),
+}
+METRIC = "fit_iters_per_sec"
+UNIT = "it/s"
+
+
+# ----------------------------------------------------------------------------------------------------
+# synthetic data: Gaussian latent-factor model, row-block seeded so ranks build only
+# their own rows
+# ----------------------------------------------------------------------------------------------------
+def make_rows(n_total, n_vars, n_factors, lo, hi, seed=0, snr=1.0, block=4096, threads=None):
+    from concurrent.futures import ThreadPoolExecutor
+    out = np.empty((hi - lo, n_vars), dtype=np.float32)
+    groups = np.arange(n_vars) % n_factors
+    a, b = np.float32(np.sqrt(snr / (1.0 + snr))), np.float32(1.0 / np.sqrt(1.0 + snr))
+    first = lo // block
+
+    def fill(bi):
+        r0, r1 = max(lo, bi * block), min(hi, (bi + 1) * block)
+        rng = np.random.default_rng([seed, bi])
+        rows = min(n_total, (bi + 1) * block) - bi * block
+        z = rng.standard_normal((rows, n_factors), dtype=np.float32)
+        e = rng.standard_normal((rows, n_vars), dtype=np.float32)
+        e *= b
+        e += a * z[:, groups]
+        out[r0 - lo:r1 - lo] = e[r0 - bi * block:r1 - bi * block]
+
+    blocks = list(range(first, (hi + block - 1) // block))
+    with ThreadPoolExecutor(max_workers=threads or min(16, os.cpu_count() or 1)) as ex:
+        list(ex.map(fill, blocks))
+    return out
+
+
+# ----------------------------------------------------------------------------------------------------
+# clocks during the timed region (nvidia-smi fields through NVML)
+# ----------------------------------------------------------------------------------------------------
+class ClockSampler(object):
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+               0x80: "hw_power_brake", 0x2: "applications_clocks_setting", 0x100: "display_clock_setting"}
+
+    def __init__(self, index):
+        self.samples, self.mask, self.max_mhz, self._stop, self._th = [], 0, None, threading.Event(), None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                self.mask |= int(self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+            except Exception:
+                pass
+            time.sleep(0.05)
+
+    def __enter__(self):
+        if self.nv is not None:
+            self._th = threading.Thread(target=self._run, daemon=True)
+            self._th.start()
+        return self
+
+    def __exit__(self, *exc):
+        self._stop.set()
+        if self._th is not None:
+            self._th.join()
+
+    def summary(self):
+        return {"sm_mhz": statistics.median(self.samples) if self.samples else None, "sm_max_mhz": self.max_mhz,
+                "samples": len(self.samples),
+                "reasons": sorted(name for bit, name in self.REASONS.items() if self.mask & bit)}
+
+
+# ----------------------------------------------------------------------------------------------------
+# reference algorithm on the host cores (oracle port; the only place bench.py executes oracle/)
+# ----------------------------------------------------------------------------------------------------
+def time_reference_cpu(n_total, n_vars, n_factors, steps, warmup, flop_budget):
+    """Time `step_ns` of oracle/corex_oracle.py in float64 on a row subsample; scale linearly in N.
+
+    Per-iteration cost is linear in N apart from the O(m n) / O(m^2 n) terms (<1 % here), SURVEY.md 8(d)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import corex_oracle as oc
+    per_row = 11.0 * n_vars * n_factors  # ~ (4 + 4t) N n m flops per iteration at t ~ 1.7 trials
+    rows = int(min(n_total, max(512, flop_budget / (per_row * (steps + warmup)))))
+    x = make_rows(n_total, n_vars, n_factors, 0, rows).astype(np.float64)
+    t0 = time.perf_counter()
+    xt, theta, _ = oc.standardize(x, 'standard', None)
+    t_pre = time.perf_counter() - t0
+    del x
+    np.random.seed(0)
+    eps = 0.6
+    w = np.random.randn(n_factors, n_vars)
+    w /= (10. * oc.norm_y(xt, w, 0.0))[:, np.newaxis]
+    m = oc.moments_ns(xt, w, eps)
+    trials = []
+    for _ in range(warmup):
+        rec = {}
+        w, m = oc.step_ns(xt, w, m, eps, 1e-12, trace=rec)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        rec = {}
+        w, m = oc.step_ns(xt, w, m, eps, 1e-12, trace=rec)
+        trials.append(rec.get("trials", 0))
+    dt = time.perf_counter() - t0
+    try:
+        from threadpoolctl import threadpool_info
+        cores = max([p.get("num_threads", 1) for p in threadpool_info()] + [1])
+    except Exception:
+        cores = os.cpu_count() or 1
+    it_s_sample = steps / dt
+    scale = rows / float(n_total)
+    return {"value": it_s_sample * scale, "unit": UNIT, "cores": int(cores), "kind": "port",
+            "sample": "oracle/corex_oracle.py step_ns (numpy float64 restatement of linearcorex.py:290-334), "
+                      "%d of %d rows x %d vars x %d factors, %d iterations after %d warm-up, %.2f trials/iteration; "
+                      "%.4g it/s on the sample scaled x%.4g (cost linear in N); preprocess of the sample %.2f s"
+                      % (rows, n_total, n_vars, n_factors, steps, warmup, float(np.mean(trials)) if trials else 0.0,
+                         it_s_sample, scale, t_pre),
+            "ms_per_step_sample": 1e3 * dt / steps, "rows": rows}
+
+
+def run_reference(args, shape):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n_total, n_vars, n_factors = shape
+    base = time_reference_cpu(n_total, n_vars, n_factors, args.steps, args.warmup, flop_budget=6e12)
+    line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / base["value"], "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(args, shape), "n_samples": n_total, "n_variables": n_vars,
+                       "n_factors": n_factors, "mode": "numpy float64 on host cores"},
+            "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def workload_name(args, shape):
+    return "%s: synthetic latent-factor data N=%d x n=%d, m=%d, %s mode" % (
+        args.workload, shape[0], shape[1], shape[2], "FP64" if args.precision == "fp64" else "fast (3xTF32)")
+
+
+# ----------------------------------------------------------------------------------------------------
+# this repo's CUDA path
+# ----------------------------------------------------------------------------------------------------
+def measure_dgemm_peak(torch):
+    n = 6144
+    a = torch.randn(n, n, dtype=torch.float64, device="cuda")
+    b = torch.randn(n, n, dtype=torch.float64, device="cuda")
+    best = 1e30
+    for i in range(5):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        torch.matmul(a, b)
+        e1.record()
+        torch.cuda.synchronize()
+        if i > 0:
+            best = min(best, e0.elapsed_time(e1))
+    return 2.0 * n ** 3 / best / 1e9
+
+
+def run_ours(args, shape):
+    import torch
+    import torch.distributed as dist
+    from linearcorex_b200 import Corex, shard_rows
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    n_total, n_vars, n_factors = shape
+    lo, hi = shard_rows(n_total, rank, world)
+    x_host = make_rows(n_total, n_vars, n_factors, lo, hi)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            peaks = json.load(fh)
+    except Exception:
+        pass
+    dgemm_peak = measure_dgemm_peak(torch) if rank == 0 else 0.0
+
+    # ---- device-resident timing: exactly K iterations ----------------------------------------------
+    x_dev = torch.from_numpy(x_host).cuda()
+    mdl = Corex(n_hidden=n_factors, seed=0, tol=1e-12, max_iter=10 ** 9, precision=args.precision,
+                gaussianize=args.gaussianize, comm=True if world > 1 else None)
+    schedule = mdl._prepare(x_dev)
+    del x_dev
+    mdl._begin_stage(schedule[0], rescale=False)
+    sess = mdl._sess
+    for _ in range(args.warmup):
+        mdl._iterate()
+    sess.lib.lcx_profile_enable(sess.h, 1)
+    k1, k2, pairs = C.c_double(), C.c_double(), C.c_longlong()
+    sess.lib.lcx_profile_read(sess.h, C.byref(k1), C.byref(k2), C.byref(pairs), 1)
+    launches0 = sess.launches()
+    n_trace0 = len(mdl.trace)
+    barrier()
+    with ClockSampler(local) as clocks:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            mdl._iterate()
+        e1.record()
+        barrier()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = t.item()
+    sess.lib.lcx_profile_read(sess.h, C.byref(k1), C.byref(k2), C.byref(pairs), 1)
+    sess.lib.lcx_profile_enable(sess.h, 0)
+    launches = sess.launches() - launches0
+    trace = mdl.trace[n_trace0:]
+    trials = float(np.mean([t["trials"] for t in trace])) if trace else 0.0
+    tc_last = float(mdl.tc)
+    it_s = args.steps / (ms / 1e3)
+    n_local = hi - lo
+    pair_flops = 4.0 * n_local * n_vars * n_factors           # K1 + K2 of one pass pair on this rank
+    pair_ms = (k1.value + k2.value) / max(1, pairs.value)
+    achieved = pair_flops / (pair_ms / 1e3) / 1e12 if pair_ms > 0 else 0.0
+    del mdl, sess
+    torch.cuda.empty_cache()
+
+    # ---- end to end through the public API, host buffers in, host results out -----------------------
+    per_stage = max(1, args.steps // 7)
+    x_pin = torch.from_numpy(x_host).pin_memory() if args.pin else None
+    barrier()
+    e2e_mdl = Corex(n_hidden=n_factors, seed=0, tol=1e-12, max_iter=per_stage, precision=args.precision,
+                    gaussianize=args.gaussianize, comm=True if world > 1 else None)
+    t0 = time.perf_counter()
+    e2e_mdl.fit(x_pin.numpy() if x_pin is not None else x_host)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = t.item()
+    e2e_iters = len(e2e_mdl.history["TC"])
+    d2h = sum(np.asarray(v).nbytes for v in e2e_mdl.moments.values()) * 2 + e2e_mdl.ws.nbytes + 16 * 8 * 4 * e2e_iters
+    e2e = {"value": e2e_iters / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(x_host.nbytes * world / e2e_iters),
+           "d2h_bytes_per_step": int(d2h / e2e_iters), "iterations": e2e_iters, "seconds": e2e_s,
+           "what": "Corex(n_hidden=%d, max_iter=%d).fit(host float32 X): H2D of X, preprocess, 7 anneal stages, "
+                   "final sort + full moments, D2H of ws and every moments key" % (n_factors, per_stage)}
+    del e2e_mdl
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        cpu = time_reference_cpu(n_total, n_vars, n_factors, steps=3, warmup=1, flop_budget=2.5e12)
+        cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    line = {
+        "metric": METRIC, "value": it_s, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f64" if args.precision == "fp64" else "tf32x3", "data": "synthetic",
+        "config": {"workload": workload_name(args, shape), "n_samples": n_total, "n_variables": n_vars,
+                   "n_factors": n_factors, "rows_per_gpu": n_local, "parallelism": "sample-sharded x%d" % world,
+                   "l2": "inputs_exceed_l2 (X~ block is %.1f GB per GPU)" % (n_local * n_vars * 8 / 1e9),
+                   "trials_per_iteration": trials, "TC_after_timed_region": tc_last},
+        "updates_per_sec": it_s * n_total * n_vars * n_factors,
+        "roofline": {"bound": "tensor", "achieved": achieved, "peak": dgemm_peak, "unit": "TFLOP/s",
+                     "frac": achieved / dgemm_peak if dgemm_peak else None, "traffic": args.traffic,
+                     "kernel": "dgemm_mma_kernel (Y = X~ A^T and X~^T Y, DMMA.8x8x4), %d pass pairs timed by CUDA events; "
+                               "K1 %.3f ms, K2 %.3f ms per launch" % (pairs.value, k1.value / max(1, pairs.value),
+                                                                      k2.value / max(1, pairs.value)),
+                     "algorithmic_flops_per_pair": pair_flops,
+                     "share_of_step": pair_ms * pairs.value / ms if ms > 0 else None,
+                     "peak_source": "cuBLAS DGEMM 6144^3 measured in this run (MEASURED_PEAKS.json has no FP64 entry; "
+                                    "nominal B200 FP64 tensor peak is 40 TFLOP/s); bf16 measured peak for context: %s TF/s"
+                                    % peaks.get("bf16_tflops")},
+        "clocks": clocks.summary(),
+        "e2e": e2e,
+        "gpu_launches": int(launches),
+    }
+    if cpu is not None:
+        line["cpu_baseline"] = cpu
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=42)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="config3", choices=sorted(WORKLOADS))
+    ap.add_argument("--precision", default="fp64", choices=["fp64", "fast"])
+    ap.add_argument("--gaussianize", default="standard")
+    ap.add_argument("--rows", type=int, default=0)
+    ap.add_argument("--vars", type=int, default=0)
+    ap.add_argument("--factors", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--pin", action="store_true", help="stage the e2e input through a pinned host tensor")
+    ap.add_argument("--traffic", type=float, default=None, help="dram bytes per launch from an ncu capture, if known")
+    args = ap.parse_args()
+    args.warmup = max(3, args.warmup)
+    shape = list(WORKLOADS[args.workload])
+    for i, v in enumerate((args.rows, args.vars, args.factors)):
+        if v:
+            shape[i] = v
+    if args.workload == "config4":
+        args.gaussianize = "outliers"
+    if args.impl == "reference":
+        run_reference(args, tuple(shape))
+    else:
+        run_ours(args, tuple(shape))
+
+
+if __name__ == "__main__":
+    main()

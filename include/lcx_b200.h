@@ -99,6 +99,10 @@ int lcx_session_destroy(lcx_session* s);
 int lcx_set_stream(lcx_session* s, void* cuda_stream);
 int lcx_set_allreduce(lcx_session* s, lcx_allreduce_fn fn, void* user);
 int lcx_launch_count(lcx_session* s, long long* launches);   /* kernels launched so far by this session */
+/* Device-side timing of the two X contractions (CUDA events on the session stream around each launch).
+ * lcx_profile_read synchronises the stream and returns accumulated milliseconds and the pair count. */
+int lcx_profile_enable(lcx_session* s, int on);
+int lcx_profile_read(lcx_session* s, double* k1_ms, double* k2_ms, long long* pairs, int reset);
 
 /* ---- layout --------------------------------------------------------------------------------- */
 long long lcx_ld(int n_vars);                       /* leading dimension of m x n arrays */

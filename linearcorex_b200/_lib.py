@@ -32,6 +32,8 @@ SIGNATURES = {
     "lcx_set_stream": (_i, [_p, _p]),
     "lcx_set_allreduce": (_i, [_p, ALLREDUCE_FN, _p]),
     "lcx_launch_count": (_i, [_p, _pll]),
+    "lcx_profile_enable": (_i, [_p, _i]),
+    "lcx_profile_read": (_i, [_p, _pd, _pd, _pll, _i]),
     "lcx_ld": (_ll, [_i]),
     "lcx_ldy": (_ll, [_i]),
     "lcx_workspace_doubles": (_ll, [_ll, _i, _i]),

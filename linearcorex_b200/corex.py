@@ -294,6 +294,27 @@ class Corex(object):
     # fit (:107-164)
     # ------------------------------------------------------------------------------------------
     def fit(self, x):
+        schedule = self._prepare(x)
+        for i_eps, eps in enumerate(schedule):
+            self._begin_stage(eps, rescale=i_eps > 0)
+            delta = 0.0
+            for i_loop in range(self.max_iter):
+                ok, delta = self._iterate()
+                if not ok:  # the reference returns from inside the loop (:149) without the final sort
+                    self.ws = self._get_w()
+                    return self
+                if delta < self.tol:
+                    if self.verbose:
+                        print('{:d} iterations to tol: {:f}, TC={:f}'.format(i_loop, self.tol, self.tc))
+                    break
+            else:
+                if self.verbose:
+                    print("Warning: Convergence not achieved in {:d} iterations. Final delta: {:f}".format(
+                        self.max_iter, float(delta)))
+        return self._finish()
+
+    def _prepare(self, x):
+        """Preprocess, bind the device problem and initialise W (:108-122).  Returns the anneal schedule."""
         sess = self._session()
         lib = sess.lib
         red = self._reducer()
@@ -303,8 +324,6 @@ class Corex(object):
         if self.m is None:
             raise ValueError("n_hidden=None (pick_n_hidden) is not supported: the reference helper is broken (:458-480)")
         sess.bind(xt, self.n_samples, self.nv, self.m, red)
-        tcv, muj, tang, addv = (C.c_double() for _ in range(4))
-
         schedule = [0.]
         if self.ws.size == 0:  # :114-121
             if self.discourage_overlap:
@@ -319,60 +338,58 @@ class Corex(object):
                 self._set_w(np.random.randn(self.m, self.nv) * self.yscale ** 2 / np.sqrt(self.nv))
         else:
             self._set_w(self.ws)
+        self.moments = {"TC": self._moments_from_x()}  # :122
+        return schedule
 
-        def moments_from_x():
-            if self.discourage_overlap:
-                _lib.check(lib.lcx_moments_ns(sess.h, float(self.eps), 0, C.byref(tcv), C.byref(muj)), "lcx_moments_ns")
-            else:
-                _lib.check(lib.lcx_moments_syn(sess.h, C.byref(tcv), C.byref(addv)), "lcx_moments_syn")
-            return tcv.value
+    def _moments_from_x(self):
+        """quick moments of the current W from X~ (one pass pair); returns TC."""
+        sess = self._sess
+        tcv, muj, addv = C.c_double(), C.c_double(), C.c_double()
+        if self.discourage_overlap:
+            _lib.check(sess.lib.lcx_moments_ns(sess.h, float(self.eps), 0, C.byref(tcv), C.byref(muj)), "lcx_moments_ns")
+        else:
+            _lib.check(sess.lib.lcx_moments_syn(sess.h, C.byref(tcv), C.byref(addv)), "lcx_moments_syn")
+        return tcv.value
 
-        self.moments = {"TC": moments_from_x()}  # :122
-        early_exit = False
-        for i_eps, eps in enumerate(schedule):
-            eps0, self.eps = self.eps, eps
-            if i_eps > 0:  # :129-133
-                _lib.check(lib.lcx_stage_rescale(sess.h, float(eps), float(eps0)), "lcx_stage_rescale")
-            self.moments = {"TC": moments_from_x()}  # :134
-            delta = 0.0
-            for i_loop in range(self.max_iter):
-                last_tc = self.tc
-                rec = {"eps": eps}
-                if self.discourage_overlap:
-                    ok = self._update_ns(rec)
-                else:
-                    _lib.check(lib.lcx_update_syn(sess.h, 0.1, C.byref(tcv), C.byref(addv)), "lcx_update_syn")
-                    self.moments = {"TC": tcv.value, "additivity": addv.value}
-                    ok = True
-                if not ok or not np.isfinite(self.tc):  # :144-149
-                    if not ok:
-                        print("Error... updates giving invalid solutions?")
-                        early_exit = True
-                        break
-                    print("Error: TC is no longer finite: {}".format(self.tc))
-                delta = np.abs(self.tc - last_tc)
-                rec["TC"] = self.tc
-                self.trace.append(rec)
-                self.history["TC"] = self.history.get("TC", []) + [self.tc]
-                if self.verbose > 1:
-                    print("TC={:.3f}\tadd={:.3f}\tdelta={:.6f}".format(self.tc, self.moments.get("additivity", 0), delta))
-                if delta < self.tol:
-                    if self.verbose:
-                        print('{:d} iterations to tol: {:f}, TC={:f}'.format(i_loop, self.tol, self.tc))
-                    break
-            else:
-                if self.verbose:
-                    print("Warning: Convergence not achieved in {:d} iterations. Final delta: {:f}".format(
-                        self.max_iter, float(delta)))
-            if early_exit:
-                break
-        if early_exit:  # the reference returns from inside the loop (:149) without the final sort
-            self.ws = self._get_w()
-            return self
-        # :160-163 full moments, sort factors by TCs (descending), full moments again
+    def _begin_stage(self, eps, rescale):
+        """Switch the annealing parameter (:127-134): rescale W so uj < 1 still holds, recompute moments."""
+        sess = self._sess
+        eps0, self.eps = self.eps, eps
+        if rescale:
+            _lib.check(sess.lib.lcx_stage_rescale(sess.h, float(eps), float(eps0)), "lcx_stage_rescale")
+        self.moments = {"TC": self._moments_from_x()}
+
+    def _iterate(self):
+        """One pass of the loop body (:137-151).  Returns (ok, |delta TC|)."""
+        sess = self._sess
+        last_tc = self.tc
+        rec = {"eps": self.eps}
+        if self.discourage_overlap:
+            ok = self._update_ns(rec)
+        else:
+            tcv, addv = C.c_double(), C.c_double()
+            _lib.check(sess.lib.lcx_update_syn(sess.h, 0.1, C.byref(tcv), C.byref(addv)), "lcx_update_syn")
+            self.moments = {"TC": tcv.value, "additivity": addv.value}
+            ok = True
+        if not ok:  # :144-149: moments is False -> formatting raises -> early return
+            print("Error... updates giving invalid solutions?")
+            return False, 0.0
+        if not np.isfinite(self.tc):
+            print("Error: TC is no longer finite: {}".format(self.tc))
+        delta = np.abs(self.tc - last_tc)
+        rec["TC"] = self.tc
+        self.trace.append(rec)
+        self.history["TC"] = self.history.get("TC", []) + [self.tc]
+        if self.verbose > 1:
+            print("TC={:.3f}\tadd={:.3f}\tdelta={:.6f}".format(self.tc, self.moments.get("additivity", 0), delta))
+        return True, delta
+
+    def _finish(self):
+        """:160-163 full moments, sort factors by TCs (descending), full moments again."""
+        sess = self._sess
         self._full_moments()
         order = np.argsort(-self.moments["TCs"])
-        _lib.check(lib.lcx_permute_rows(sess.h, (C.c_int * self.m)(*[int(o) for o in order])), "lcx_permute_rows")
+        _lib.check(sess.lib.lcx_permute_rows(sess.h, (C.c_int * self.m)(*[int(o) for o in order])), "lcx_permute_rows")
         self._full_moments()
         self.ws = self._get_w()
         return self

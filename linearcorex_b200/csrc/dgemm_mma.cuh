@@ -233,21 +233,25 @@ __global__ void __launch_bounds__(256, 1) dgemm_mma_kernel(const GemmArgs p) {
 }
 
 // Fixed-order reduction of split-K partials: out[i] = sum_z part[z*stride + i]  (deterministic).
+// Only the valid rows x cols region (leading dimension ld, even) is read or written.
 __global__ void reduce_splits_kernel(const double* __restrict__ part, int splits, long long stride,
-                                     double* __restrict__ out, long long count) {
-    const long long i2 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 2;
-    if (i2 + 1 < count) {
-        double2 acc = *reinterpret_cast<const double2*>(part + i2);
+                                     double* __restrict__ out, int rows, int cols, long long ld) {
+    const int c2 = (blockIdx.x * blockDim.x + threadIdx.x) * 2;
+    const int r = blockIdx.y;
+    if (r >= rows) return;
+    const long long o = (long long)r * ld + c2;
+    if (c2 + 1 < cols) {
+        double2 acc = *reinterpret_cast<const double2*>(part + o);
         for (int z = 1; z < splits; ++z) {
-            const double2 v = *reinterpret_cast<const double2*>(part + (long long)z * stride + i2);
+            const double2 v = *reinterpret_cast<const double2*>(part + (long long)z * stride + o);
             acc.x += v.x;
             acc.y += v.y;
         }
-        *reinterpret_cast<double2*>(out + i2) = acc;
-    } else if (i2 < count) {
-        double a = part[i2];
-        for (int z = 1; z < splits; ++z) a += part[(long long)z * stride + i2];
-        out[i2] = a;
+        *reinterpret_cast<double2*>(out + o) = acc;
+    } else if (c2 < cols) {
+        double a = part[o];
+        for (int z = 1; z < splits; ++z) a += part[(long long)z * stride + o];
+        out[o] = a;
     }
 }
 
@@ -344,10 +348,10 @@ inline int launch_gemm(GemmLayout lay, const GemmPlan& pl, GemmArgs a, cudaStrea
     return fail(-1, "launch_gemm", "unknown layout");
 }
 
-inline int launch_reduce_splits(const double* part, int splits, long long stride, double* out, long long count,
-                                cudaStream_t st) {
-    const long long pairs = (count + 1) / 2;
-    reduce_splits_kernel<<<cdiv(pairs, 256), 256, 0, st>>>(part, splits, stride, out, count);
+inline int launch_reduce_splits(const double* part, int splits, long long stride, double* out, int rows, int cols,
+                                long long ld, cudaStream_t st) {
+    LCX_REQUIRE(rows <= 65535, "split-K reduction supports at most 65535 output rows");
+    reduce_splits_kernel<<<dim3(cdiv((cols + 1) / 2, 128), rows), 128, 0, st>>>(part, splits, stride, out, rows, cols, ld);
     LCX_CUDA(cudaGetLastError());
     return 0;
 }

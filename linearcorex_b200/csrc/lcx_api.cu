@@ -149,6 +149,13 @@ struct lcx_session {
     double* ws;
     Layout L;
     int cur;  // which physical set is "set 0" (current)
+    // optional device-side timing of the two X contractions (bench.py roofline); events are
+    // recorded on the session stream around each launch and resolved at lcx_profile_read
+    bool prof_on;
+    cudaEvent_t* prof_ev;      // 4 per pair: [0] before K1, [1] after K1, [3] before K2, [2] after K2 (+ split reduction)
+    int prof_pending, prof_cap;
+    double prof_k1_ms, prof_k2_ms;
+    long long prof_pairs;
 
     double* ptr(int id, int set = 0) const {
         const int phys = (id <= LCX_A_UJ) ? (set ^ cur) : 0;
@@ -192,8 +199,48 @@ extern "C" int lcx_session_create(lcx_session** out, int device, int precision) 
     return 0;
 }
 
+extern "C" int lcx_profile_enable(lcx_session* s, int on) {
+    LCX_REQUIRE(s != nullptr, "null session");
+    LCX_CUDA(cudaSetDevice(s->device));
+    if (on && s->prof_ev == nullptr) {
+        s->prof_cap = 4096;
+        s->prof_ev = new cudaEvent_t[4 * s->prof_cap];
+        for (int i = 0; i < 4 * s->prof_cap; ++i) LCX_CUDA(cudaEventCreate(&s->prof_ev[i]));
+    }
+    s->prof_on = on != 0;
+    return 0;
+}
+
+extern "C" int lcx_profile_read(lcx_session* s, double* k1_ms, double* k2_ms, long long* pairs, int reset) {
+    LCX_REQUIRE(s != nullptr, "null session");
+    LCX_CUDA(cudaSetDevice(s->device));
+    LCX_CUDA(cudaStreamSynchronize(s->stream));
+    for (int i = 0; i < s->prof_pending; ++i) {
+        cudaEvent_t* ev = s->prof_ev + 4 * i;
+        float a = 0.f, b = 0.f;
+        LCX_CUDA(cudaEventElapsedTime(&a, ev[0], ev[1]));
+        LCX_CUDA(cudaEventElapsedTime(&b, ev[3], ev[2]));
+        s->prof_k1_ms += a;
+        s->prof_k2_ms += b;
+        s->prof_pairs++;
+    }
+    s->prof_pending = 0;
+    if (k1_ms) *k1_ms = s->prof_k1_ms;
+    if (k2_ms) *k2_ms = s->prof_k2_ms;
+    if (pairs) *pairs = s->prof_pairs;
+    if (reset) {
+        s->prof_k1_ms = s->prof_k2_ms = 0.0;
+        s->prof_pairs = 0;
+    }
+    return 0;
+}
+
 extern "C" int lcx_session_destroy(lcx_session* s) {
     if (!s) return 0;
+    if (s->prof_ev) {
+        for (int i = 0; i < 4 * s->prof_cap; ++i) cudaEventDestroy(s->prof_ev[i]);
+        delete[] s->prof_ev;
+    }
     if (s->mailbox) cudaFreeHost(s->mailbox);
     delete s;
     return 0;
@@ -387,7 +434,8 @@ static int run_gemm(lcx_session* s, GemmLayout lay, const GemmPlan& pl, GemmArgs
         a.c_split_stride = out_count;
         LCX_TRY(launch_gemm(lay, pl, a, s->stream));
         LAUNCHED(s);
-        LCX_TRY(launch_reduce_splits(part, pl.splits, out_count, final_c, out_count, s->stream));
+        const int out_rows = a.trans_out ? a.N : a.M, out_cols = a.trans_out ? a.M : a.N;
+        LCX_TRY(launch_reduce_splits(part, pl.splits, out_count, final_c, out_rows, out_cols, a.ldc, s->stream));
         LAUNCHED(s);
     } else {
         a.c_split_stride = 0;
@@ -404,6 +452,9 @@ static int xpair(lcx_session* s, const double* A, bool want_colsq) {
     double* Y = s->ptr(LCX_A_Y);
     double* D = s->ptr(LCX_A_D);
     double* svec = D + (long long)m * L.ld;
+    cudaEvent_t* ev = nullptr;
+    if (s->prof_on && s->prof_pending < s->prof_cap) ev = s->prof_ev + 4 * s->prof_pending;
+    if (ev) LCX_CUDA(cudaEventRecord(ev[0], s->stream));
     {   // K1
         GemmArgs a;
         memset(&a, 0, sizeof(a));
@@ -413,6 +464,7 @@ static int xpair(lcx_session* s, const double* A, bool want_colsq) {
         a.colsq_part = want_colsq ? s->ptr(I_COLSQ) : nullptr;
         a.ld_colsq = (int)L.ldy;
         LCX_TRY(run_gemm(s, kLayoutKK, L.plan_k1, a, nullptr, 0));
+        if (ev) LCX_CUDA(cudaEventRecord(ev[1], s->stream));
         if (want_colsq) {
             reduce_colsq_kernel<<<cdiv(m, 128), 128, 0, s->stream>>>(s->ptr(I_COLSQ), L.plan_k1.grid.x, (int)L.ldy, svec, m);
             LAUNCHED(s);
@@ -425,7 +477,12 @@ static int xpair(lcx_session* s, const double* A, bool want_colsq) {
         a.M = n; a.N = m; a.K = (int)s->Nl;
         a.lda = s->ldx; a.ldb = L.ldy; a.ldc = L.ld;
         a.trans_out = 1;
+        if (ev) LCX_CUDA(cudaEventRecord(ev[3], s->stream));  // K2 starts after the (tiny) colsq reduction
         LCX_TRY(run_gemm(s, kLayoutMN, L.plan_k2, a, s->ptr(I_PART), (long long)m * L.ld));
+        if (ev) {
+            LCX_CUDA(cudaEventRecord(ev[2], s->stream));
+            s->prof_pending++;
+        }
     }
     LCX_CUDA(cudaGetLastError());
     if (s->hook) {

@@ -1,0 +1,99 @@
+"""CPU-only checks: the C-ABI library loads and exports every symbol the header declares, the
+workspace layout arithmetic works without a GPU, the product refuses to run without CUDA (no CPU
+fallback), and the host-side helpers behave."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_symbols():
+    src = open(os.path.join(ROOT, "include", "lcx_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(lcx_[a-z0-9_]+)\s*\(", src)) - {"lcx_allreduce_fn"})
+
+
+def test_library_exports_every_declared_symbol():
+    from linearcorex_b200 import _lib
+    lib = _lib.load()
+    declared = _header_symbols()
+    assert len(declared) >= 30
+    for name in declared:
+        assert hasattr(lib, name), "liblcx_b200.so lacks %s" % name
+    assert sorted(_lib.SIGNATURES) == declared, set(_lib.SIGNATURES) ^ set(declared)
+    assert lib.lcx_version() >= 100
+
+
+def test_layout_arithmetic_without_gpu():
+    from linearcorex_b200 import _lib
+    lib = _lib.load()
+    assert lib.lcx_ld(50) == 64 and lib.lcx_ld(10000) == 10000 and lib.lcx_ld(5) == 16
+    assert lib.lcx_ldy(100) == 104 and lib.lcx_ldy(5) == 8
+    small = lib.lcx_workspace_doubles(2000, 50, 5)
+    big = lib.lcx_workspace_doubles(100000, 10000, 100)
+    assert 0 < small < big
+    # config 3 workspace: Y (100000 x 104) + ~20 m x n arrays + split-K partials, well under 1 GB
+    assert big * 8 < 1.0e9
+    assert lib.lcx_workspace_doubles(-1, 10, 2) < 0
+    assert lib.lcx_colstats_scratch_doubles(100000, 10000) > 0
+    assert lib.lcx_project_scratch_doubles(100000, 100) >= 782 * 104
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    from linearcorex_b200 import Corex, _lib
+    with pytest.raises(_lib.LcxError):
+        Corex(n_hidden=2, seed=0).fit(np.random.RandomState(0).randn(20, 6))
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "linearcorex_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "corex_oracle" not in text and "/root/reference" not in text, f
+
+
+def test_constructor_mirrors_reference_signature():
+    from linearcorex_b200 import Corex
+    c = Corex()
+    assert (c.m, c.max_iter, c.tol, c.anneal, c.missing_values, c.discourage_overlap, c.gaussianize) == \
+        (10, 10000, 1e-5, True, None, True, 'standard')
+    assert c.ws.shape == (0, 0) and c.moments == {} and c.theta is None and c.eps == 0
+    # seeding the global legacy RNG at construction (linearcorex.py:89)
+    Corex(seed=3)
+    a = np.random.randn(2)
+    np.random.seed(3)
+    assert np.array_equal(a, np.random.randn(2))
+    assert Corex(eliminate_synergy=False).discourage_overlap is False
+    with pytest.raises(ValueError):
+        Corex(gaussianize="empirical")
+
+
+def test_shard_rows_partition():
+    from linearcorex_b200 import shard_rows
+    for n, w in ((10, 3), (100000, 8), (7, 8), (1, 1)):
+        spans = [shard_rows(n, r, w) for r in range(w)]
+        assert spans[0][0] == 0 and spans[-1][1] == n
+        assert all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))
+        sizes = [b - a for a, b in spans]
+        assert max(sizes) - min(sizes) <= 1
+
+
+def test_bench_data_is_row_shardable():
+    import sys
+    sys.path.insert(0, ROOT)
+    import bench
+    full = bench.make_rows(10000, 64, 4, 0, 10000, threads=2)
+    part = bench.make_rows(10000, 64, 4, 3000, 9000, threads=2)
+    assert np.array_equal(full[3000:9000], part)
+    assert abs(full.std() - 1.0) < 0.02
+    # planted structure: variables i and i+4 share a parent
+    c = np.corrcoef(full[:, 0], full[:, 4])[0, 1]
+    assert 0.4 < c < 0.6
