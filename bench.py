@@ -181,7 +181,8 @@ def run_reference(args, shape):
 
 def workload_name(args, shape):
     return "%s: synthetic latent-factor data N=%d x n=%d, m=%d, %s mode" % (
-        args.workload, shape[0], shape[1], shape[2], "FP64" if args.precision == "fp64" else "fast (3xTF32)")
+        args.workload, shape[0], shape[1], shape[2],
+        {"fp64": "FP64 (DMMA)", "fp64_split": "FP64 (split-int8 x6 on tcgen05)", "fast": "fast (split-int8 x4)"}[args.precision])
 
 
 # ----------------------------------------------------------------------------------------------------
@@ -307,7 +308,8 @@ def run_ours(args, shape):
     line = {
         "metric": METRIC, "value": it_s, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-        "dtype": "f64" if args.precision == "fp64" else "tf32x3", "data": "synthetic",
+        "dtype": {"fp64": "f64", "fp64_split": "f64 (int8x6 split products, int32/f64 accumulation)",
+                  "fast": "int8x4 split products"}[args.precision], "data": "synthetic",
         "config": {"workload": workload_name(args, shape), "n_samples": n_total, "n_variables": n_vars,
                    "n_factors": n_factors, "rows_per_gpu": n_local, "parallelism": "sample-sharded x%d" % world,
                    "l2": "inputs_exceed_l2 (X~ block is %.1f GB per GPU)" % (n_local * n_vars * 8 / 1e9),
@@ -341,7 +343,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="config3", choices=sorted(WORKLOADS))
-    ap.add_argument("--precision", default="fp64", choices=["fp64", "fast"])
+    ap.add_argument("--precision", default="fp64", choices=["fp64", "fp64_split", "fast"])
     ap.add_argument("--gaussianize", default="standard")
     ap.add_argument("--rows", type=int, default=0)
     ap.add_argument("--vars", type=int, default=0)

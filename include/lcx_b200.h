@@ -43,7 +43,9 @@ extern "C" {
 
 /* precision modes */
 #define LCX_PRECISION_FP64 0   /* DMMA (mma.sync m8n8k4 f64) contractions, everything in binary64 */
-#define LCX_PRECISION_FAST 1   /* fp32-equivalent 3xTF32 tcgen05 contractions for the two X passes  */
+#define LCX_PRECISION_FAST 1   /* opt-in fast mode: split-integer tcgen05 (kind::i8) X contractions, 4 digits = 28 bits */
+#define LCX_PRECISION_FP64_SPLIT 2 /* FP64-faithful split-integer tcgen05 X contractions, 6 digits = 42 bits below the
+                                      row/column maximum (validated against FP64 at 1e-9), everything else binary64 */
 
 /* input dtypes of raw X */
 #define LCX_F32 0
@@ -108,7 +110,7 @@ int lcx_profile_read(lcx_session* s, double* k1_ms, double* k2_ms, long long* pa
 long long lcx_ld(int n_vars);                       /* leading dimension of m x n arrays */
 long long lcx_ldy(int n_factors);                   /* leading dimension of Y            */
 /* Doubles the caller must provide to lcx_bind for a problem of this size. */
-long long lcx_workspace_doubles(long long n_rows_local, int n_vars, int n_factors);
+long long lcx_workspace_doubles(long long n_rows_local, int n_vars, int n_factors, int precision);
 /* Bind a preprocessed data block X~ (n_rows_local x n_vars, fp64, ld = ldx) and a workspace.
  * n_rows_total = sum of n_rows_local over ranks (the reference's n_samples, :110). */
 int lcx_bind(lcx_session* s, const double* xt, long long n_rows_local, long long n_rows_total, int n_vars,

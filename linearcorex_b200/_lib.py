@@ -9,7 +9,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "liblcx_b200.so")
 
 OK, QUICK_FAIL = 0, 1
-PRECISION_FP64, PRECISION_FAST = 0, 1
+PRECISION_FP64, PRECISION_FAST, PRECISION_FP64_SPLIT = 0, 1, 2
+PRECISIONS = {"fp64": PRECISION_FP64, "fast": PRECISION_FAST, "fp64_split": PRECISION_FP64_SPLIT}
 F32, F64 = 0, 1
 GAUSS = {"standard": 0, "outliers": 1, "none": 2}
 
@@ -36,7 +37,7 @@ SIGNATURES = {
     "lcx_profile_read": (_i, [_p, _pd, _pd, _pll, _i]),
     "lcx_ld": (_ll, [_i]),
     "lcx_ldy": (_ll, [_i]),
-    "lcx_workspace_doubles": (_ll, [_ll, _i, _i]),
+    "lcx_workspace_doubles": (_ll, [_ll, _i, _i, _i]),
     "lcx_bind": (_i, [_p, _p, _ll, _ll, _i, _ll, _i, _p, _ll]),
     "lcx_array_info": (_i, [_p, _i, _i, _pll, _pll, _pll, _pll]),
     "lcx_colstats_sum": (_i, [_p, _p, _i, _ll, _i, _ll, _i, _d, _p, _p, _p, _ll]),

@@ -16,8 +16,12 @@ device session raises.
 Extensions over the reference signature (all keyword-only in spirit, defaults keep reference
 behaviour):
   eliminate_synergy   README/docstring name of `discourage_overlap` (README.md:32)
-  precision           'fp64' (default): all arithmetic binary64, parity target = the reference's
-                      numpy float64 path.  'fast': 3xTF32 tensor-core X contractions.
+  precision           'fp64' (default): all arithmetic binary64 (DMMA tensor-core contractions), parity
+                      target = the reference's numpy float64 path.
+                      'fp64_split': the two X contractions run as exact int8 digit products on tcgen05
+                      (6 digits = 42 bits below each row/column maximum, validated to the same 1e-9),
+                      everything else binary64.
+                      'fast': the same engine with 4 digits (28 bits; opt-in, 1e-4 tolerance).
   exact_trials        False (default): backtracking trials are evaluated through the linearity of
                       `_sig` (rho(W + eta U) = rho(W) + eta _sig(U)) -- one pass pair over X per
                       iteration instead of one per trial.  True: every trial
@@ -47,6 +51,7 @@ class _DeviceSession(object):
 
     def __init__(self, precision, device=None):
         torch = _torch()
+        self.precision = precision
         self.lib = _lib.load()
         if not torch.cuda.is_available():
             raise _lib.LcxError("no CUDA device: linearcorex_b200 has no CPU path")
@@ -82,7 +87,7 @@ class _DeviceSession(object):
     def bind(self, xt, n_rows_total, n_vars, n_factors, reducer):
         torch = _torch()
         n_local = xt.shape[0]
-        need = self.lib.lcx_workspace_doubles(n_local, n_vars, n_factors)
+        need = self.lib.lcx_workspace_doubles(n_local, n_vars, n_factors, self.precision)
         if need <= 0:
             raise _lib.LcxError("bad problem shape")
         self.ws = torch.zeros(need, dtype=torch.float64, device=self.device)
@@ -139,8 +144,8 @@ class Corex(object):
         if gaussianize not in ('standard', 'outliers', 'none'):
             raise ValueError("gaussianize must be 'standard', 'outliers' or 'none' "
                              "('empirical' is not supported: the reference itself cannot invert it, :425)")
-        if precision not in ('fp64', 'fast'):
-            raise ValueError("precision must be 'fp64' or 'fast'")
+        if precision not in _lib.PRECISIONS:
+            raise ValueError("precision must be one of %s" % sorted(_lib.PRECISIONS))
         if input_dtype not in ('float64', 'float32'):
             raise ValueError("input_dtype must be 'float64' or 'float32'")
         self.precision = precision
@@ -195,8 +200,7 @@ class Corex(object):
     # ------------------------------------------------------------------------------------------
     def _session(self):
         if self._sess is None:
-            prec = _lib.PRECISION_FP64 if self.precision == 'fp64' else _lib.PRECISION_FAST
-            self._sess = _DeviceSession(prec, self._device)
+            self._sess = _DeviceSession(_lib.PRECISIONS[self.precision], self._device)
         return self._sess
 
     def _reducer(self):
@@ -536,7 +540,7 @@ class Corex(object):
                                    ldy, None, None, 0), "lcx_project")
         y_host = y[:, :self.m].cpu().numpy().copy()
         if details:
-            other = _DeviceSession(_lib.PRECISION_FP64 if self.precision == 'fp64' else _lib.PRECISION_FAST, self._device)
+            other = _DeviceSession(_lib.PRECISIONS[self.precision], self._device)
             red = self._reducer()
             other.bind(xt, int(red.sum_scalar(ns)), nv, self.m, red)
             _lib.check(lib.lcx_set_w(other.h, w.ctypes.data_as(C.c_void_p), nv), "lcx_set_w")

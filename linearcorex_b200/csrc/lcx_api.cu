@@ -8,6 +8,7 @@
 #include "common.cuh"
 #include "corex_kernels.cuh"
 #include "dgemm_mma.cuh"
+#include "ozaki_i8.cuh"
 #include "preprocess_kernels.cuh"
 
 namespace lcx {
@@ -49,6 +50,12 @@ enum {
     I_RYINV,            // m x ldm
     I_AUG,              // m x 2m
     I_STATUS,           // 2 doubles (int status of the inverse)
+    I_XS,               // split modes: int8 digit slices of X~   [S][N_local][ld8]
+    I_AS,               //              int8 digit slices of A    [S][m][ld8]
+    I_YS,               //              int8 digit slices of Y    [S][N_local][ldy8]
+    I_OZV,              //              scales: x(16) | a(ldm) | c(ldm) | y(ldm) | d(ldm)
+    I_YSTAT,            //              per-slab column max / sum of squares of Y
+    I_AMAX,             //              per-CTA partial max |X~|
     I_COUNT
 };
 
@@ -62,13 +69,28 @@ struct Layout {
     long long ld, ldm, ldy;
     GemmPlan plan_k1, plan_k2, plan_mm, plan_mn;  // K1, K2, (m x m over n), (m x n over m)
     int nstrips;
+    // split-integer modes (ozaki_i8.cuh)
+    int S;                       // digits per operand, 0 = DMMA mode
+    long long ld8, ldy8;         // byte leading dimensions of the X~/A and Y slices
+    int oz_splits, oz_chunk;     // split-K of the second contraction
+    int ystat_slabs;
 };
+
+static int digits_for(int precision) {
+    if (precision == LCX_PRECISION_FP64) return 0;
+    const char* env = getenv("LCX_SPLIT_DIGITS");
+    if (env && atoi(env) >= 3 && atoi(env) <= 6) return atoi(env);
+    return precision == LCX_PRECISION_FAST ? 4 : 6;
+}
+constexpr int kYStatRows = 2048;
+constexpr int kAmaxCtas = 592;
 
 static long long align16(long long v) { return round_up(v, 16); }
 
-static Layout make_layout(long long Nl, int n, int m) {
+static Layout make_layout(long long Nl, int n, int m, int precision) {
     Layout L;
     memset(&L, 0, sizeof(L));
+    L.S = digits_for(precision);
     L.ld = round_up(n, 16);
     L.ldm = round_up(m, 16);
     L.ldy = round_up(m, 8);
@@ -131,6 +153,37 @@ static Layout make_layout(long long Nl, int n, int m) {
     put1(I_RYINV, mn, m, L.ldm);
     put1(I_AUG, mn, 2 * mn, 2 * mn);
     put1(I_STATUS, 1, 2, 2);
+    if (L.S > 0) {
+        L.ld8 = round_up(n, 128);
+        L.ldy8 = round_up(m, 128);
+        // second contraction: 128 x 64 tiles over (factors x variables), split over samples to fill whole waves;
+        // at most 65536 samples per split keeps every int32 accumulator exact (<= 6 * 2^16 * 2^12 < 2^31)
+        const long long tiles = (long long)cdiv(n, oz::kBN) * cdiv(m, oz::kBM);
+        const int kblocks = cdiv(Nl, oz::kBK);
+        int best = 1;
+        double best_score = -1.0;
+        const int smin = cdiv(Nl, 65536), smax = (int)min(64LL, (long long)max(1, kblocks / 8));
+        for (int sp = smin; sp <= max(smin, smax); ++sp) {
+            const long long ctas = tiles * sp;
+            const long long waves = (ctas + kSMs - 1) / kSMs;
+            const double kb = (double)kblocks / sp;
+            const double score = (double)ctas / (double)(waves * kSMs) * kb / (kb + 8.0);
+            if (score > best_score + 1e-9) { best_score = score; best = sp; }
+        }
+        L.oz_chunk = (int)round_up(cdiv(Nl, best), oz::kBK);
+        L.oz_splits = cdiv(Nl, L.oz_chunk);
+        L.ystat_slabs = cdiv(Nl, kYStatRows);
+        const long long part = (long long)L.oz_splits * mn * L.ld;
+        if (part > L.slot[I_PART][0].cols) {  // grow the split-K partial buffer (it is the last big slot before these)
+            put1(I_PART, 1, part, part);
+        }
+        put1(I_XS, 1, cdiv((long long)L.S * Nl * L.ld8, 8), cdiv((long long)L.S * Nl * L.ld8, 8));
+        put1(I_AS, 1, cdiv((long long)L.S * mn * L.ld8, 8), cdiv((long long)L.S * mn * L.ld8, 8));
+        put1(I_YS, 1, cdiv((long long)L.S * Nl * L.ldy8, 8), cdiv((long long)L.S * Nl * L.ldy8, 8));
+        put1(I_OZV, 1, 16 + 4 * L.ldm, 16 + 4 * L.ldm);
+        put1(I_YSTAT, (long long)L.ystat_slabs * 2, m, L.ldm);
+        put1(I_AMAX, 1, kAmaxCtas, kAmaxCtas);
+    }
     L.total = cur;
     return L;
 }
@@ -156,6 +209,16 @@ struct lcx_session {
     int prof_pending, prof_cap;
     double prof_k1_ms, prof_k2_ms;
     long long prof_pairs;
+    // split-integer modes: TMA descriptors over the digit slices
+    CUtensorMap map_x_k1, map_a_k1, map_y_k2, map_x_k2;
+    int8_t* xs() const { return (int8_t*)(ws + L.slot[I_XS][0].off); }
+    int8_t* as() const { return (int8_t*)(ws + L.slot[I_AS][0].off); }
+    int8_t* ys() const { return (int8_t*)(ws + L.slot[I_YS][0].off); }
+    double* oz_xscale() const { return ws + L.slot[I_OZV][0].off; }
+    double* oz_ascale() const { return ws + L.slot[I_OZV][0].off + 16; }
+    double* oz_cscale() const { return ws + L.slot[I_OZV][0].off + 16 + L.ldm; }
+    double* oz_yscale() const { return ws + L.slot[I_OZV][0].off + 16 + 2 * L.ldm; }
+    double* oz_dscale() const { return ws + L.slot[I_OZV][0].off + 16 + 3 * L.ldm; }
 
     double* ptr(int id, int set = 0) const {
         const int phys = (id <= LCX_A_UJ) ? (set ^ cur) : 0;
@@ -184,7 +247,8 @@ extern "C" const char* lcx_last_error(void) { return g_err; }
 
 extern "C" int lcx_session_create(lcx_session** out, int device, int precision) {
     LCX_REQUIRE(out != nullptr, "out is null");
-    LCX_REQUIRE(precision == LCX_PRECISION_FP64 || precision == LCX_PRECISION_FAST, "unknown precision mode");
+    LCX_REQUIRE(precision == LCX_PRECISION_FP64 || precision == LCX_PRECISION_FAST || precision == LCX_PRECISION_FP64_SPLIT,
+                "unknown precision mode");
     LCX_CUDA(cudaSetDevice(device));
     cudaDeviceProp prop;
     LCX_CUDA(cudaGetDeviceProperties(&prop, device));
@@ -269,9 +333,108 @@ extern "C" int lcx_launch_count(lcx_session* s, long long* launches) {
 extern "C" long long lcx_ld(int n_vars) { return round_up(n_vars, 16); }
 extern "C" long long lcx_ldy(int n_factors) { return round_up(n_factors, 8); }
 
-extern "C" long long lcx_workspace_doubles(long long n_rows_local, int n_vars, int n_factors) {
-    if (n_rows_local < 0 || n_vars <= 0 || n_factors <= 0) return -1;
-    return make_layout(n_rows_local, n_vars, n_factors).total;
+extern "C" long long lcx_workspace_doubles(long long n_rows_local, int n_vars, int n_factors, int precision) {
+    if (n_rows_local < 0 || n_vars <= 0 || n_factors <= 0 || precision < 0 || precision > 2) return -1;
+    return make_layout(n_rows_local, n_vars, n_factors, precision).total;
+}
+
+// ---- split-integer plumbing (ozaki_i8.cuh) -------------------------------------------------------
+template <int S>
+static int oz_slice_x_t(lcx_session* s) {
+    const Layout& L = s->L;
+    oz::absmax_partial_kernel<<<kAmaxCtas, 256, 0, s->stream>>>(s->xt, s->ldx, s->Nl, s->n, s->ws + L.slot[I_AMAX][0].off);
+    LAUNCHED(s);
+    oz::absmax_finish_kernel<<<1, 256, 0, s->stream>>>(s->ws + L.slot[I_AMAX][0].off, kAmaxCtas, s->oz_xscale());
+    LAUNCHED(s);
+    dim3 grid((unsigned)s->Nl, cdiv(L.ld8, 4 * 128));
+    oz::slice_rows_kernel<S><<<grid, 128, 0, s->stream>>>(s->xt, s->ldx, (int)s->Nl, s->n, nullptr, s->oz_xscale(), s->xs(), L.ld8,
+                                                        s->Nl * L.ld8);
+    LAUNCHED(s);
+    LCX_CUDA(cudaGetLastError());
+    return 0;
+}
+
+static int oz_prepare(lcx_session* s) {
+    const Layout& L = s->L;
+    LCX_REQUIRE(s->n <= 65536, "split-integer modes support at most 65536 variables per contraction (int32 exactness)");
+    switch (L.S) {
+        case 3: LCX_TRY(oz_slice_x_t<3>(s)); break;
+        case 4: LCX_TRY(oz_slice_x_t<4>(s)); break;
+        case 5: LCX_TRY(oz_slice_x_t<5>(s)); break;
+        case 6: LCX_TRY(oz_slice_x_t<6>(s)); break;
+        default: return fail(LCX_ERR_STATE, "oz_prepare", "bad digit count");
+    }
+    // X~ slices as the M operand of Y = X~ A^T (K-major: inner = variables) and as the N operand of D = X~^T Y
+    // (MN-major: inner = variables, rows = samples); A slices K-major; Y slices MN-major (inner = factors).
+    LCX_TRY(oz::make_slice_map(&s->map_x_k1, s->xs(), s->n, s->Nl, L.S, L.ld8, s->Nl * L.ld8, oz::kBK, oz::kBM, false));
+    LCX_TRY(oz::make_slice_map(&s->map_a_k1, s->as(), s->n, s->m, L.S, L.ld8, (long long)s->m * L.ld8, oz::kBK, oz::kBN, false));
+    LCX_TRY(oz::make_slice_map(&s->map_y_k2, s->ys(), L.ldy8, s->Nl, L.S, L.ldy8, s->Nl * L.ldy8, oz::kBM, oz::kBK, true));
+    LCX_TRY(oz::make_slice_map(&s->map_x_k2, s->xs(), s->n, s->Nl, L.S, L.ld8, s->Nl * L.ld8, oz::kBN, oz::kBK, false));
+    return 0;
+}
+
+template <int S>
+static int oz_pair_t(lcx_session* s, const double* A, double* svec, cudaEvent_t* ev) {
+    const Layout& L = s->L;
+    const int m = s->m, n = s->n;
+    double* Y = s->ptr(LCX_A_Y);
+    double* D = s->ptr(LCX_A_D);
+    // ---- Y = X~ A^T ----
+    oz::row_scale_kernel<<<m, 256, 0, s->stream>>>(A, L.ld, n, s->oz_ascale());
+    LAUNCHED(s);
+    oz::mul_scale_kernel<<<cdiv(m, 128), 128, 0, s->stream>>>(s->oz_xscale(), s->oz_ascale(), s->oz_cscale(), m);
+    LAUNCHED(s);
+    oz::slice_rows_kernel<S><<<dim3(m, cdiv(L.ld8, 4 * 128)), 128, 0, s->stream>>>(A, L.ld, m, n, s->oz_ascale(), nullptr, s->as(), L.ld8,
+                                                                              (long long)m * L.ld8);
+    LAUNCHED(s);
+    {
+        oz::GemmParams p;
+        memset(&p, 0, sizeof(p));
+        p.C = Y; p.ldc = L.ldy; p.col_scale = s->oz_cscale();
+        p.rows = (int)s->Nl; p.cols = m; p.k_total = n; p.k_chunk = (int)round_up(n, oz::kBK);
+        LCX_TRY((oz::launch_oz_gemm<S, true>(s->map_x_k1, s->map_a_k1, p, dim3(cdiv(m, oz::kBN), cdiv(s->Nl, oz::kBM), 1), s->stream)));
+        LAUNCHED(s);
+    }
+    if (ev) LCX_CUDA(cudaEventRecord(ev[1], s->stream));
+    if (ev) LCX_CUDA(cudaEventRecord(ev[3], s->stream));
+    // ---- column max / sum of squares of Y, digit slices of Y ----
+    double* ystat = s->ws + L.slot[I_YSTAT][0].off;
+    oz::y_stats_kernel<<<dim3(cdiv(m, 32), L.ystat_slabs), dim3(32, 8), 0, s->stream>>>(Y, L.ldy, s->Nl, m, kYStatRows, ystat, L.ldm);
+    LAUNCHED(s);
+    oz::y_stats_finish_kernel<<<cdiv(m, 128), 128, 0, s->stream>>>(ystat, L.ystat_slabs, L.ldm, m, s->oz_xscale(), svec, s->oz_yscale(),
+                                                                  s->oz_dscale());
+    LAUNCHED(s);
+    oz::slice_cols_kernel<S><<<dim3((unsigned)cdiv(s->Nl, 8), cdiv(L.ldy8, 4 * 32)), dim3(32, 8), 0, s->stream>>>(
+        Y, L.ldy, s->Nl, m, s->oz_yscale(), s->ys(), L.ldy8, s->Nl * L.ldy8);
+    LAUNCHED(s);
+    // ---- D = (X~^T Y)^T, factor-major, split over samples ----
+    {
+        oz::GemmParams p;
+        memset(&p, 0, sizeof(p));
+        const bool split = L.oz_splits > 1;
+        p.C = split ? s->ptr(I_PART) : D;
+        p.ldc = L.ld; p.c_split_stride = split ? (long long)m * L.ld : 0;
+        p.row_scale = s->oz_dscale();
+        p.rows = m; p.cols = n; p.k_total = (int)s->Nl; p.k_chunk = L.oz_chunk;
+        LCX_TRY((oz::launch_oz_gemm<S, false>(s->map_y_k2, s->map_x_k2, p, dim3(cdiv(n, oz::kBN), cdiv(m, oz::kBM), L.oz_splits), s->stream)));
+        LAUNCHED(s);
+        if (split) {
+            LCX_TRY(launch_reduce_splits(s->ptr(I_PART), L.oz_splits, (long long)m * L.ld, D, m, n, L.ld, s->stream));
+            LAUNCHED(s);
+        }
+    }
+    LCX_CUDA(cudaGetLastError());
+    return 0;
+}
+
+static int oz_pair(lcx_session* s, const double* A, double* svec, cudaEvent_t* ev) {
+    switch (s->L.S) {
+        case 3: return oz_pair_t<3>(s, A, svec, ev);
+        case 4: return oz_pair_t<4>(s, A, svec, ev);
+        case 5: return oz_pair_t<5>(s, A, svec, ev);
+        case 6: return oz_pair_t<6>(s, A, svec, ev);
+    }
+    return fail(LCX_ERR_STATE, "oz_pair", "bad digit count");
 }
 
 extern "C" int lcx_bind(lcx_session* s, const double* xt, long long n_rows_local, long long n_rows_total, int n_vars,
@@ -282,7 +445,7 @@ extern "C" int lcx_bind(lcx_session* s, const double* xt, long long n_rows_local
     LCX_REQUIRE(n_vars > 0 && n_factors > 0, "bad shape");
     LCX_REQUIRE(ldx >= n_vars && ldx % 2 == 0, "ldx must be even and >= n_vars");
     LCX_REQUIRE(((uintptr_t)xt % 16 == 0) && ((uintptr_t)workspace % 128 == 0), "misaligned device pointer");
-    Layout L = make_layout(n_rows_local, n_vars, n_factors);
+    Layout L = make_layout(n_rows_local, n_vars, n_factors, s->precision);
     LCX_REQUIRE(workspace_doubles >= L.total, "workspace too small (see lcx_workspace_doubles)");
     LCX_CUDA(cudaSetDevice(s->device));
     s->xt = xt;
@@ -300,6 +463,7 @@ extern "C" int lcx_bind(lcx_session* s, const double* xt, long long n_rows_local
     LCX_CUDA(cudaMemsetAsync(workspace, 0, (size_t)y_off * sizeof(double), s->stream));
     const long long y_end = align16(y_off + n_rows_local * L.ldy);
     LCX_CUDA(cudaMemsetAsync(workspace + y_end, 0, (size_t)(L.total - y_end) * sizeof(double), s->stream));
+    if (L.S > 0) LCX_TRY(oz_prepare(s));  // digit slices of X~ (after this X~ itself is no longer read)
     return 0;
 }
 
@@ -455,6 +619,13 @@ static int xpair(lcx_session* s, const double* A, bool want_colsq) {
     cudaEvent_t* ev = nullptr;
     if (s->prof_on && s->prof_pending < s->prof_cap) ev = s->prof_ev + 4 * s->prof_pending;
     if (ev) LCX_CUDA(cudaEventRecord(ev[0], s->stream));
+    if (L.S > 0) {
+        LCX_TRY(oz_pair(s, A, svec, ev));
+        if (ev) {
+            LCX_CUDA(cudaEventRecord(ev[2], s->stream));
+            s->prof_pending++;
+        }
+    } else {
     {   // K1
         GemmArgs a;
         memset(&a, 0, sizeof(a));
@@ -483,6 +654,7 @@ static int xpair(lcx_session* s, const double* A, bool want_colsq) {
             LCX_CUDA(cudaEventRecord(ev[2], s->stream));
             s->prof_pending++;
         }
+    }
     }
     LCX_CUDA(cudaGetLastError());
     if (s->hook) {

@@ -1,0 +1,486 @@
+// Split-integer ("Ozaki") emulation of the two FP64 X contractions on the 5th-generation tensor cores.
+//
+//   Y = X~ A^T      (linearcorex.py:247 / :210)      K-major  x K-major   operands
+//   D = X~^T Y      (linearcorex.py:259 / :211)      MN-major x MN-major  operands
+//
+// tcgen05.mma has no f64 kind, but kind::i8 multiplies int8 digits exactly into int32 TMEM accumulators.
+// Each fp64 operand is written as a fixed-point number with S signed 7-bit digits ("slices"):
+//     v = 2^E * sum_{k=1..S} d_k 2^(-7k),   d_k in [-64, 64]
+// with one exponent E for all of X~ (standardised data is bounded; chosen from max|X~|), one per factor
+// row of A and one per factor column of Y.  The product is then
+//     sum_i x_i a_i = 2^(Ex+Ea) * sum_{g=2..S+1} 2^(-7g) * P_g,   P_g = sum_{k+l=g} sum_i dx_k[i] da_l[i]
+// where every P_g is an exact int32 dot product (|d d'| <= 2^12, so 2^19 terms fit).  Pairs with k+l > S+1
+// are dropped (they sit below the digits that were truncated anyway).  S = 6 keeps 42 bits below the row/
+// column maximum -- the FP64-faithful mode, validated against FP64 at 1e-9 on every parity case; S = 3 is
+// the opt-in fast mode (21 bits, fp32-equivalent like 3xTF32 but at 3 bytes/element and int8 rates).
+//
+// One CTA owns a 128 x 64 output tile and S accumulators of 64 TMEM columns (group g at column 64 (g-2)).
+// Warp 0 streams operand slices with TMA (cp.async.bulk.tensor, 64 B / 128 B swizzle) through a 3-stage
+// mbarrier ring; warp 1 issues the S(S+1)/2 tcgen05.mma per 32-deep K step and commits to the ring;
+// warps 2-5 drain TMEM (tcgen05.ld), recombine the groups in fp64 (Horner from the smallest weight) and
+// store.  The same row-major int8 image of X~ feeds both contractions: K-major as the M operand of the
+// first, MN-major as the N operand of the second, so X~ is stored once (S bytes per element, less than fp64).
+#pragma once
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace lcx {
+namespace oz {
+
+constexpr int kBM = 128;      // output rows per CTA (UMMA M)
+constexpr int kBN = 64;       // output cols per CTA (UMMA N)
+constexpr int kBK = 64;       // contraction depth per pipeline stage (two UMMA K=32 steps)
+constexpr int kStages = 3;
+constexpr int kThreads = 192; // warp 0 TMA, warp 1 MMA, warps 2..5 epilogue
+
+// ---- PTX wrappers ----------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+            smem_u32(dst)),
+        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols));
+}
+__device__ __forceinline__ void umma_i8(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate));
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start address >> 4 in [0,14), leading byte
+// offset >> 4 in [16,30), stride byte offset >> 4 in [32,46), version = 1 in [46,48), layout type in [61,64)
+// (2 = SWIZZLE_128B, 4 = SWIZZLE_64B).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)(layout & 7) << 61;
+    return d;
+}
+
+// Instruction descriptor (cute::UMMA::InstrDescriptor) for kind::i8: c_format = S32 (2) at [4,6), a/b format =
+// INT8 (1) at [7,10)/[10,13), a/b major at 15/16 (0 = K, 1 = MN), N >> 3 at [17,23), M >> 4 at [24,29).
+__host__ __device__ constexpr uint32_t make_idesc_i8(int M, int N, int a_mn, int b_mn) {
+    return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) | ((uint32_t)(N >> 3) << 17) |
+           ((uint32_t)(M >> 4) << 24);
+}
+
+struct GemmParams {
+    double* C;                   // fp64 output, row-major [rows][ldc] (+ z * c_split_stride)
+    long long ldc;
+    long long c_split_stride;
+    const double* row_scale;     // optional per-output-row factor (2^(Ex + Ey_j) for D)
+    const double* col_scale;     // optional per-output-col factor (2^(Ex + Ea_j) for Y)
+    int rows, cols;              // valid output extent
+    int k_total;                 // contraction length
+    int k_chunk;                 // contraction range per blockIdx.z (multiple of kBK)
+};
+
+// KMAJOR = true : A tile = [128 rows][64 B of K]  (SW64), B tile = [64 rows][64 B of K]  (SW64); tensor maps are
+//                 (K, rows, slice); TMA coordinates (k0, row0, s).
+// KMAJOR = false: A tile = [64 K rows][128 B of M] (SW128), B tile = [64 K rows][64 B of N] (SW64); tensor maps are
+//                 (M or N, K rows, slice); TMA coordinates (m0 or n0, k0, s).
+template <int S, bool KMAJOR>
+__global__ void __launch_bounds__(kThreads, 1)
+oz_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const GemmParams p) {
+    constexpr int A_BYTES = kBM * kBK;          // 8 KB per slice either way
+    constexpr int B_BYTES = kBN * kBK;          // 4 KB per slice
+    constexpr int STAGE_BYTES = S * (A_BYTES + B_BYTES);
+    constexpr uint32_t TMEM_COLS = (S * kBN <= 128) ? 128 : (S * kBN <= 256 ? 256 : 512);
+    static_assert(S * kBN <= 512, "accumulators exceed TMEM");
+
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    __shared__ __align__(8) uint64_t full_bar[kStages];
+    __shared__ __align__(8) uint64_t empty_bar[kStages];
+    __shared__ __align__(8) uint64_t tmem_full_bar;
+    __shared__ uint32_t tmem_base_smem;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_tile = blockIdx.x, m_tile = blockIdx.y;
+    const int kbeg = blockIdx.z * p.k_chunk;
+    const int kend = min(p.k_total, kbeg + p.k_chunk);
+    const int num_kb = (kend > kbeg) ? (kend - kbeg + kBK - 1) / kBK : 0;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB) : "memory");
+        for (int i = 0; i < kStages; ++i) {
+            mbar_init(&full_bar[i], 1);
+            mbar_init(&empty_bar[i], 1);
+        }
+        mbar_init(&tmem_full_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) tmem_alloc(&tmem_base_smem, TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_smem;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int st = kb % kStages;
+                const uint32_t ph = (kb / kStages) & 1;
+                mbar_wait(&empty_bar[st], ph ^ 1);
+                uint8_t* sa = smem + st * STAGE_BYTES;
+                uint8_t* sb = sa + S * A_BYTES;
+                mbar_expect_tx(&full_bar[st], STAGE_BYTES);
+                const int k0 = kbeg + kb * kBK;
+#pragma unroll
+                for (int s = 0; s < S; ++s) {
+                    if (KMAJOR) {
+                        tma_load_3d(sa + s * A_BYTES, &mapA, &full_bar[st], k0, m_tile * kBM, s);
+                        tma_load_3d(sb + s * B_BYTES, &mapB, &full_bar[st], k0, n_tile * kBN, s);
+                    } else {
+                        tma_load_3d(sa + s * A_BYTES, &mapA, &full_bar[st], m_tile * kBM, k0, s);
+                        tma_load_3d(sb + s * B_BYTES, &mapB, &full_bar[st], n_tile * kBN, k0, s);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer (one elected lane) =====
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_i8(kBM, kBN, KMAJOR ? 0 : 1, KMAJOR ? 0 : 1);
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int st = kb % kStages;
+                const uint32_t ph = (kb / kStages) & 1;
+                mbar_wait(&full_bar[st], ph);
+                tc_fence_after();
+                const uint32_t sa = smem_u32(smem + st * STAGE_BYTES);
+                const uint32_t sb = sa + S * A_BYTES;
+#pragma unroll
+                for (int kk = 0; kk < kBK / 32; ++kk) {
+#pragma unroll
+                    for (int ka = 0; ka < S; ++ka) {
+#pragma unroll
+                        for (int kq = 0; kq < S - ka; ++kq) {
+                            uint64_t da, db;
+                            if (KMAJOR) {
+                                // rows at 64 B pitch, 8-row swizzle atoms of 512 B; a K step is +32 B inside the span
+                                da = make_smem_desc(sa + ka * A_BYTES + kk * 32, 16, 512, 4);
+                                db = make_smem_desc(sb + kq * B_BYTES + kk * 32, 16, 512, 4);
+                            } else {
+                                // A: K rows of 128 B (SW128, atoms of 8 rows = 1 KB); a K step is 32 rows = 4 KB
+                                // B: K rows of 64 B  (SW64,  atoms of 8 rows = 512 B); a K step is 32 rows = 2 KB
+                                da = make_smem_desc(sa + ka * A_BYTES + kk * 4096, 8192, 1024, 2);
+                                db = make_smem_desc(sb + kq * B_BYTES + kk * 2048, 4096, 512, 4);
+                            }
+                            const uint32_t acc = (kb > 0 || kk > 0 || ka > 0) ? 1u : 0u;
+                            umma_i8(tmem_base + (uint32_t)(ka + kq) * kBN, da, db, idesc, acc);
+                        }
+                    }
+                }
+                umma_commit(&empty_bar[st]);  // frees the stage once these MMAs have read it
+            }
+            umma_commit(&tmem_full_bar);
+        }
+    } else {
+        // ===== epilogue: TMEM -> registers -> fp64 recombination -> global =====
+        const int quarter = warp & 3;              // TMEM lane quarter this warp may read
+        const int row_in_tile = quarter * 32 + lane;
+        const int row = m_tile * kBM + row_in_tile;
+        mbar_wait(&tmem_full_bar, 0);
+        tc_fence_after();
+        double* C = p.C + (long long)blockIdx.z * p.c_split_stride;
+        const double rs = (p.row_scale != nullptr && row < p.rows) ? p.row_scale[row] : 1.0;
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+#pragma unroll 1
+        for (int c0 = 0; c0 < kBN; c0 += 16) {
+            double acc[16];
+            if (num_kb > 0) {
+                uint32_t r[16];
+                tmem_ld16(lane_addr + (uint32_t)((S - 1) * kBN + c0), r);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 16; ++j) acc[j] = (double)(int)r[j];
+#pragma unroll
+                for (int g = S - 2; g >= 0; --g) {
+                    tmem_ld16(lane_addr + (uint32_t)(g * kBN + c0), r);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) acc[j] = acc[j] * 0.0078125 + (double)(int)r[j];  // 2^-7 per group
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) acc[j] = 0.0;
+            }
+            if (row < p.rows) {
+                const int col0 = n_tile * kBN + c0;
+#pragma unroll
+                for (int j = 0; j < 16; j += 2) {
+                    const int col = col0 + j;
+                    // group g = 0 carries weight 2^-14 (digits k = l = 1)
+                    double v0 = acc[j] * 6.103515625e-05 * rs, v1 = acc[j + 1] * 6.103515625e-05 * rs;
+                    if (p.col_scale != nullptr) {
+                        if (col < p.cols) v0 *= p.col_scale[col];
+                        if (col + 1 < p.cols) v1 *= p.col_scale[col + 1];
+                    }
+                    if (col + 1 < p.cols) {
+                        *reinterpret_cast<double2*>(C + (long long)row * p.ldc + col) = make_double2(v0, v1);
+                    } else if (col < p.cols) {
+                        C[(long long)row * p.ldc + col] = v0;
+                    }
+                }
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+// ---- digit extraction -----------------------------------------------------------------------------
+// v = x * 2^-E in (-0.5, 0.5);  repeat: t = 128 v, d = rint(t), v = t - d   (all exact in binary64).
+template <int S>
+__device__ __forceinline__ void split_digits(double x, double inv_scale, int8_t (&d)[S]) {
+    double v = x * inv_scale;
+#pragma unroll
+    for (int k = 0; k < S; ++k) {
+        const double t = v * 128.0;
+        const double r = rint(t);
+        d[k] = (int8_t)(int)r;
+        v = t - r;
+    }
+}
+
+// Power-of-two scale 2^E with max * 2^-E < 0.5 (so the first digit stays within [-64, 64]).
+__device__ __forceinline__ double pow2_above(double amax) {
+    if (!(amax > 0.0) || !isfinite(amax)) return 1.0;
+    int e;
+    frexp(amax, &e);       // amax = f * 2^e, f in [0.5, 1)
+    return ldexp(1.0, e + 1);
+}
+
+// Slices of a row-major fp64 matrix [rows][ld_in] into out[s][rows][ld_out] (int8), one scale per row
+// (row_scale != nullptr: value 2^E_row) or a single scale.  Columns in [cols, ld_out) are zero-filled.
+template <int S>
+__global__ void slice_rows_kernel(const double* __restrict__ in, long long ld_in, int rows, int cols,
+                                  const double* __restrict__ row_scale, const double* __restrict__ one_scale,
+                                  int8_t* __restrict__ out, long long ld_out, long long slice_stride) {
+    const long long r = blockIdx.x;  // rows on grid.x (up to 2^31 - 1), column blocks on grid.y
+    const int c4 = (blockIdx.y * blockDim.x + threadIdx.x) * 4;
+    if (r >= rows || c4 >= ld_out) return;
+    const double inv = 1.0 / (row_scale ? row_scale[r] : one_scale[0]);
+    int8_t d[4][S];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int c = c4 + j;
+        const double x = (c < cols) ? in[r * ld_in + c] : 0.0;
+        split_digits<S>(x, inv, d[j]);
+    }
+#pragma unroll
+    for (int k = 0; k < S; ++k) {
+        char4 v = make_char4(d[0][k], d[1][k], d[2][k], d[3][k]);
+        *reinterpret_cast<char4*>(out + (long long)k * slice_stride + r * ld_out + c4) = v;
+    }
+}
+
+// Same with one scale per column (Y for the second contraction: exponent per factor).
+template <int S>
+__global__ void slice_cols_kernel(const double* __restrict__ in, long long ld_in, long long rows, int cols,
+                                  const double* __restrict__ col_scale, int8_t* __restrict__ out, long long ld_out,
+                                  long long slice_stride) {
+    const long long r = (long long)blockIdx.x * blockDim.y + threadIdx.y;
+    const int c4 = (blockIdx.y * blockDim.x + threadIdx.x) * 4;
+    if (r >= rows || c4 >= ld_out) return;
+    int8_t d[4][S];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int c = c4 + j;
+        const double x = (c < cols) ? in[r * ld_in + c] : 0.0;
+        const double inv = (c < cols) ? 1.0 / col_scale[c] : 1.0;
+        split_digits<S>(x, inv, d[j]);
+    }
+#pragma unroll
+    for (int k = 0; k < S; ++k) {
+        char4 v = make_char4(d[0][k], d[1][k], d[2][k], d[3][k]);
+        *reinterpret_cast<char4*>(out + (long long)k * slice_stride + r * ld_out + c4) = v;
+    }
+}
+
+// max |a[r][c]| over a row (one CTA of 256 threads per row) -> scale[r] = 2^E;  used for A (W or grad).
+__global__ void row_scale_kernel(const double* __restrict__ a, long long ld, int cols, double* __restrict__ scale) {
+    __shared__ double scratch[8];
+    const double* ra = a + (long long)blockIdx.x * ld;
+    double mx = 0.0;
+    for (int i = threadIdx.x; i < cols; i += 256) mx = fmax(mx, fabs(ra[i]));
+    mx = block_max_256(mx, scratch);
+    if (threadIdx.x == 0) scale[blockIdx.x] = pow2_above(mx);
+}
+
+// Column statistics of Y (N x ldy): per-slab partial max|Y| and sum Y^2 -> part[slab][2][ldp]
+__global__ void __launch_bounds__(256) y_stats_kernel(const double* __restrict__ y, long long ldy, long long rows, int cols,
+                                                      int rows_per_slab, double* __restrict__ part, long long ldp) {
+    __shared__ double rm[8][32], rs[8][32];
+    const int c = blockIdx.x * 32 + threadIdx.x;
+    const long long r0 = (long long)blockIdx.y * rows_per_slab;
+    const long long r1 = min(rows, r0 + (long long)rows_per_slab);
+    double mx = 0.0, sq = 0.0;
+    if (c < cols) {
+        for (long long r = r0 + threadIdx.y; r < r1; r += 8) {
+            const double v = y[r * ldy + c];
+            mx = fmax(mx, fabs(v));
+            sq += v * v;
+        }
+    }
+    rm[threadIdx.y][threadIdx.x] = mx;
+    rs[threadIdx.y][threadIdx.x] = sq;
+    __syncthreads();
+    if (threadIdx.y == 0 && c < cols) {
+        double a = 0.0, b = 0.0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            a = fmax(a, rm[k][threadIdx.x]);
+            b += rs[k][threadIdx.x];
+        }
+        part[((long long)blockIdx.y * 2 + 0) * ldp + c] = a;
+        part[((long long)blockIdx.y * 2 + 1) * ldp + c] = b;
+    }
+}
+
+// Combine the slab partials: colsq[c] = sum, yscale[c] = 2^E from max; dscale[c] = x_scale * yscale[c]
+__global__ void y_stats_finish_kernel(const double* __restrict__ part, int slabs, long long ldp, int cols,
+                                      const double* __restrict__ x_scale, double* __restrict__ colsq,
+                                      double* __restrict__ yscale, double* __restrict__ dscale) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= cols) return;
+    double mx = 0.0, sq = 0.0;
+    for (int s = 0; s < slabs; ++s) {
+        mx = fmax(mx, part[((long long)s * 2 + 0) * ldp + c]);
+        sq += part[((long long)s * 2 + 1) * ldp + c];
+    }
+    if (colsq) colsq[c] = sq;
+    const double sc = pow2_above(mx);
+    yscale[c] = sc;
+    dscale[c] = x_scale[0] * sc;
+}
+
+// cscale[j] = x_scale * a_scale[j]   (output scale of Y = X~ A^T)
+__global__ void mul_scale_kernel(const double* __restrict__ x_scale, const double* __restrict__ a_scale, double* __restrict__ out,
+                                 int m) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < m) out[j] = x_scale[0] * a_scale[j];
+}
+
+// Global max |x| of the N x n block (per-CTA partial max, then one CTA finishes) -> scale[0] = 2^E
+__global__ void __launch_bounds__(256) absmax_partial_kernel(const double* __restrict__ x, long long ld, long long rows, int cols,
+                                                             double* __restrict__ part) {
+    __shared__ double scratch[8];
+    double mx = 0.0;
+    for (long long r = blockIdx.x; r < rows; r += gridDim.x) {
+        const double* xr = x + r * ld;
+        for (int c = threadIdx.x; c < cols; c += 256) mx = fmax(mx, fabs(xr[c]));
+    }
+    mx = block_max_256(mx, scratch);
+    if (threadIdx.x == 0) part[blockIdx.x] = mx;
+}
+__global__ void absmax_finish_kernel(const double* __restrict__ part, int nparts, double* __restrict__ scale) {
+    __shared__ double scratch[8];
+    double mx = 0.0;
+    for (int i = threadIdx.x; i < nparts; i += 256) mx = fmax(mx, part[i]);
+    mx = block_max_256(mx, scratch);
+    if (threadIdx.x == 0) scale[0] = pow2_above(mx);
+}
+
+// ---- host side -----------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (fn == nullptr) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+// 3-D uint8 tensor map over slices[s][rows][ld]: dims (inner = ld-extent `inner`, rows, s).
+inline int make_slice_map(CUtensorMap* map, const void* base, long long inner, long long rows, int slices, long long ld,
+                          long long slice_stride, int box_inner, int box_rows, bool swizzle128) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return fail(-2, "cuTensorMapEncodeTiled", "driver entry point unavailable");
+    cuuint64_t dims[3] = {(cuuint64_t)inner, (cuuint64_t)rows, (cuuint64_t)slices};
+    cuuint64_t strides[2] = {(cuuint64_t)ld, (cuuint64_t)slice_stride};
+    cuuint32_t box[3] = {(cuuint32_t)box_inner, (cuuint32_t)box_rows, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult rc = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (rc != CUDA_SUCCESS) return fail(-2, "cuTensorMapEncodeTiled", "encode failed (check alignment / strides)");
+    return 0;
+}
+
+template <int S, bool KMAJOR>
+inline int launch_oz_gemm(const CUtensorMap& mapA, const CUtensorMap& mapB, const GemmParams& p, dim3 grid, cudaStream_t st) {
+    constexpr int SMEM = kStages * S * (kBM * kBK + kBN * kBK) + 1024;
+    static bool configured = false;
+    auto kern = oz_gemm_kernel<S, KMAJOR>;
+    if (!configured) {
+        LCX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+        configured = true;
+    }
+    kern<<<grid, kThreads, SMEM, st>>>(mapA, mapB, p);
+    LCX_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace oz
+}  // namespace lcx

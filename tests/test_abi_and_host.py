@@ -32,12 +32,14 @@ def test_layout_arithmetic_without_gpu():
     lib = _lib.load()
     assert lib.lcx_ld(50) == 64 and lib.lcx_ld(10000) == 10000 and lib.lcx_ld(5) == 16
     assert lib.lcx_ldy(100) == 104 and lib.lcx_ldy(5) == 8
-    small = lib.lcx_workspace_doubles(2000, 50, 5)
-    big = lib.lcx_workspace_doubles(100000, 10000, 100)
+    small = lib.lcx_workspace_doubles(2000, 50, 5, 0)
+    big = lib.lcx_workspace_doubles(100000, 10000, 100, 0)
+    split = lib.lcx_workspace_doubles(100000, 10000, 100, 2)
+    assert split > big + 6 * 100000 * 10000 // 8  # six int8 digit planes of X~
     assert 0 < small < big
     # config 3 workspace: Y (100000 x 104) + ~20 m x n arrays + split-K partials, well under 1 GB
     assert big * 8 < 1.0e9
-    assert lib.lcx_workspace_doubles(-1, 10, 2) < 0
+    assert lib.lcx_workspace_doubles(-1, 10, 2, 0) < 0
     assert lib.lcx_colstats_scratch_doubles(100000, 10000) > 0
     assert lib.lcx_project_scratch_doubles(100000, 100) >= 782 * 104
 
