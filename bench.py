@@ -269,9 +269,33 @@ def run_ours(args, shape):
     tc_last = float(mdl.tc)
     it_s = args.steps / (ms / 1e3)
     n_local = hi - lo
-    pair_flops = 4.0 * n_local * n_vars * n_factors           # K1 + K2 of one pass pair on this rank
+    pair_flops = 4.0 * n_local * n_vars * n_factors           # K1 + K2 of one pass pair on this rank (FP64-equivalent)
     pair_ms = (k1.value + k2.value) / max(1, pairs.value)
-    achieved = pair_flops / (pair_ms / 1e3) / 1e12 if pair_ms > 0 else 0.0
+    fp64_equiv = pair_flops / (pair_ms / 1e3) / 1e12 if pair_ms > 0 else 0.0
+    digits = {"fp64": 0, "fp64_split": 6, "fast": 4}[args.precision]
+    if os.environ.get("LCX_SPLIT_DIGITS") and digits:
+        digits = int(os.environ["LCX_SPLIT_DIGITS"])
+    if digits:
+        # split-integer modes: each FP64 multiply-add is S(S+1)/2 exact int8 multiply-adds on tcgen05 (kind::i8)
+        pair_ops = pair_flops * digits * (digits + 1) / 2
+        achieved = pair_ops / (pair_ms / 1e3) / 1e12 if pair_ms > 0 else 0.0
+        peak = 2.0 * float(peaks.get("bf16_tflops", 1590.0))
+        rl_unit = "TOP/s"
+        rl_kernel = ("oz_gemm_kernel<%d,*> (tcgen05.mma kind::i8 + TMA; Y = X~ A^T and X~^T Y as %d int8 digit-plane products "
+                     "each, incl. digit slicing of A and Y), %d pass pairs timed by CUDA events; K1 %.3f ms, K2 %.3f ms per launch; "
+                     "FP64-equivalent %.1f TFLOP/s" % (digits, digits * (digits + 1) // 2, pairs.value,
+                                                        k1.value / max(1, pairs.value), k2.value / max(1, pairs.value), fp64_equiv))
+        rl_source = ("2 x bf16_tflops of MEASURED_PEAKS.json%s (kind::i8 runs at twice the bf16 rate on B200; no int8 entry is "
+                     "measured); cuBLAS DGEMM in this run: %.1f TFLOP/s"
+                     % ("" if "bf16_tflops" in peaks else " [fallback 1590]", dgemm_peak))
+    else:
+        pair_ops = pair_flops
+        achieved, peak, rl_unit = fp64_equiv, dgemm_peak, "TFLOP/s"
+        rl_kernel = ("dgemm_mma_kernel (Y = X~ A^T and X~^T Y, DMMA.8x8x4), %d pass pairs timed by CUDA events; "
+                     "K1 %.3f ms, K2 %.3f ms per launch" % (pairs.value, k1.value / max(1, pairs.value),
+                                                            k2.value / max(1, pairs.value)))
+        rl_source = ("cuBLAS DGEMM 6144^3 measured in this run (MEASURED_PEAKS.json has no FP64 entry; nominal B200 FP64 "
+                     "tensor peak is 40 TFLOP/s); bf16 measured peak for context: %s TF/s" % peaks.get("bf16_tflops"))
     del mdl, sess
     torch.cuda.empty_cache()
 
@@ -315,16 +339,12 @@ def run_ours(args, shape):
                    "l2": "inputs_exceed_l2 (X~ block is %.1f GB per GPU)" % (n_local * n_vars * 8 / 1e9),
                    "trials_per_iteration": trials, "TC_after_timed_region": tc_last},
         "updates_per_sec": it_s * n_total * n_vars * n_factors,
-        "roofline": {"bound": "tensor", "achieved": achieved, "peak": dgemm_peak, "unit": "TFLOP/s",
-                     "frac": achieved / dgemm_peak if dgemm_peak else None, "traffic": args.traffic,
-                     "kernel": "dgemm_mma_kernel (Y = X~ A^T and X~^T Y, DMMA.8x8x4), %d pass pairs timed by CUDA events; "
-                               "K1 %.3f ms, K2 %.3f ms per launch" % (pairs.value, k1.value / max(1, pairs.value),
-                                                                      k2.value / max(1, pairs.value)),
-                     "algorithmic_flops_per_pair": pair_flops,
+        "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": rl_unit,
+                     "frac": achieved / peak if peak else None, "traffic": args.traffic,
+                     "kernel": rl_kernel,
+                     "algorithmic_ops_per_pair": pair_ops, "fp64_equivalent_tflops": fp64_equiv,
                      "share_of_step": pair_ms * pairs.value / ms if ms > 0 else None,
-                     "peak_source": "cuBLAS DGEMM 6144^3 measured in this run (MEASURED_PEAKS.json has no FP64 entry; "
-                                    "nominal B200 FP64 tensor peak is 40 TFLOP/s); bf16 measured peak for context: %s TF/s"
-                                    % peaks.get("bf16_tflops")},
+                     "peak_source": rl_source},
         "clocks": clocks.summary(),
         "e2e": e2e,
         "gpu_launches": int(launches),

@@ -112,7 +112,9 @@ long long lcx_ldy(int n_factors);                   /* leading dimension of Y   
 /* Doubles the caller must provide to lcx_bind for a problem of this size. */
 long long lcx_workspace_doubles(long long n_rows_local, int n_vars, int n_factors, int precision);
 /* Bind a preprocessed data block X~ (n_rows_local x n_vars, fp64, ld = ldx) and a workspace.
- * n_rows_total = sum of n_rows_local over ranks (the reference's n_samples, :110). */
+ * n_rows_total = sum of n_rows_local over ranks (the reference's n_samples, :110).
+ * LCX_PRECISION_FP64: xt must stay valid while the session is bound.  Split modes: xt is converted to int8 digit
+ * planes inside the workspace before lcx_bind returns and may be released by the caller afterwards. */
 int lcx_bind(lcx_session* s, const double* xt, long long n_rows_local, long long n_rows_total, int n_vars,
              long long ldx, int n_factors, double* workspace, long long workspace_doubles);
 /* Offset (in doubles, from the workspace base), rows, cols and leading dimension of an array. */

@@ -95,6 +95,8 @@ class _DeviceSession(object):
         self.n, self.m = n_vars, n_factors
         _lib.check(self.lib.lcx_bind(self.h, xt.data_ptr(), n_local, n_rows_total, n_vars, xt.stride(0), n_factors,
                                      self.ws.data_ptr(), need), "lcx_bind")
+        if self.precision != _lib.PRECISION_FP64:
+            self.xt = None  # the split modes keep int8 digit planes in the workspace; the fp64 block is released
         if reducer is not None and reducer.world > 1:
             ws = self.ws
 

@@ -82,7 +82,7 @@ static int digits_for(int precision) {
     if (env && atoi(env) >= 3 && atoi(env) <= 6) return atoi(env);
     return precision == LCX_PRECISION_FAST ? 4 : 6;
 }
-constexpr int kYStatRows = 2048;
+constexpr int kYStatRows = 512;
 constexpr int kAmaxCtas = 592;
 
 static long long align16(long long v) { return round_up(v, 16); }
@@ -374,7 +374,7 @@ static int oz_prepare(lcx_session* s) {
 }
 
 template <int S>
-static int oz_pair_t(lcx_session* s, const double* A, double* svec, cudaEvent_t* ev) {
+static int oz_pair_t(lcx_session* s, const double* A, double* svec, cudaEvent_t* ev, bool first_only) {
     const Layout& L = s->L;
     const int m = s->m, n = s->n;
     double* Y = s->ptr(LCX_A_Y);
@@ -404,6 +404,10 @@ static int oz_pair_t(lcx_session* s, const double* A, double* svec, cudaEvent_t*
     oz::y_stats_finish_kernel<<<cdiv(m, 128), 128, 0, s->stream>>>(ystat, L.ystat_slabs, L.ldm, m, s->oz_xscale(), svec, s->oz_yscale(),
                                                                   s->oz_dscale());
     LAUNCHED(s);
+    if (first_only) {  // _norm (:215-228): only Y and its column sums of squares are needed
+        LCX_CUDA(cudaGetLastError());
+        return 0;
+    }
     oz::slice_cols_kernel<S><<<dim3((unsigned)cdiv(s->Nl, 8), cdiv(L.ldy8, 4 * 32)), dim3(32, 8), 0, s->stream>>>(
         Y, L.ldy, s->Nl, m, s->oz_yscale(), s->ys(), L.ldy8, s->Nl * L.ldy8);
     LAUNCHED(s);
@@ -427,12 +431,12 @@ static int oz_pair_t(lcx_session* s, const double* A, double* svec, cudaEvent_t*
     return 0;
 }
 
-static int oz_pair(lcx_session* s, const double* A, double* svec, cudaEvent_t* ev) {
+static int oz_pair(lcx_session* s, const double* A, double* svec, cudaEvent_t* ev, bool first_only = false) {
     switch (s->L.S) {
-        case 3: return oz_pair_t<3>(s, A, svec, ev);
-        case 4: return oz_pair_t<4>(s, A, svec, ev);
-        case 5: return oz_pair_t<5>(s, A, svec, ev);
-        case 6: return oz_pair_t<6>(s, A, svec, ev);
+        case 3: return oz_pair_t<3>(s, A, svec, ev, first_only);
+        case 4: return oz_pair_t<4>(s, A, svec, ev, first_only);
+        case 5: return oz_pair_t<5>(s, A, svec, ev, first_only);
+        case 6: return oz_pair_t<6>(s, A, svec, ev, first_only);
     }
     return fail(LCX_ERR_STATE, "oz_pair", "bad digit count");
 }
@@ -463,7 +467,11 @@ extern "C" int lcx_bind(lcx_session* s, const double* xt, long long n_rows_local
     LCX_CUDA(cudaMemsetAsync(workspace, 0, (size_t)y_off * sizeof(double), s->stream));
     const long long y_end = align16(y_off + n_rows_local * L.ldy);
     LCX_CUDA(cudaMemsetAsync(workspace + y_end, 0, (size_t)(L.total - y_end) * sizeof(double), s->stream));
-    if (L.S > 0) LCX_TRY(oz_prepare(s));  // digit slices of X~ (after this X~ itself is no longer read)
+    if (L.S > 0) {
+        LCX_TRY(oz_prepare(s));  // digit slices of X~; after this X~ itself is never read again in the split modes,
+        LCX_CUDA(cudaStreamSynchronize(s->stream));  // so the caller may release it as soon as lcx_bind returns
+        s->xt = nullptr;
+    }
     return 0;
 }
 
@@ -791,8 +799,12 @@ extern "C" int lcx_init_scale(lcx_session* s, double eps) {
     const int m = s->m, n = s->n;
     double* W = s->ptr(LCX_A_W);
     double* svec = s->ptr(LCX_A_D) + (long long)m * L.ld;
-    LCX_TRY(lcx_project(s, s->xt, s->Nl, n, s->ldx, W, L.ld, m, s->ptr(LCX_A_Y), L.ldy, svec, s->ptr(I_COLSQ),
-                        lcx_project_scratch_doubles(s->Nl, m)));
+    if (L.S > 0) {
+        LCX_TRY(oz_pair(s, W, svec, nullptr, true));
+    } else {
+        LCX_TRY(lcx_project(s, s->xt, s->Nl, n, s->ldx, W, L.ld, m, s->ptr(LCX_A_Y), L.ldy, svec, s->ptr(I_COLSQ),
+                            lcx_project_scratch_doubles(s->Nl, m)));
+    }
     if (s->hook) {
         if (s->hook(s->hook_user, s->off(LCX_A_D) + (long long)m * L.ld, m) != 0)
             return fail(LCX_ERR_STATE, "allreduce hook", "hook reported failure");

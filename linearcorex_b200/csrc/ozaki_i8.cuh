@@ -190,7 +190,10 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     } else if (warp == 1) {
         // ===== MMA issuer (one elected lane) =====
         if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc_i8(kBM, kBN, KMAJOR ? 0 : 1, KMAJOR ? 0 : 1);
+            // Digit ka of A meets digits 0..S-1-ka of B, landing in groups ka..S-1 = CONSECUTIVE TMEM columns, and
+            // the B digit planes are consecutive in shared memory, so those S-ka products are issued as one wide
+            // MMA (N = 64 (S-ka), at most 256 per instruction): A is re-read from shared memory 8 times per K step
+            // instead of 21 -- the narrow 128x64 form is shared-memory-bandwidth bound (6 KB of operands per 32 cycles).
             for (int kb = 0; kb < num_kb; ++kb) {
                 const int st = kb % kStages;
                 const uint32_t ph = (kb / kStages) & 1;
@@ -203,20 +206,24 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 #pragma unroll
                     for (int ka = 0; ka < S; ++ka) {
 #pragma unroll
-                        for (int kq = 0; kq < S - ka; ++kq) {
+                        for (int q0 = 0; q0 < S - ka; q0 += 4) {
+                            const int cnt = (S - ka - q0) < 4 ? (S - ka - q0) : 4;  // B digit planes in this instruction
+                            const uint32_t idesc = make_idesc_i8(kBM, kBN * cnt, KMAJOR ? 0 : 1, KMAJOR ? 0 : 1);
                             uint64_t da, db;
                             if (KMAJOR) {
-                                // rows at 64 B pitch, 8-row swizzle atoms of 512 B; a K step is +32 B inside the span
+                                // rows at 64 B pitch, 8-row swizzle atoms of 512 B (SBO); a K step is +32 B inside the
+                                // span; the next B plane starts 8 atoms further, i.e. N simply continues.
                                 da = make_smem_desc(sa + ka * A_BYTES + kk * 32, 16, 512, 4);
-                                db = make_smem_desc(sb + kq * B_BYTES + kk * 32, 16, 512, 4);
+                                db = make_smem_desc(sb + q0 * B_BYTES + kk * 32, 16, 512, 4);
                             } else {
                                 // A: K rows of 128 B (SW128, atoms of 8 rows = 1 KB); a K step is 32 rows = 4 KB
-                                // B: K rows of 64 B  (SW64,  atoms of 8 rows = 512 B); a K step is 32 rows = 2 KB
+                                // B: K rows of 64 B  (SW64,  atoms of 8 rows = 512 B); a K step is 32 rows = 2 KB;
+                                //    the next 64 columns of N are the next digit plane, 4 KB further (LBO).
                                 da = make_smem_desc(sa + ka * A_BYTES + kk * 4096, 8192, 1024, 2);
-                                db = make_smem_desc(sb + kq * B_BYTES + kk * 2048, 4096, 512, 4);
+                                db = make_smem_desc(sb + q0 * B_BYTES + kk * 2048, 4096, 512, 4);
                             }
                             const uint32_t acc = (kb > 0 || kk > 0 || ka > 0) ? 1u : 0u;
-                            umma_i8(tmem_base + (uint32_t)(ka + kq) * kBN, da, db, idesc, acc);
+                            umma_i8(tmem_base + (uint32_t)(ka + q0) * kBN, da, db, idesc, acc);
                         }
                     }
                 }

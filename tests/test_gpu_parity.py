@@ -212,6 +212,39 @@ def test_toy_duplicate_columns_known_answer():
     assert c[0] == c[1] == c[2] and c[3] == c[4] and c[0] != c[3]
 
 
+SPLIT_CASES = ["readme_demo_f64", "big5_l0_f64", "syn_400x300x10_f64", "syn_60x400x8_f64", "outliers_missing_f64",
+               "standard_missing_f64", "adni_l1_f64"]
+
+
+@pytest.mark.parametrize("name", SPLIT_CASES)
+def test_full_fit_fp64_split(name):
+    """FP64-faithful split-integer mode (tcgen05 kind::i8, 6 digits): same 1e-9 bar as the DMMA mode."""
+    z, mdl, x = _fit(name, precision="fp64_split")
+    _check_fit(z, mdl, x, RTOL)
+
+
+@pytest.mark.parametrize("name", ["syn_400x300x10_f64", "big5_l0_f64", "outliers_missing_f64"])
+def test_fit_fast_mode_fixed_budget(name):
+    """Opt-in fast mode (4 digits): 1e-4 on W / TCs at a fixed iteration budget (near convergence the
+    stopping iteration itself is precision dependent, so the comparison is made at equal iteration counts)."""
+    import corex_oracle as oc
+    from linearcorex_b200 import Corex
+    z, kw, x = load_golden(name)
+    kw = dict(kw, max_iter=12, tol=1e-12)
+    ref = oc.OracleCorex(work_dtype=np.float64, **kw).fit(x)
+    mdl = Corex(precision="fast", **kw).fit(x)
+    assert len(mdl.history["TC"]) == len(ref.history["TC"])
+    assert_close(mdl.ws, ref.ws, 1e-4, "ws")
+    assert_close(mdl.tcs, ref.tcs, 1e-4, "TCs")
+    assert_close(mdl.tc, ref.tc, 1e-4, "TC")
+    np.testing.assert_array_equal(mdl.clusters(), ref.clusters())
+
+
+def test_synthetic_4000x2000x20_fp64_split():
+    z, mdl, x = _fit("syn_4000x2000x20_f64", precision="fp64_split")
+    _check_fit(z, mdl, x, RTOL)
+
+
 def test_adni_layer0_missing_values():
     """566 x 200, 3.1 % missing, 30 factors, ~2400 iterations: long trajectories amplify rounding, so this one
     is held to the iteration count, TC at 1e-9 and cluster labels."""

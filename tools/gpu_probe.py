@@ -58,7 +58,9 @@ def main():
     out["cublas_sgemm_tflops_best"] = 2 * n ** 3 / best / 1e9
     del a32, b32
 
-    sess = _DeviceSession(_lib.PRECISION_FP64)
+    prec = int(sys.argv[4]) if len(sys.argv) >= 5 else _lib.PRECISION_FP64
+    out["precision"] = prec
+    sess = _DeviceSession(prec)
     lib = sess.lib
     ld = lib.lcx_ld(nv)
     assert ld == nv or True
