@@ -363,7 +363,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="config3", choices=sorted(WORKLOADS))
-    ap.add_argument("--precision", default="fp64", choices=["fp64", "fp64_split", "fast"])
+    ap.add_argument("--precision", default="fp64_split", choices=["fp64", "fp64_split", "fast"])
     ap.add_argument("--gaussianize", default="standard")
     ap.add_argument("--rows", type=int, default=0)
     ap.add_argument("--vars", type=int, default=0)
