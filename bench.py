@@ -317,6 +317,7 @@ def run_ours(args, shape):
     d2h = sum(np.asarray(v).nbytes for v in e2e_mdl.moments.values()) * 2 + e2e_mdl.ws.nbytes + 16 * 8 * 4 * e2e_iters
     e2e = {"value": e2e_iters / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(x_host.nbytes * world / e2e_iters),
            "d2h_bytes_per_step": int(d2h / e2e_iters), "iterations": e2e_iters, "seconds": e2e_s,
+           "phases_s": {k: round(v, 4) for k, v in e2e_mdl.timings.items()},
            "what": "Corex(n_hidden=%d, max_iter=%d).fit(host float32 X): H2D of X, preprocess, 7 anneal stages, "
                    "final sort + full moments, D2H of ws and every moments key" % (n_factors, per_stage)}
     del e2e_mdl

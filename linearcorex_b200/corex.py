@@ -32,6 +32,7 @@ behaviour):
                       `fit(x)` then takes this rank's row block of X (sample sharding).
 """
 import ctypes as C
+import time
 
 import numpy as np
 
@@ -165,6 +166,7 @@ class Corex(object):
         self.n_obs = 0
         self.history = {}
         self.trace = []          # per-iteration: eps, eta, trials, quick_fails, tangent, TC
+        self.timings = {}        # wall-clock seconds of the one-off phases (upload, preprocess, bind, finish)
         self._comm = comm
         self._device = device
         self._sess = None
@@ -214,19 +216,36 @@ class Corex(object):
         sess = self._session()
         x = np.ascontiguousarray(x)
         out = torch.empty(x.shape, dtype=torch.float32 if x.dtype == np.float32 else torch.float64, device=sess.device)
-        rows = max(1, int((256 << 20) // max(1, x.shape[1] * x.itemsize)))
-        stage = None
-        for lo in range(0, x.shape[0], rows):
-            hi = min(x.shape[0], lo + rows)
-            src = torch.from_numpy(x[lo:hi])
-            if x.shape[0] > rows:  # large input: pinned double-buffer-free staging
-                if stage is None:
-                    stage = torch.empty((rows, x.shape[1]), dtype=src.dtype).pin_memory()
-                stage[:hi - lo].copy_(src)
-                out[lo:hi].copy_(stage[:hi - lo], non_blocking=True)
-                torch.cuda.current_stream().synchronize()
-            else:
-                out[lo:hi].copy_(src)
+        row_bytes = max(1, x.shape[1] * x.itemsize)
+        if x.nbytes <= (64 << 20):
+            out.copy_(torch.from_numpy(x))
+            return out
+        # Large input: two pinned staging buffers.  Worker threads fill buffer b (pageable -> pinned memcpy, GIL
+        # released) while the DMA engine drains buffer 1-b, so the upload runs at min(host memcpy, PCIe) speed.
+        from concurrent.futures import ThreadPoolExecutor
+        rows = max(1, int((128 << 20) // row_bytes))
+        nthr = 8
+        stages = [torch.empty((rows, x.shape[1]), dtype=out.dtype).pin_memory() for _ in range(2)]
+        done = [None, None]
+        stream = torch.cuda.current_stream()
+
+        def fill(buf, base, lo, hi):
+            if hi > lo:
+                buf[lo:hi].copy_(torch.from_numpy(x[base + lo:base + hi]))
+
+        with ThreadPoolExecutor(max_workers=nthr) as pool:
+            for i, lo in enumerate(range(0, x.shape[0], rows)):
+                hi = min(x.shape[0], lo + rows)
+                b = i & 1
+                if done[b] is not None:
+                    done[b].synchronize()  # the DMA that last read this staging buffer has finished
+                cnt = hi - lo
+                step = (cnt + nthr - 1) // nthr
+                list(pool.map(lambda k: fill(stages[b], lo, k * step, min(cnt, (k + 1) * step)), range(nthr)))
+                out[lo:hi].copy_(stages[b][:cnt], non_blocking=True)
+                done[b] = torch.cuda.Event()
+                done[b].record(stream)
+        stream.synchronize()
         return out
 
     def _as_input(self, x):
@@ -250,7 +269,9 @@ class Corex(object):
         sess = self._session()
         lib = sess.lib
         red = self._reducer()
+        t_up = time.perf_counter()
         xd = self._as_input(x)
+        self.timings["upload_s"] = time.perf_counter() - t_up
         N, n = xd.shape
         dt = _lib.F32 if xd.dtype == torch.float32 else _lib.F64
         ldo = lib.lcx_ld(n)
@@ -324,12 +345,18 @@ class Corex(object):
         sess = self._session()
         lib = sess.lib
         red = self._reducer()
+        t0 = time.perf_counter()
         xt = self.preprocess(x, fit=True)
+        _torch().cuda.synchronize()
+        self.timings["preprocess_s"] = time.perf_counter() - t0
         n_local, self.nv = xt.shape[0], int(np.shape(x)[1])
         self.n_samples = int(red.sum_scalar(n_local))
         if self.m is None:
             raise ValueError("n_hidden=None (pick_n_hidden) is not supported: the reference helper is broken (:458-480)")
+        t0 = time.perf_counter()
         sess.bind(xt, self.n_samples, self.nv, self.m, red)
+        _torch().cuda.synchronize()
+        self.timings["bind_s"] = time.perf_counter() - t0
         schedule = [0.]
         if self.ws.size == 0:  # :114-121
             if self.discourage_overlap:
@@ -393,11 +420,13 @@ class Corex(object):
     def _finish(self):
         """:160-163 full moments, sort factors by TCs (descending), full moments again."""
         sess = self._sess
-        self._full_moments()
+        t0 = time.perf_counter()
+        self._full_moments(export=False)  # only TCs is needed to order the factors
         order = np.argsort(-self.moments["TCs"])
         _lib.check(sess.lib.lcx_permute_rows(sess.h, (C.c_int * self.m)(*[int(o) for o in order])), "lcx_permute_rows")
         self._full_moments()
         self.ws = self._get_w()
+        self.timings["finish_s"] = time.perf_counter() - t0
         return self
 
     def fit_transform(self, x):
@@ -464,8 +493,8 @@ class Corex(object):
     # ------------------------------------------------------------------------------------------
     # moments export
     # ------------------------------------------------------------------------------------------
-    def _full_moments(self):
-        """`_calculate_moments(x, ws, quick=False)` from X~, then pull every key to the host."""
+    def _full_moments(self, export=True):
+        """`_calculate_moments(x, ws, quick=False)` from X~, then pull every key (or only TCs) to the host."""
         sess = self._sess
         lib = sess.lib
         tcv, muj, a, b = (C.c_double() for _ in range(4))
@@ -474,7 +503,10 @@ class Corex(object):
             _lib.check(lib.lcx_details_ns(sess.h, C.byref(a), C.byref(b)), "lcx_details_ns")
         else:
             _lib.check(lib.lcx_moments_syn(sess.h, C.byref(tcv), C.byref(b)), "lcx_moments_syn")
-        self.moments = self._export_moments(sess, tcv.value)
+        if export:
+            self.moments = self._export_moments(sess, tcv.value)
+        else:
+            self.moments = {"TC": tcv.value, "TCs": sess.host(_lib.A_TCS, squeeze=True)}
 
     def _export_moments(self, sess, tc):
         L = _lib
