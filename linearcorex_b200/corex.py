@@ -258,6 +258,14 @@ class Corex(object):
                 x = x.float()
             return x.contiguous()
         want = np.float32 if self.input_dtype == 'float32' else np.float64
+        if isinstance(x, torch.Tensor):  # host tensor: page-locked memory goes straight to the DMA engine
+            if x.is_pinned() and x.is_contiguous() and x.dtype in (torch.float32, torch.float64) and \
+                    not (self.input_dtype == 'float32' and x.dtype != torch.float32):
+                out = torch.empty(x.shape, dtype=x.dtype, device=self._session().device)
+                out.copy_(x, non_blocking=True)
+                torch.cuda.current_stream().synchronize()
+                return out
+            x = x.numpy()
         x = np.asarray(x)
         if x.dtype == np.float32 and want == np.float64:
             return self._upload(x)  # float32 values are exact in float64: keep the narrow upload
@@ -555,9 +563,10 @@ class Corex(object):
     # ------------------------------------------------------------------------------------------
     # transform / invert / predict / get_covariance (:386-395, :431-455)
     # ------------------------------------------------------------------------------------------
-    def transform(self, x, details=False):
+    def transform(self, x, details=False, return_device=False):
         """Y = preprocess(x) . ws^T (:386-395).  Returns an (N, m) float64 ndarray; with
-        `details=True` also the full moments of `x` under the fitted weights."""
+        `details=True` also the full moments of `x` under the fitted weights.  `return_device=True`
+        returns the (N, m) CUDA tensor instead (layer stacking keeps Y resident, hierarchy.py)."""
         torch = _torch()
         sess = self._session()
         lib = sess.lib
@@ -572,6 +581,8 @@ class Corex(object):
         y = torch.empty((ns, ldy), dtype=torch.float64, device=sess.device)
         _lib.check(lib.lcx_project(sess.h, xt.data_ptr(), ns, nv, xt.stride(0), wd.data_ptr(), ld, self.m, y.data_ptr(),
                                    ldy, None, None, 0), "lcx_project")
+        if return_device and not details:
+            return y[:, :self.m]
         y_host = y[:, :self.m].cpu().numpy().copy()
         if details:
             other = _DeviceSession(_lib.PRECISIONS[self.precision], self._device)

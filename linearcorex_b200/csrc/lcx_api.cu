@@ -401,7 +401,7 @@ static int oz_pair_t(lcx_session* s, const double* A, double* svec, cudaEvent_t*
     double* ystat = s->ws + L.slot[I_YSTAT][0].off;
     oz::y_stats_kernel<<<dim3(cdiv(m, 32), L.ystat_slabs), dim3(32, 8), 0, s->stream>>>(Y, L.ldy, s->Nl, m, kYStatRows, ystat, L.ldm);
     LAUNCHED(s);
-    oz::y_stats_finish_kernel<<<cdiv(m, 128), 128, 0, s->stream>>>(ystat, L.ystat_slabs, L.ldm, m, s->oz_xscale(), svec, s->oz_yscale(),
+    oz::y_stats_finish_kernel<<<m, 256, 0, s->stream>>>(ystat, L.ystat_slabs, L.ldm, m, s->oz_xscale(), svec, s->oz_yscale(),
                                                                   s->oz_dscale());
     LAUNCHED(s);
     if (first_only) {  // _norm (:215-228): only Y and its column sums of squares are needed

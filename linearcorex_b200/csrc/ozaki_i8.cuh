@@ -402,17 +402,23 @@ __global__ void __launch_bounds__(256) y_stats_kernel(const double* __restrict__
 __global__ void y_stats_finish_kernel(const double* __restrict__ part, int slabs, long long ldp, int cols,
                                       const double* __restrict__ x_scale, double* __restrict__ colsq,
                                       double* __restrict__ yscale, double* __restrict__ dscale) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    // one CTA of 256 threads per column; fixed-order block reduction keeps the sum deterministic
+    __shared__ double scratch[8];
+    const int c = blockIdx.x;
     if (c >= cols) return;
     double mx = 0.0, sq = 0.0;
-    for (int s = 0; s < slabs; ++s) {
+    for (int s = threadIdx.x; s < slabs; s += 256) {
         mx = fmax(mx, part[((long long)s * 2 + 0) * ldp + c]);
         sq += part[((long long)s * 2 + 1) * ldp + c];
     }
-    if (colsq) colsq[c] = sq;
-    const double sc = pow2_above(mx);
-    yscale[c] = sc;
-    dscale[c] = x_scale[0] * sc;
+    mx = block_max_256(mx, scratch);
+    sq = block_sum_256(sq, scratch);
+    if (threadIdx.x == 0) {
+        if (colsq) colsq[c] = sq;
+        const double sc = pow2_above(mx);
+        yscale[c] = sc;
+        dscale[c] = x_scale[0] * sc;
+    }
 }
 
 // cscale[j] = x_scale * a_scale[j]   (output scale of Y = X~ A^T)

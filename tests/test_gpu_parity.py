@@ -262,6 +262,24 @@ def test_synthetic_4000x2000x20():
     assert all(len(set(c[g::20])) == 1 for g in range(20)) and len(set(c[:20])) == 20
 
 
+def test_layer_stacking_matches_reference_chain():
+    """vis_corex.py:529-545: layers 5,1 on big5 and 30,5,1 on adni, intermediate Y kept on the device."""
+    from linearcorex_b200 import fit_layers
+    z0, kw, x = load_golden("big5_l0_f64")
+    z1, _, _ = load_golden("big5_l1_f64")
+    models = fit_layers(x, [5, 1], seed=0)
+    assert [m.m for m in models] == [5, 1]
+    assert_close(models[0].tc, z0["m_TC"], RTOL, "layer 0 TC")
+    assert_close(models[0].ws, z0["ws"], RTOL, "layer 0 ws")
+    assert_close(models[1].tc, z1["m_TC"], 1e-8, "layer 1 TC")
+    assert_close(models[1].ws, z1["ws"], 1e-8, "layer 1 ws")
+    za, kwa, xa = load_golden("adni_l1_f64")   # its X is the stored transform of adni layer 0
+    zb, _, _ = load_golden("adni_l2_f64")
+    upper = fit_layers(xa, [5, 1], seed=0)
+    assert_close(upper[0].tc, za["m_TC"], RTOL, "adni layer 1 TC")
+    assert_close(upper[1].tc, zb["m_TC"], 1e-7, "adni layer 2 TC")
+
+
 def test_pickle_and_warm_start():
     from linearcorex_b200 import Corex
     z, mdl, x = _fit("syn_400x300x10_f64")
