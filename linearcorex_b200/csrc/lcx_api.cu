@@ -94,7 +94,9 @@ static Layout make_layout(long long Nl, int n, int m, int precision) {
     L.ld = round_up(n, 16);
     L.ldm = round_up(m, 16);
     L.ldy = round_up(m, 8);
-    L.plan_k1 = plan_gemm((int)Nl, m, n, kSMs, 1, false);
+    // few samples (N << 128 * 148 rows): split the first contraction over the variables as well
+    const bool k1_split = (long long)cdiv(Nl, 128) * cdiv(m, 128) < kSMs / 2;
+    L.plan_k1 = plan_gemm((int)Nl, m, n, kSMs, k1_split ? 16 : 1, k1_split);
     L.plan_k2 = plan_gemm(n, m, (int)Nl, kSMs, kMaxSplitsX, true);
     L.plan_mm = plan_gemm(m, m, n, kSMs, kMaxSplitsSmall, true);
     L.plan_mn = plan_gemm(m, n, m, kSMs, 1, false);
@@ -140,6 +142,7 @@ static Layout make_layout(long long Nl, int n, int m, int precision) {
     long long part = 0;
     if (L.plan_k2.splits > 1) part = max(part, (long long)L.plan_k2.splits * mn * L.ld);
     if (L.plan_mm.splits > 1) part = max(part, (long long)L.plan_mm.splits * mn * L.ldm);
+    if (L.plan_k1.splits > 1) part = max(part, (long long)L.plan_k1.splits * Nl * L.ldy);
     put1(I_PART, 1, max(part, 16LL), max(part, 16LL));
     put1(I_COLSQ, L.plan_k1.grid.x, m, L.ldy);
     const long long spart = max(3LL * L.nstrips, (long long)m * cdiv(n, 256));
@@ -153,6 +156,9 @@ static Layout make_layout(long long Nl, int n, int m, int precision) {
     put1(I_RYINV, mn, m, L.ldm);
     put1(I_AUG, mn, 2 * mn, 2 * mn);
     put1(I_STATUS, 1, 2, 2);
+    L.ystat_slabs = cdiv(Nl, kYStatRows);
+    put1(I_OZV, 1, 16 + 4 * L.ldm, 16 + 4 * L.ldm);
+    put1(I_YSTAT, (long long)L.ystat_slabs * 2, m, L.ldm);
     if (L.S > 0) {
         L.ld8 = round_up(n, 128);
         L.ldy8 = round_up(m, 128);
@@ -172,7 +178,6 @@ static Layout make_layout(long long Nl, int n, int m, int precision) {
         }
         L.oz_chunk = (int)round_up(cdiv(Nl, best), oz::kBK);
         L.oz_splits = cdiv(Nl, L.oz_chunk);
-        L.ystat_slabs = cdiv(Nl, kYStatRows);
         const long long part = (long long)L.oz_splits * mn * L.ld;
         if (part > L.slot[I_PART][0].cols) {  // grow the split-K partial buffer (it is the last big slot before these)
             put1(I_PART, 1, part, part);
@@ -180,8 +185,6 @@ static Layout make_layout(long long Nl, int n, int m, int precision) {
         put1(I_XS, 1, cdiv((long long)L.S * Nl * L.ld8, 8), cdiv((long long)L.S * Nl * L.ld8, 8));
         put1(I_AS, 1, cdiv((long long)L.S * mn * L.ld8, 8), cdiv((long long)L.S * mn * L.ld8, 8));
         put1(I_YS, 1, cdiv((long long)L.S * Nl * L.ldy8, 8), cdiv((long long)L.S * Nl * L.ldy8, 8));
-        put1(I_OZV, 1, 16 + 4 * L.ldm, 16 + 4 * L.ldm);
-        put1(I_YSTAT, (long long)L.ystat_slabs * 2, m, L.ldm);
         put1(I_AMAX, 1, kAmaxCtas, kAmaxCtas);
     }
     L.total = cur;
@@ -640,11 +643,20 @@ static int xpair(lcx_session* s, const double* A, bool want_colsq) {
         a.A = s->xt; a.B = A; a.C = Y;
         a.M = (int)s->Nl; a.N = m; a.K = n;
         a.lda = s->ldx; a.ldb = L.ld; a.ldc = L.ldy;
-        a.colsq_part = want_colsq ? s->ptr(I_COLSQ) : nullptr;
+        const bool k1_split = L.plan_k1.splits > 1;
+        a.colsq_part = (want_colsq && !k1_split) ? s->ptr(I_COLSQ) : nullptr;
         a.ld_colsq = (int)L.ldy;
-        LCX_TRY(run_gemm(s, kLayoutKK, L.plan_k1, a, nullptr, 0));
+        LCX_TRY(run_gemm(s, kLayoutKK, L.plan_k1, a, k1_split ? s->ptr(I_PART) : nullptr, s->Nl * L.ldy));
         if (ev) LCX_CUDA(cudaEventRecord(ev[1], s->stream));
-        if (want_colsq) {
+        if (want_colsq && k1_split) {  // split over variables: the sums of squares come from the reduced Y
+            double* ystat = s->ws + L.slot[I_YSTAT][0].off;
+            oz::y_stats_kernel<<<dim3(cdiv(m, 32), L.ystat_slabs), dim3(32, 8), 0, s->stream>>>(Y, L.ldy, s->Nl, m, kYStatRows, ystat,
+                                                                                          L.ldm);
+            LAUNCHED(s);
+            oz::y_stats_finish_kernel<<<m, 256, 0, s->stream>>>(ystat, L.ystat_slabs, L.ldm, m, s->oz_xscale(), svec, s->oz_yscale(),
+                                                               s->oz_dscale());
+            LAUNCHED(s);
+        } else if (want_colsq) {
             reduce_colsq_kernel<<<cdiv(m, 128), 128, 0, s->stream>>>(s->ptr(I_COLSQ), L.plan_k1.grid.x, (int)L.ldy, svec, m);
             LAUNCHED(s);
         }
