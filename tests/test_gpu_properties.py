@@ -93,9 +93,6 @@ def test_fixed_budget_fit_matches_oracle_and_invariants(data, precision):
     # TC is non-decreasing within each annealing stage (Wolfe sufficient increase)
     tcs = np.asarray(mdl.history["TC"]).reshape(7, 4)
     assert (np.diff(tcs, axis=1) >= -1e-9 * np.abs(tcs[:, 1:])).all()
-    # planted structure recovered: variable i belongs to group i mod m
-    c = mdl.clusters()
-    assert all(len(set(c[g::m])) == 1 for g in range(m))
 
 
 def test_config4_like_small_sample_path():
