@@ -279,15 +279,17 @@ def run_ours(args, shape):
         # split-integer modes: each FP64 multiply-add is S(S+1)/2 exact int8 multiply-adds on tcgen05 (kind::i8)
         pair_ops = pair_flops * digits * (digits + 1) / 2
         achieved = pair_ops / (pair_ms / 1e3) / 1e12 if pair_ms > 0 else 0.0
-        peak = 2.0 * float(peaks.get("bf16_tflops", 1590.0))
+        # the kernel is timed inside a long, power-capped step -> the sustained bf16 figure is the right denominator
+        peak = 2.0 * float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1400.0)))
         rl_unit = "TOP/s"
         rl_kernel = ("oz_gemm_kernel<%d,*> (tcgen05.mma kind::i8 + TMA; Y = X~ A^T and X~^T Y as %d int8 digit-plane products "
                      "each, incl. digit slicing of A and Y), %d pass pairs timed by CUDA events; K1 %.3f ms, K2 %.3f ms per launch; "
                      "FP64-equivalent %.1f TFLOP/s" % (digits, digits * (digits + 1) // 2, pairs.value,
                                                         k1.value / max(1, pairs.value), k2.value / max(1, pairs.value), fp64_equiv))
-        rl_source = ("2 x bf16_tflops of MEASURED_PEAKS.json%s (kind::i8 runs at twice the bf16 rate on B200; no int8 entry is "
-                     "measured); cuBLAS DGEMM in this run: %.1f TFLOP/s"
-                     % ("" if "bf16_tflops" in peaks else " [fallback 1590]", dgemm_peak))
+        rl_source = ("2 x bf16_tflops_sustained of MEASURED_PEAKS.json%s (kind::i8 runs at twice the bf16 rate on B200; no int8 "
+                     "entry is measured; sustained because the kernel is timed inside a long power-capped step; the burst "
+                     "figure would be 2 x %s); cuBLAS DGEMM in this run: %.1f TFLOP/s"
+                     % ("" if "bf16_tflops_sustained" in peaks else " [fallback 1400]", peaks.get("bf16_tflops"), dgemm_peak))
     else:
         pair_ops = pair_flops
         achieved, peak, rl_unit = fp64_equiv, dgemm_peak, "TFLOP/s"
