@@ -298,6 +298,9 @@ def run_ours(args, shape):
                                                             k2.value / max(1, pairs.value)))
         rl_source = ("cuBLAS DGEMM 6144^3 measured in this run (MEASURED_PEAKS.json has no FP64 entry; nominal B200 FP64 "
                      "tensor peak is 40 TFLOP/s); bf16 measured peak for context: %s TF/s" % peaks.get("bf16_tflops"))
+    exchange = ("none (single rank)" if world == 1 else
+                "fused split-K combine + two-shot all-reduce kernel over NVLink peer memory" if sess._peer_buf is not None
+                else "split-K combine kernel + NCCL all-reduce (torch.distributed hook)")
     del mdl, sess
     torch.cuda.empty_cache()
 
@@ -340,7 +343,7 @@ def run_ours(args, shape):
         "dtype": {"fp64": "f64", "fp64_split": "f64 (int8x6 split products, int32/f64 accumulation)",
                   "fast": "int8x4 split products"}[args.precision], "data": "synthetic",
         "config": {"workload": workload_name(args, shape), "n_samples": n_total, "n_variables": n_vars,
-                   "n_factors": n_factors, "rows_per_gpu": n_local, "parallelism": "sample-sharded x%d" % world,
+                   "n_factors": n_factors, "rows_per_gpu": n_local, "parallelism": "sample-sharded x%d" % world, "exchange_per_pass_pair": exchange,
                    "l2": "inputs_exceed_l2 (X~ block is %.1f GB per GPU)" % (n_local * n_vars * 8 / 1e9),
                    "trials_per_iteration": trials, "TC_after_timed_region": tc_last},
         "updates_per_sec": it_s * n_total * n_vars * n_factors,

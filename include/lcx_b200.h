@@ -100,6 +100,13 @@ int lcx_session_create(lcx_session** out, int device, int precision);
 int lcx_session_destroy(lcx_session* s);
 int lcx_set_stream(lcx_session* s, void* cuda_stream);
 int lcx_set_allreduce(lcx_session* s, lcx_allreduce_fn fn, void* user);
+/* Sample sharding over NVLink peer memory (preferred over the hook when every rank can map every other rank's
+ * buffer): `bases[r]` = rank r's copy of one symmetric buffer of lcx_peer_buffer_doubles() doubles, zero-filled
+ * before the first call on any rank.  With peers set, the split-K combine of X~^T Y and the sum over ranks run as
+ * ONE kernel (two-shot reduce-scatter / all-gather with P2P loads and stores, release/acquire flags), and every
+ * rank ends with bit-identical moments.  Call after lcx_bind; world <= 1 or bases == NULL switches it off. */
+long long lcx_peer_buffer_doubles(int n_vars, int n_factors);
+int lcx_set_peer_allreduce(lcx_session* s, int world, int rank, void* const* bases, long long buffer_doubles);
 int lcx_launch_count(lcx_session* s, long long* launches);   /* kernels launched so far by this session */
 /* Device-side timing of the two X contractions (CUDA events on the session stream around each launch).
  * lcx_profile_read synchronises the stream and returns accumulated milliseconds and the pair count. */

@@ -32,6 +32,8 @@ SIGNATURES = {
     "lcx_session_destroy": (_i, [_p]),
     "lcx_set_stream": (_i, [_p, _p]),
     "lcx_set_allreduce": (_i, [_p, ALLREDUCE_FN, _p]),
+    "lcx_peer_buffer_doubles": (_ll, [_i, _i]),
+    "lcx_set_peer_allreduce": (_i, [_p, _i, _i, C.POINTER(C.c_void_p), _ll]),
     "lcx_launch_count": (_i, [_p, _pll]),
     "lcx_profile_enable": (_i, [_p, _i]),
     "lcx_profile_read": (_i, [_p, _pd, _pd, _pll, _i]),

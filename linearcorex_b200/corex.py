@@ -32,6 +32,7 @@ behaviour):
                       `fit(x)` then takes this rank's row block of X (sample sharding).
 """
 import ctypes as C
+import os
 import time
 
 import numpy as np
@@ -98,7 +99,12 @@ class _DeviceSession(object):
                                      self.ws.data_ptr(), need), "lcx_bind")
         if self.precision != _lib.PRECISION_FP64:
             self.xt = None  # the split modes keep int8 digit planes in the workspace; the fp64 block is released
-        if reducer is not None and reducer.world > 1:
+        self._peer_buf = None
+        if reducer is not None and reducer.world > 1 and reducer.backend == "nccl" and \
+                os.environ.get("LCX_PEER_ALLREDUCE", "1") != "0" and self._bind_peers(reducer, n_vars, n_factors):
+            self._hook = None  # sums over ranks run inside the fused peer-memory kernel
+            _lib.check(self.lib.lcx_set_allreduce(self.h, C.cast(None, _lib.ALLREDUCE_FN), None), "lcx_set_allreduce")
+        elif reducer is not None and reducer.world > 1:
             ws = self.ws
 
             def hook(_user, offset, count):
@@ -112,6 +118,32 @@ class _DeviceSession(object):
         else:
             self._hook = None
             _lib.check(self.lib.lcx_set_allreduce(self.h, C.cast(None, _lib.ALLREDUCE_FN), None), "lcx_set_allreduce")
+
+    def _bind_peers(self, reducer, n_vars, n_factors):
+        """Map one symmetric buffer on every rank (torch symmetric memory: CUDA VMM handles exchanged over the process
+        group) and hand the peer pointers to the library.  Returns False when peer mapping is unavailable, in which
+        case the NCCL hook is used instead."""
+        torch = _torch()
+        try:
+            import torch.distributed as dist
+            import torch.distributed._symmetric_memory as symm
+            need = self.lib.lcx_peer_buffer_doubles(n_vars, n_factors)
+            buf = symm.empty(need, dtype=torch.float64, device=self.device)
+            group = reducer.group if reducer.group is not None else dist.group.WORLD
+            hdl = symm.rendezvous(buf, group)
+            buf.zero_()
+            torch.cuda.synchronize(self.device)
+            dist.barrier(group=reducer.group)  # nobody signals before every rank has zeroed its flags
+            ptrs = (C.c_void_p * reducer.world)(*[int(p) for p in hdl.buffer_ptrs])
+            _lib.check(self.lib.lcx_set_peer_allreduce(self.h, reducer.world, reducer.rank, ptrs, need),
+                       "lcx_set_peer_allreduce")
+            self._peer_buf, self._peer_hdl = buf, hdl
+            return True
+        except Exception as exc:  # noqa: BLE001 -- any failure here just selects the NCCL path
+            if os.environ.get("LCX_PEER_ALLREDUCE") == "require":
+                raise
+            self._peer_error = repr(exc)
+            return False
 
     def view(self, array_id, which=0):
         off, rows, cols, ld = (C.c_longlong() for _ in range(4))

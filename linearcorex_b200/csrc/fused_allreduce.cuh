@@ -1,0 +1,100 @@
+// Split-K reduction of X~^T Y fused with the cross-GPU sum over sample shards, in ONE kernel over NVLink peer memory.
+//
+// Reference context: in the single-process reference the sum over samples is inside one GEMM (linearcorex.py:211,
+// :259).  Sharded over ranks it becomes  D = sum_r sum_z partial[r][z]  -- a split-K combine followed by an all-reduce.
+// Instead of `reduce_splits_kernel` + an NCCL call, this kernel does both: every rank
+//   A. adds its own split-K partials (fixed order) into its slot of a symmetric buffer,
+//   -- cross-GPU barrier (release/acquire flags written into the peers' memory) --
+//   B. owns 1/P of the elements: reads that slice from every rank's slot over NVLink (P2P loads), adds in rank order,
+//      and stores the result into EVERY rank's output buffer (P2P stores)   [reduce-scatter + all-gather, two-shot],
+//   -- cross-GPU barrier --
+// so each rank ends with bit-identical D (same additions in the same order everywhere), which keeps the replicated
+// line-search / convergence decisions in lock-step without further communication.
+//
+// The symmetric buffer (allocated by the host through torch.distributed._symmetric_memory) is laid out as
+//   [ slot0 : count ][ slot1 : count ][ out : count ][ flags : 2 * kMaxRanks uint64 ][ grid barrier : 2 uint64 ]
+// Slots alternate per call so a fast rank's next phase A never overwrites what a slow rank is still reading.
+#pragma once
+#include <cooperative_groups.h>
+
+#include "common.cuh"
+
+namespace lcx {
+namespace far {
+
+namespace cg = cooperative_groups;
+constexpr int kMaxRanks = 8;
+
+struct Peers {
+    double* base[kMaxRanks];  // symmetric buffer base of every rank (peer-mapped)
+    int world, rank;
+    long long count;          // doubles per slot
+};
+
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__device__ __forceinline__ unsigned long long* flags_of(double* base, long long count) {
+    return reinterpret_cast<unsigned long long*>(base + 3 * count);
+}
+
+// All ranks arrive with `epoch`; returns when every rank has.  Called by every CTA after a grid-wide sync.
+__device__ __forceinline__ void cross_gpu_barrier(const Peers& p, unsigned long long epoch, cg::grid_group& grid) {
+    __threadfence_system();
+    grid.sync();
+    if (blockIdx.x == 0 && threadIdx.x < p.world)
+        st_release_sys(flags_of(p.base[threadIdx.x], p.count) + p.rank, epoch);
+    if (threadIdx.x < p.world) {
+        const unsigned long long* mine = flags_of(p.base[p.rank], p.count) + threadIdx.x;
+        while (ld_acquire_sys(mine) < epoch) {
+        }
+    }
+    __syncthreads();
+}
+
+// part: this rank's split-K partials [splits][rows][ld] (valid cols < cols); tail: `ntail` extra doubles (the column sums
+// of squares) appended after the rows*ld block.  epoch0 = 2 * call_index (flags are monotonically increasing).
+__global__ void __launch_bounds__(512) reduce_allreduce_kernel(Peers p, const double* __restrict__ part, int splits,
+                                                               long long stride, int rows, int cols, long long ld,
+                                                               const double* __restrict__ tail, int ntail, int slot,
+                                                               unsigned long long epoch0) {
+    cg::grid_group grid = cg::this_grid();
+    const long long body = (long long)rows * ld;
+    const long long count = body + ntail;
+    double* my_slot = p.base[p.rank] + (long long)slot * p.count;
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long nthr = (long long)gridDim.x * blockDim.x;
+    // ---- A: local split-K combine (fixed order), padding columns zeroed ----
+    for (long long i = tid; i < count; i += nthr) {
+        double acc = 0.0;
+        if (i < body) {
+            const int c = (int)(i % ld);
+            if (c < cols) {
+                acc = part[i];
+                for (int z = 1; z < splits; ++z) acc += part[(long long)z * stride + i];
+            }
+        } else {
+            acc = tail[i - body];
+        }
+        my_slot[i] = acc;
+    }
+    cross_gpu_barrier(p, epoch0 + 1, grid);
+    // ---- B: this rank reduces its 1/P slice over all ranks (rank order) and broadcasts it ----
+    const long long per = (count + p.world - 1) / p.world;
+    const long long lo = per * p.rank, hi = min(count, lo + per);
+    for (long long i = lo + tid; i < hi; i += nthr) {
+        double acc = (p.base[0] + (long long)slot * p.count)[i];
+        for (int r = 1; r < p.world; ++r) acc += (p.base[r] + (long long)slot * p.count)[i];
+        for (int r = 0; r < p.world; ++r) (p.base[r] + 2 * p.count)[i] = acc;
+    }
+    cross_gpu_barrier(p, epoch0 + 2, grid);
+}
+
+}  // namespace far
+}  // namespace lcx

@@ -8,6 +8,7 @@
 #include "common.cuh"
 #include "corex_kernels.cuh"
 #include "dgemm_mma.cuh"
+#include "fused_allreduce.cuh"
 #include "ozaki_i8.cuh"
 #include "preprocess_kernels.cuh"
 
@@ -212,6 +213,9 @@ struct lcx_session {
     int prof_pending, prof_cap;
     double prof_k1_ms, prof_k2_ms;
     long long prof_pairs;
+    // sample sharding over NVLink peers (fused_allreduce.cuh); peers.world <= 1 means off
+    far::Peers peers;
+    unsigned long long ar_calls;
     // split-integer modes: TMA descriptors over the digit slices
     CUtensorMap map_x_k1, map_a_k1, map_y_k2, map_x_k2;
     int8_t* xs() const { return (int8_t*)(ws + L.slot[I_XS][0].off); }
@@ -241,6 +245,9 @@ struct lcx_session {
     } while (0)
 
 #define LAUNCHED(s) ((s)->launches++)
+
+static int combine_and_allreduce(lcx_session* s, const double* part, int splits, long long stride, int rows, int cols,
+                                 long long ld, double* dst_body, double* tail, int ntail);
 
 static dim3 grid_mn(int m, int n) { return dim3(cdiv(n, 256), m); }
 
@@ -326,6 +333,31 @@ extern "C" int lcx_set_allreduce(lcx_session* s, lcx_allreduce_fn fn, void* user
     return 0;
 }
 
+extern "C" long long lcx_peer_buffer_doubles(int n_vars, int n_factors) {
+    if (n_vars <= 0 || n_factors <= 0) return -1;
+    const long long count = (long long)n_factors * round_up(n_vars, 16) + round_up(n_factors, 16);
+    return 3 * count + 4 * far::kMaxRanks;
+}
+
+extern "C" int lcx_set_peer_allreduce(lcx_session* s, int world, int rank, void* const* bases, long long buffer_doubles) {
+    S_REQUIRE_BOUND(s);
+    if (world <= 1 || bases == nullptr) {
+        s->peers.world = 0;
+        return 0;
+    }
+    LCX_REQUIRE(world <= far::kMaxRanks && rank >= 0 && rank < world, "bad world / rank (at most 8 ranks)");
+    LCX_REQUIRE(buffer_doubles >= lcx_peer_buffer_doubles(s->n, s->m), "peer buffer too small (see lcx_peer_buffer_doubles)");
+    for (int r = 0; r < world; ++r) {
+        LCX_REQUIRE(bases[r] != nullptr && ((uintptr_t)bases[r] % 16 == 0), "bad peer pointer");
+        s->peers.base[r] = (double*)bases[r];
+    }
+    s->peers.world = world;
+    s->peers.rank = rank;
+    s->peers.count = (long long)s->m * s->L.ld + s->L.ldm;
+    s->ar_calls = 0;
+    return 0;
+}
+
 extern "C" int lcx_launch_count(lcx_session* s, long long* launches) {
     LCX_REQUIRE(s != nullptr && launches != nullptr, "null argument");
     *launches = s->launches;
@@ -377,7 +409,7 @@ static int oz_prepare(lcx_session* s) {
 }
 
 template <int S>
-static int oz_pair_t(lcx_session* s, const double* A, double* svec, cudaEvent_t* ev, bool first_only) {
+static int oz_pair_t(lcx_session* s, const double* A, double* svec, cudaEvent_t* ev, bool first_only, bool want_tail) {
     const Layout& L = s->L;
     const int m = s->m, n = s->n;
     double* Y = s->ptr(LCX_A_Y);
@@ -425,21 +457,19 @@ static int oz_pair_t(lcx_session* s, const double* A, double* svec, cudaEvent_t*
         p.rows = m; p.cols = n; p.k_total = (int)s->Nl; p.k_chunk = L.oz_chunk;
         LCX_TRY((oz::launch_oz_gemm<S, false>(s->map_y_k2, s->map_x_k2, p, dim3(cdiv(n, oz::kBN), cdiv(m, oz::kBM), L.oz_splits), s->stream)));
         LAUNCHED(s);
-        if (split) {
-            LCX_TRY(launch_reduce_splits(s->ptr(I_PART), L.oz_splits, (long long)m * L.ld, D, m, n, L.ld, s->stream));
-            LAUNCHED(s);
-        }
+        LCX_TRY(combine_and_allreduce(s, split ? s->ptr(I_PART) : D, split ? L.oz_splits : 1, (long long)m * L.ld, m, n, L.ld, D, svec,
+                                      want_tail ? m : 0));
     }
     LCX_CUDA(cudaGetLastError());
     return 0;
 }
 
-static int oz_pair(lcx_session* s, const double* A, double* svec, cudaEvent_t* ev, bool first_only = false) {
+static int oz_pair(lcx_session* s, const double* A, double* svec, cudaEvent_t* ev, bool first_only, bool want_tail) {
     switch (s->L.S) {
-        case 3: return oz_pair_t<3>(s, A, svec, ev, first_only);
-        case 4: return oz_pair_t<4>(s, A, svec, ev, first_only);
-        case 5: return oz_pair_t<5>(s, A, svec, ev, first_only);
-        case 6: return oz_pair_t<6>(s, A, svec, ev, first_only);
+        case 3: return oz_pair_t<3>(s, A, svec, ev, first_only, want_tail);
+        case 4: return oz_pair_t<4>(s, A, svec, ev, first_only, want_tail);
+        case 5: return oz_pair_t<5>(s, A, svec, ev, first_only, want_tail);
+        case 6: return oz_pair_t<6>(s, A, svec, ev, first_only, want_tail);
     }
     return fail(LCX_ERR_STATE, "oz_pair", "bad digit count");
 }
@@ -599,9 +629,52 @@ extern "C" int lcx_standardize(lcx_session* s, const void* x, int dtype, long lo
 }
 
 // ---- GEMM plumbing -----------------------------------------------------------------------------
-static int run_gemm(lcx_session* s, GemmLayout lay, const GemmPlan& pl, GemmArgs a, double* part, long long out_count) {
+// Sum over ranks of [body = sum_z part[z] (rows x ld, valid cols) | tail (ntail doubles)] -> dst_body / dst_tail.
+// Peer path: ONE kernel (split-K combine + two-shot all-reduce over NVLink peer memory).  Otherwise the fixed-order
+// local combine followed by the installed hook (NCCL through torch.distributed), or nothing on a single rank.
+static int combine_and_allreduce(lcx_session* s, const double* part, int splits, long long stride, int rows, int cols,
+                                 long long ld, double* dst_body, double* tail, int ntail) {
+    const long long body = (long long)rows * ld;
+    if (s->peers.world > 1) {
+        LCX_REQUIRE(body + ntail <= s->peers.count, "peer buffer too small");
+        const int slot = (int)(s->ar_calls & 1);
+        unsigned long long epoch0 = 2ULL * s->ar_calls;
+        s->ar_calls++;
+        far::Peers pp = s->peers;
+        const double* tl = tail;
+        void* args[] = {&pp, &part, &splits, &stride, &rows, &cols, &ld, &tl, &ntail, (void*)&slot, &epoch0};
+        LCX_CUDA(cudaLaunchCooperativeKernel((void*)far::reduce_allreduce_kernel, dim3(kSMs), dim3(512), args, 0, s->stream));
+        LAUNCHED(s);
+        const double* out = s->peers.base[s->peers.rank] + 2 * s->peers.count;
+        if (rows > 0)
+            LCX_CUDA(cudaMemcpyAsync(dst_body, out, (size_t)body * sizeof(double), cudaMemcpyDeviceToDevice, s->stream));
+        if (ntail > 0)
+            LCX_CUDA(cudaMemcpyAsync(tail, out + body, (size_t)ntail * sizeof(double), cudaMemcpyDeviceToDevice, s->stream));
+        return 0;
+    }
+    if (rows > 0 && (splits > 1 || part != dst_body)) {
+        LCX_TRY(launch_reduce_splits(part, splits, stride, dst_body, rows, cols, ld, s->stream));
+        LAUNCHED(s);
+    }
+    if (s->hook) {
+        // body and tail are contiguous in the workspace (D is followed by the column sums of squares)
+        const long long off = (rows > 0 ? dst_body : tail) - s->ws;
+        if (s->hook(s->hook_user, off, (rows > 0 ? body : 0) + ntail) != 0)
+            return fail(LCX_ERR_STATE, "allreduce hook", "hook reported failure");
+    }
+    return 0;
+}
+
+static int run_gemm(lcx_session* s, GemmLayout lay, const GemmPlan& pl, GemmArgs a, double* part, long long out_count,
+                    bool leave_partials = false) {
     // out_count = number of doubles of one full output (rows * ldc) -- the split stride
-    if (pl.splits > 1) {
+    if (pl.splits > 1 && leave_partials) {
+        LCX_REQUIRE(a.Cadd == nullptr, "split-K with Cadd is not supported");
+        a.C = part;
+        a.c_split_stride = out_count;
+        LCX_TRY(launch_gemm(lay, pl, a, s->stream));
+        LAUNCHED(s);
+    } else if (pl.splits > 1) {
         double* final_c = a.C;
         const double* cadd = a.Cadd;
         LCX_REQUIRE(cadd == nullptr, "split-K with Cadd is not supported");
@@ -631,7 +704,7 @@ static int xpair(lcx_session* s, const double* A, bool want_colsq) {
     if (s->prof_on && s->prof_pending < s->prof_cap) ev = s->prof_ev + 4 * s->prof_pending;
     if (ev) LCX_CUDA(cudaEventRecord(ev[0], s->stream));
     if (L.S > 0) {
-        LCX_TRY(oz_pair(s, A, svec, ev));
+        LCX_TRY(oz_pair(s, A, svec, ev, false, want_colsq));
         if (ev) {
             LCX_CUDA(cudaEventRecord(ev[2], s->stream));
             s->prof_pending++;
@@ -669,18 +742,17 @@ static int xpair(lcx_session* s, const double* A, bool want_colsq) {
         a.lda = s->ldx; a.ldb = L.ldy; a.ldc = L.ld;
         a.trans_out = 1;
         if (ev) LCX_CUDA(cudaEventRecord(ev[3], s->stream));  // K2 starts after the (tiny) colsq reduction
-        LCX_TRY(run_gemm(s, kLayoutMN, L.plan_k2, a, s->ptr(I_PART), (long long)m * L.ld));
+        LCX_TRY(run_gemm(s, kLayoutMN, L.plan_k2, a, s->ptr(I_PART), (long long)m * L.ld, true));
         if (ev) {
             LCX_CUDA(cudaEventRecord(ev[2], s->stream));
             s->prof_pending++;
         }
+        const bool split = L.plan_k2.splits > 1;
+        LCX_TRY(combine_and_allreduce(s, split ? s->ptr(I_PART) : D, split ? L.plan_k2.splits : 1, (long long)m * L.ld, m, n, L.ld,
+                                      D, svec, want_colsq ? m : 0));
     }
     }
     LCX_CUDA(cudaGetLastError());
-    if (s->hook) {
-        const int rc = s->hook(s->hook_user, s->off(LCX_A_D), (long long)m * L.ld + (want_colsq ? m : 0));
-        if (rc != 0) return fail(LCX_ERR_STATE, "allreduce hook", "hook reported failure");
-    }
     return 0;
 }
 
@@ -812,15 +884,12 @@ extern "C" int lcx_init_scale(lcx_session* s, double eps) {
     double* W = s->ptr(LCX_A_W);
     double* svec = s->ptr(LCX_A_D) + (long long)m * L.ld;
     if (L.S > 0) {
-        LCX_TRY(oz_pair(s, W, svec, nullptr, true));
+        LCX_TRY(oz_pair(s, W, svec, nullptr, true, true));
     } else {
         LCX_TRY(lcx_project(s, s->xt, s->Nl, n, s->ldx, W, L.ld, m, s->ptr(LCX_A_Y), L.ldy, svec, s->ptr(I_COLSQ),
                             lcx_project_scratch_doubles(s->Nl, m)));
     }
-    if (s->hook) {
-        if (s->hook(s->hook_user, s->off(LCX_A_D) + (long long)m * L.ld, m) != 0)
-            return fail(LCX_ERR_STATE, "allreduce hook", "hook reported failure");
-    }
+    LCX_TRY(combine_and_allreduce(s, nullptr, 1, 0, 0, 0, L.ld, nullptr, svec, m));  // sum of Y^2 over ranks
     row_dot_kernel<<<m, 256, 0, s->stream>>>(W, W, s->ptr(I_W2), n, L.ld);
     LAUNCHED(s);
     const double c1 = (1.0 - eps * eps) / (double)s->Nt, e2 = eps * eps;

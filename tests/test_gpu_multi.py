@@ -10,7 +10,8 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _worker(rank, world, port, ret):
+def _worker(rank, world, port, ret, peer_mode):
+    os.environ["LCX_PEER_ALLREDUCE"] = peer_mode
     import torch
     import torch.distributed as dist
     sys.path.insert(0, ROOT)
@@ -24,11 +25,13 @@ def _worker(rank, world, port, ret):
         from conftest import load_golden
         from linearcorex_b200 import Corex, shard_rows
         out = {}
-        for name in ("syn_400x300x10_f64", "standard_missing_f64"):
+        for name, prec in (("syn_400x300x10_f64", "fp64"), ("standard_missing_f64", "fp64"), ("syn_400x300x10_f64", "fp64_split")):
             z, kw, x = load_golden(name)
+            kw = dict(kw, precision=prec)
             lo, hi = shard_rows(x.shape[0], rank, world)
             mdl = Corex(comm=True, **kw).fit(x[lo:hi])
             assert mdl.n_samples == x.shape[0]
+            assert (mdl._sess._peer_buf is not None) == (peer_mode == "require")
             assert len(mdl.history["TC"]) == len(z["history_TC"])
             err = np.abs(mdl.ws - z["ws"]).max() / np.abs(z["ws"]).max()
             err_tc = np.abs(mdl.moments["TCs"] - z["m_TCs"]).max() / np.abs(z["m_TCs"]).max()
@@ -51,12 +54,14 @@ def _worker(rank, world, port, ret):
         dist.destroy_process_group()
 
 
-def test_two_rank_nccl_fit_matches_golden():
+@pytest.mark.parametrize("peer_mode", ["require", "0"])
+def test_two_rank_nccl_fit_matches_golden(peer_mode):
+    """peer_mode 'require': the fused split-K-combine + all-reduce kernel over NVLink peer memory; '0': NCCL hook."""
     import torch
     import torch.multiprocessing as mp
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     mgr = mp.Manager()
     ret = mgr.dict()
-    mp.spawn(_worker, args=(2, 29700 + os.getpid() % 1000, ret), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, 29700 + os.getpid() % 1000 + (7 if peer_mode == "0" else 0), ret, peer_mode), nprocs=2, join=True)
     assert all(str(v).startswith("ok") for v in ret.values()) and len(ret) == 2, dict(ret)
