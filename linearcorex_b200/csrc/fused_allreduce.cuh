@@ -70,28 +70,54 @@ __global__ void __launch_bounds__(512) reduce_allreduce_kernel(Peers p, const do
     double* my_slot = p.base[p.rank] + (long long)slot * p.count;
     const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long nthr = (long long)gridDim.x * blockDim.x;
-    // ---- A: local split-K combine (fixed order), padding columns zeroed ----
-    for (long long i = tid; i < count; i += nthr) {
-        double acc = 0.0;
-        if (i < body) {
-            const int c = (int)(i % ld);
-            if (c < cols) {
-                acc = part[i];
-                for (int z = 1; z < splits; ++z) acc += part[(long long)z * stride + i];
+    // ---- A: local split-K combine (fixed order z = 0, 1, ...), 16-byte accesses, four loads in flight; padding
+    //         columns are written as zeros.  body and ld are even, so pairs never straddle a row. ----
+    const unsigned ld2 = (unsigned)(ld >> 1);
+    const long long body2 = body >> 1;
+    for (long long i2 = tid; i2 < body2; i2 += nthr) {
+        const unsigned c = ((unsigned)i2 % ld2) * 2u;  // body < 2^32 doubles is enforced by the caller
+        double2 acc = make_double2(0.0, 0.0);
+        if ((int)c < cols) {
+            const double2* src = reinterpret_cast<const double2*>(part) + i2;
+            const long long s2 = stride >> 1;
+            acc = src[0];
+            int z = 1;
+            for (; z + 3 < splits; z += 4) {
+                const double2 v0 = src[(long long)z * s2], v1 = src[(long long)(z + 1) * s2];
+                const double2 v2 = src[(long long)(z + 2) * s2], v3 = src[(long long)(z + 3) * s2];
+                acc.x += v0.x; acc.y += v0.y;
+                acc.x += v1.x; acc.y += v1.y;
+                acc.x += v2.x; acc.y += v2.y;
+                acc.x += v3.x; acc.y += v3.y;
             }
-        } else {
-            acc = tail[i - body];
+            for (; z < splits; ++z) {
+                const double2 v = src[(long long)z * s2];
+                acc.x += v.x; acc.y += v.y;
+            }
+            if ((int)c + 1 >= cols) acc.y = 0.0;
         }
-        my_slot[i] = acc;
+        reinterpret_cast<double2*>(my_slot)[i2] = acc;
     }
+    for (long long i = body + tid; i < count; i += nthr) my_slot[i] = tail[i - body];
     cross_gpu_barrier(p, epoch0 + 1, grid);
-    // ---- B: this rank reduces its 1/P slice over all ranks (rank order) and broadcasts it ----
-    const long long per = (count + p.world - 1) / p.world;
-    const long long lo = per * p.rank, hi = min(count, lo + per);
-    for (long long i = lo + tid; i < hi; i += nthr) {
-        double acc = (p.base[0] + (long long)slot * p.count)[i];
-        for (int r = 1; r < p.world; ++r) acc += (p.base[r] + (long long)slot * p.count)[i];
-        for (int r = 0; r < p.world; ++r) (p.base[r] + 2 * p.count)[i] = acc;
+    // ---- B: this rank owns 1/P of the elements: P2P loads of that slice from every rank's slot (all issued before the
+    //         first add), sum in rank order, P2P stores of the result into every rank's output ----
+    const long long count2 = (count + 1) >> 1;             // slots are padded to an even length by the host
+    const long long per = (count2 + p.world - 1) / p.world;
+    const long long lo = per * p.rank, hi = min(count2, lo + per);
+    const long long slot_off2 = ((long long)slot * p.count) >> 1, out_off2 = p.count;  // (2 * count) / 2
+    for (long long i2 = lo + tid; i2 < hi; i2 += nthr) {
+        double2 v[kMaxRanks];
+#pragma unroll
+        for (int r = 0; r < kMaxRanks; ++r)
+            if (r < p.world) v[r] = (reinterpret_cast<const double2*>(p.base[r]) + slot_off2)[i2];
+        double2 acc = v[0];
+#pragma unroll
+        for (int r = 1; r < kMaxRanks; ++r)
+            if (r < p.world) { acc.x += v[r].x; acc.y += v[r].y; }
+#pragma unroll
+        for (int r = 0; r < kMaxRanks; ++r)
+            if (r < p.world) (reinterpret_cast<double2*>(p.base[r]) + out_off2)[i2] = acc;
     }
     cross_gpu_barrier(p, epoch0 + 2, grid);
 }

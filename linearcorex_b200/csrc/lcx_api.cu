@@ -646,6 +646,10 @@ static int combine_and_allreduce(lcx_session* s, const double* part, int splits,
         LCX_CUDA(cudaLaunchCooperativeKernel((void*)far::reduce_allreduce_kernel, dim3(kSMs), dim3(512), args, 0, s->stream));
         LAUNCHED(s);
         const double* out = s->peers.base[s->peers.rank] + 2 * s->peers.count;
+        if (rows > 0 && ntail > 0 && tail == dst_body + body) {  // D and the sums of squares are adjacent: one copy
+            LCX_CUDA(cudaMemcpyAsync(dst_body, out, (size_t)(body + ntail) * sizeof(double), cudaMemcpyDeviceToDevice, s->stream));
+            return 0;
+        }
         if (rows > 0)
             LCX_CUDA(cudaMemcpyAsync(dst_body, out, (size_t)body * sizeof(double), cudaMemcpyDeviceToDevice, s->stream));
         if (ntail > 0)
