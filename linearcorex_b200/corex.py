@@ -41,6 +41,7 @@ from . import _lib
 from .sharding import Reducer
 
 ANNEAL_SCHEDULE = [0.6 ** k for k in range(1, 7)] + [0]  # linearcorex.py:119
+_PEER_BUFFERS = {}  # (group, device, size) -> (symmetric tensor, handle): peer mappings are reused across fits
 
 
 def _torch():
@@ -73,6 +74,10 @@ class _DeviceSession(object):
         if getattr(self, "h", None) is not None and self.h:
             self.lib.lcx_session_destroy(self.h)
             self.h = None
+        entry = getattr(self, "_peer_entry", None)
+        if entry is not None:
+            entry[2] = False  # the peer buffer may be reused by the next session
+            self._peer_entry = None
 
     def __del__(self):
         try:
@@ -128,10 +133,20 @@ class _DeviceSession(object):
             import torch.distributed as dist
             import torch.distributed._symmetric_memory as symm
             need = self.lib.lcx_peer_buffer_doubles(n_vars, n_factors)
-            buf = symm.empty(need, dtype=torch.float64, device=self.device)
             group = reducer.group if reducer.group is not None else dist.group.WORLD
-            hdl = symm.rendezvous(buf, group)
-            buf.zero_()
+            key = (id(group), self.device.index, need)
+            # mapping peers costs ~0.1 s (VMM handles over the process group): a released buffer is reused by the next
+            # session of the same shape; a buffer still owned by a live session is never shared (its flags carry epochs)
+            entry = _PEER_BUFFERS.get(key)
+            if entry is None or entry[2]:
+                buf = symm.empty(need, dtype=torch.float64, device=self.device)
+                entry = [buf, symm.rendezvous(buf, group), True]
+                if key not in _PEER_BUFFERS:
+                    _PEER_BUFFERS[key] = entry
+            entry[2] = True
+            self._peer_entry = entry
+            buf, hdl = entry[0], entry[1]
+            buf.zero_()  # flags restart at zero for this session's epochs
             torch.cuda.synchronize(self.device)
             dist.barrier(group=reducer.group)  # nobody signals before every rank has zeroed its flags
             ptrs = (C.c_void_p * reducer.world)(*[int(p) for p in hdl.buffer_ptrs])
