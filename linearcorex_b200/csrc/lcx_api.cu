@@ -167,15 +167,17 @@ static Layout make_layout(long long Nl, int n, int m, int precision) {
         // at most 65536 samples per split keeps every int32 accumulator exact (<= 6 * 2^16 * 2^12 < 2^31)
         const long long tiles = (long long)cdiv(n, oz::kBN) * cdiv(m, oz::kBM);
         const int kblocks = cdiv(Nl, oz::kBK);
+        // time model in units of one 64-deep K block: waves x (K blocks per CTA + fixed prologue/TMEM-drain/store cost
+        // of ~16 blocks) + the partial-buffer round trip; measured at 12.5k and 100k rows per GPU
         int best = 1;
-        double best_score = -1.0;
+        double best_cost = 1e300;
         const int smin = cdiv(Nl, 65536), smax = (int)min(64LL, (long long)max(1, kblocks / 8));
         for (int sp = smin; sp <= max(smin, smax); ++sp) {
             const long long ctas = tiles * sp;
             const long long waves = (ctas + kSMs - 1) / kSMs;
-            const double kb = (double)kblocks / sp;
-            const double score = (double)ctas / (double)(waves * kSMs) * kb / (kb + 8.0);
-            if (score > best_score + 1e-9) { best_score = score; best = sp; }
+            const double kb = ceil((double)kblocks / sp);
+            const double cost = (double)waves * (kb + 16.0) + (sp > 1 ? 1.5 * sp : 0.0);
+            if (cost < best_cost - 1e-9) { best_cost = cost; best = sp; }
         }
         L.oz_chunk = (int)round_up(cdiv(Nl, best), oz::kBK);
         L.oz_splits = cdiv(Nl, L.oz_chunk);
