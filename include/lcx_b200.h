@@ -124,6 +124,11 @@ long long lcx_workspace_doubles(long long n_rows_local, int n_vars, int n_factor
  * planes inside the workspace before lcx_bind returns and may be released by the caller afterwards. */
 int lcx_bind(lcx_session* s, const double* xt, long long n_rows_local, long long n_rows_total, int n_vars,
              long long ldx, int n_factors, double* workspace, long long workspace_doubles);
+/* Streamed binding for data whose fp64 X~ does not fit beside its digit planes (split modes only): call lcx_bind with
+ * xt == NULL, then lcx_set_x_scale(max |X~|) once and lcx_slice_block for every row block [row0, row0 + rows) of X~
+ * (any order, each row exactly once) before the first fit step. */
+int lcx_set_x_scale(lcx_session* s, double max_abs);
+int lcx_slice_block(lcx_session* s, const double* xt, long long row0, long long rows, long long ldx);
 /* Offset (in doubles, from the workspace base), rows, cols and leading dimension of an array. */
 int lcx_array_info(lcx_session* s, int array_id, int set, long long* offset, long long* rows, long long* cols,
                    long long* ld);
@@ -136,8 +141,10 @@ int lcx_colstats_sum(lcx_session* s, const void* x, int dtype, long long n_rows,
 /* mean = sum / cnt  (after the caller all-reduced sum and cnt) */
 int lcx_colstats_mean(lcx_session* s, const double* sum, const double* cnt, double* mean, int n_vars);
 /* pass 2: per-column sum of squared deviations of observed entries -> sq[n] */
+/* maxdev (optional, device, n): per-column max |x - mean| over observed entries, so that max |X~| is known before
+ * X~ exists (streamed digit slicing) */
 int lcx_colstats_sqdev(lcx_session* s, const void* x, int dtype, long long n_rows, int n_vars, long long ldx,
-                       int has_marker, double marker, const double* mean, double* sq, double* scratch,
+                       int has_marker, double marker, const double* mean, double* sq, double* maxdev, double* scratch,
                        long long scratch_doubles);
 /* std = clip(sqrt(sq / (use_nobs ? cnt : n_rows_total)), 1e-10)   (:413 vs :421) */
 int lcx_colstats_std(lcx_session* s, const double* sq, const double* cnt, double n_rows_total, int use_nobs,

@@ -30,6 +30,9 @@ behaviour):
                       'float32' reproduces the reference's cast at :108 and :116.
   comm                None, or a torch.distributed process group / True for the default group:
                       `fit(x)` then takes this rank's row block of X (sample sharding).
+  stream_rows         split modes: prepare X in row blocks of this many rows (three streaming passes over the raw
+                      input, X~ never materialised in fp64).  Default: automatic when X~ would not fit -- this is
+                      what lets the 1M x 20k x 100 target run on ONE B200 (120 GB of int8 digit planes).
 """
 import ctypes as C
 import os
@@ -91,16 +94,19 @@ class _DeviceSession(object):
         _lib.check(self.lib.lcx_launch_count(self.h, C.byref(v)))
         return v.value
 
-    def bind(self, xt, n_rows_total, n_vars, n_factors, reducer):
+    def bind(self, xt, n_rows_total, n_vars, n_factors, reducer, n_local=None):
+        """xt = preprocessed fp64 block, or None (split modes) when the digit planes are filled block by block
+        through lcx_slice_block afterwards (`n_local` rows)."""
         torch = _torch()
-        n_local = xt.shape[0]
+        n_local = xt.shape[0] if xt is not None else int(n_local)
         need = self.lib.lcx_workspace_doubles(n_local, n_vars, n_factors, self.precision)
         if need <= 0:
             raise _lib.LcxError("bad problem shape")
         self.ws = torch.zeros(need, dtype=torch.float64, device=self.device)
         self.xt = xt
         self.n, self.m = n_vars, n_factors
-        _lib.check(self.lib.lcx_bind(self.h, xt.data_ptr(), n_local, n_rows_total, n_vars, xt.stride(0), n_factors,
+        _lib.check(self.lib.lcx_bind(self.h, xt.data_ptr() if xt is not None else None, n_local, n_rows_total, n_vars,
+                                     xt.stride(0) if xt is not None else self.lib.lcx_ld(n_vars), n_factors,
                                      self.ws.data_ptr(), need), "lcx_bind")
         if self.precision != _lib.PRECISION_FP64:
             self.xt = None  # the split modes keep int8 digit planes in the workspace; the fp64 block is released
@@ -178,7 +184,7 @@ class Corex(object):
     def __init__(self, n_hidden=10, max_iter=10000, tol=1e-5, anneal=True, missing_values=None,
                  discourage_overlap=True, gaussianize='standard', gpu=True, verbose=False, seed=None,
                  eliminate_synergy=None, precision='fp64', exact_trials=False, input_dtype='float64',
-                 comm=None, device=None):
+                 comm=None, device=None, stream_rows=None):
         self.m = n_hidden
         self.max_iter = max_iter
         self.tol = tol
@@ -201,6 +207,7 @@ class Corex(object):
         self.precision = precision
         self.exact_trials = bool(exact_trials)
         self.input_dtype = input_dtype
+        self.stream_rows = stream_rows  # row-block size of the streamed preparation (None = decide from free memory)
         np.random.seed(seed)  # :89 -- the reference seeds the *global* legacy RNG at construction
         self.verbose = verbose
         if verbose:
@@ -355,7 +362,7 @@ class Corex(object):
                 mean = impute
                 sq, sd = vec(), vec()
                 _lib.check(lib.lcx_colstats_sqdev(sess.h, xd.data_ptr(), dt, N, n, xd.stride(0), int(has_marker), marker,
-                                                  mean.data_ptr(), sq.data_ptr(), scratch.data_ptr(), nscr),
+                                                  mean.data_ptr(), sq.data_ptr(), None, scratch.data_ptr(), nscr),
                            "lcx_colstats_sqdev")
                 red.sum_(sq)
                 _lib.check(lib.lcx_colstats_std(sess.h, sq.data_ptr(), cnt.data_ptr(), float(n_total),
@@ -400,18 +407,22 @@ class Corex(object):
         sess = self._session()
         lib = sess.lib
         red = self._reducer()
-        t0 = time.perf_counter()
-        xt = self.preprocess(x, fit=True)
-        _torch().cuda.synchronize()
-        self.timings["preprocess_s"] = time.perf_counter() - t0
-        n_local, self.nv = xt.shape[0], int(np.shape(x)[1])
-        self.n_samples = int(red.sum_scalar(n_local))
         if self.m is None:
             raise ValueError("n_hidden=None (pick_n_hidden) is not supported: the reference helper is broken (:458-480)")
-        t0 = time.perf_counter()
-        sess.bind(xt, self.n_samples, self.nv, self.m, red)
-        _torch().cuda.synchronize()
-        self.timings["bind_s"] = time.perf_counter() - t0
+        rows = self._stream_rows_for(x)
+        if rows:
+            self._prepare_streamed(x, rows, red)
+        else:
+            t0 = time.perf_counter()
+            xt = self.preprocess(x, fit=True)
+            _torch().cuda.synchronize()
+            self.timings["preprocess_s"] = time.perf_counter() - t0
+            n_local, self.nv = xt.shape[0], int(np.shape(x)[1])
+            self.n_samples = int(red.sum_scalar(n_local))
+            t0 = time.perf_counter()
+            sess.bind(xt, self.n_samples, self.nv, self.m, red)
+            _torch().cuda.synchronize()
+            self.timings["bind_s"] = time.perf_counter() - t0
         schedule = [0.]
         if self.ws.size == 0:  # :114-121
             if self.discourage_overlap:
@@ -428,6 +439,86 @@ class Corex(object):
             self._set_w(self.ws)
         self.moments = {"TC": self._moments_from_x()}  # :122
         return schedule
+
+    def _stream_rows_for(self, x):
+        """Row-block size for streamed preparation, or 0 for the one-shot path.  Streaming applies to the split modes
+        when the fp64 image of X~ would not fit beside its int8 digit planes (or when `stream_rows` forces it)."""
+        if self.precision == 'fp64' or self.gaussianize == 'none':
+            return 0
+        if self.stream_rows:
+            return int(self.stream_rows)
+        torch = _torch()
+        n_rows, n_vars = int(np.shape(x)[0]), int(np.shape(x)[1])
+        free, _total = torch.cuda.mem_get_info(self._session().device)
+        digits = 6 if self.precision == 'fp64_split' else 4
+        need = n_rows * self._session().lib.lcx_ld(n_vars) * (8 + digits + 4)
+        return 32768 if need > 0.8 * free else 0
+
+    def _prepare_streamed(self, x, rows, red):
+        """preprocess(fit=True) + bind without ever holding all of X~ in fp64 (SURVEY.md hard part 4): three passes over
+        row blocks of the raw input -- column sums/counts; squared deviations and max |x - mean|; standardise + digit
+        slicing.  `x` only needs `.shape` and row slicing (ndarray, memmap, tensor, or a generator-backed object)."""
+        torch = _torch()
+        sess = self._session()
+        lib = sess.lib
+        t0 = time.perf_counter()
+        N, n = int(np.shape(x)[0]), int(np.shape(x)[1])
+        self.nv = n
+        ld = lib.lcx_ld(n)
+        has_marker = self.missing_values is not None
+        marker = float(self.missing_values) if has_marker else 0.0
+        mode = _lib.GAUSS[self.gaussianize]
+        vec = lambda: torch.zeros(n, dtype=torch.float64, device=sess.device)
+        nscr = lib.lcx_colstats_scratch_doubles(rows, n)
+        scratch = torch.empty(nscr, dtype=torch.float64, device=sess.device)
+        blocks = [(lo, min(N, lo + rows)) for lo in range(0, N, rows)]
+
+        def block(lo, hi):
+            xd = self._as_input(x[lo:hi])
+            return xd, (_lib.F32 if xd.dtype == torch.float32 else _lib.F64)
+
+        ssum, cnt, t1, t2 = vec(), vec(), vec(), vec()
+        for lo, hi in blocks:  # pass 1
+            xd, dt = block(lo, hi)
+            _lib.check(lib.lcx_colstats_sum(sess.h, xd.data_ptr(), dt, hi - lo, n, xd.stride(0), int(has_marker), marker,
+                                            t1.data_ptr(), t2.data_ptr(), scratch.data_ptr(), nscr), "lcx_colstats_sum")
+            ssum += t1
+            cnt += t2
+        red.sum_(ssum)
+        red.sum_(cnt)
+        n_total = red.sum_scalar(N)
+        mean, sq, maxdev, sd = vec(), vec(), vec(), vec()
+        _lib.check(lib.lcx_colstats_mean(sess.h, ssum.data_ptr(), cnt.data_ptr(), mean.data_ptr(), n))
+        for lo, hi in blocks:  # pass 2
+            xd, dt = block(lo, hi)
+            _lib.check(lib.lcx_colstats_sqdev(sess.h, xd.data_ptr(), dt, hi - lo, n, xd.stride(0), int(has_marker), marker,
+                                              mean.data_ptr(), t1.data_ptr(), t2.data_ptr(), scratch.data_ptr(), nscr),
+                       "lcx_colstats_sqdev")
+            sq += t1
+            maxdev = torch.maximum(maxdev, t2)
+        red.sum_(sq)
+        _lib.check(lib.lcx_colstats_std(sess.h, sq.data_ptr(), cnt.data_ptr(), float(n_total),
+                                        int(self.gaussianize == 'standard'), sd.data_ptr(), n))
+        self._theta_dev = (mean, sd)
+        self.theta = (mean.cpu().numpy().copy(), sd.cpu().numpy().copy())
+        self.n_obs = cnt.cpu().numpy().astype(np.int64) if has_marker else int(n_total)
+        zmax = float((maxdev / sd).max().item())
+        if self.gaussianize == 'outliers':
+            zmax = min(zmax, 4.0) + float(np.tanh(max(zmax - 4.0, 0.0)))  # g() is monotone (:483-487)
+        self.n_samples = int(n_total)
+        self.timings["preprocess_s"] = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        sess.bind(None, self.n_samples, n, self.m, red, n_local=N)
+        _lib.check(lib.lcx_set_x_scale(sess.h, zmax), "lcx_set_x_scale")
+        xt = torch.empty((rows, ld), dtype=torch.float64, device=sess.device)
+        for lo, hi in blocks:  # pass 3
+            xd, dt = block(lo, hi)
+            _lib.check(lib.lcx_standardize(sess.h, xd.data_ptr(), dt, hi - lo, n, xd.stride(0), int(has_marker), marker, mode,
+                                           mean.data_ptr(), mean.data_ptr(), sd.data_ptr(), xt.data_ptr(), ld),
+                       "lcx_standardize")
+            _lib.check(lib.lcx_slice_block(sess.h, xt.data_ptr(), lo, hi - lo, ld), "lcx_slice_block")
+        torch.cuda.synchronize()
+        self.timings["bind_s"] = time.perf_counter() - t0
 
     def _moments_from_x(self):
         """quick moments of the current W from X~ (one pass pair); returns TC."""

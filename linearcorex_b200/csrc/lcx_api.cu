@@ -391,10 +391,10 @@ static int oz_slice_x_t(lcx_session* s) {
     return 0;
 }
 
-static int oz_prepare(lcx_session* s) {
+static int oz_prepare(lcx_session* s, bool streamed) {
     const Layout& L = s->L;
     LCX_REQUIRE(s->n <= 65536, "split-integer modes support at most 65536 variables per contraction (int32 exactness)");
-    switch (L.S) {
+    if (!streamed) switch (L.S) {
         case 3: LCX_TRY(oz_slice_x_t<3>(s)); break;
         case 4: LCX_TRY(oz_slice_x_t<4>(s)); break;
         case 5: LCX_TRY(oz_slice_x_t<5>(s)); break;
@@ -479,11 +479,14 @@ static int oz_pair(lcx_session* s, const double* A, double* svec, cudaEvent_t* e
 extern "C" int lcx_bind(lcx_session* s, const double* xt, long long n_rows_local, long long n_rows_total, int n_vars,
                         long long ldx, int n_factors, double* workspace, long long workspace_doubles) {
     LCX_REQUIRE(s != nullptr, "null session");
-    LCX_REQUIRE(xt != nullptr && workspace != nullptr, "null device pointer");
+    LCX_REQUIRE(workspace != nullptr, "null device pointer");
+    LCX_REQUIRE(xt != nullptr || s->precision != LCX_PRECISION_FP64,
+                "xt may be NULL only in the split modes (digit planes are then filled by lcx_slice_block)");
     LCX_REQUIRE(n_rows_local > 0 && n_rows_local < (1LL << 31) && n_rows_total >= n_rows_local, "bad row counts");
     LCX_REQUIRE(n_vars > 0 && n_factors > 0, "bad shape");
     LCX_REQUIRE(ldx >= n_vars && ldx % 2 == 0, "ldx must be even and >= n_vars");
     LCX_REQUIRE(((uintptr_t)xt % 16 == 0) && ((uintptr_t)workspace % 128 == 0), "misaligned device pointer");
+    const bool streamed = (xt == nullptr);
     Layout L = make_layout(n_rows_local, n_vars, n_factors, s->precision);
     LCX_REQUIRE(workspace_doubles >= L.total, "workspace too small (see lcx_workspace_doubles)");
     LCX_CUDA(cudaSetDevice(s->device));
@@ -503,11 +506,51 @@ extern "C" int lcx_bind(lcx_session* s, const double* xt, long long n_rows_local
     const long long y_end = align16(y_off + n_rows_local * L.ldy);
     LCX_CUDA(cudaMemsetAsync(workspace + y_end, 0, (size_t)(L.total - y_end) * sizeof(double), s->stream));
     if (L.S > 0) {
-        LCX_TRY(oz_prepare(s));  // digit slices of X~; after this X~ itself is never read again in the split modes,
+        LCX_TRY(oz_prepare(s, streamed));  // digit slices of X~; after this X~ itself is never read again in the split modes,
         LCX_CUDA(cudaStreamSynchronize(s->stream));  // so the caller may release it as soon as lcx_bind returns
         s->xt = nullptr;
     }
     return 0;
+}
+
+// ---- streamed digit slicing (X~ never materialised as a whole: the 1M x 20k target on one GPU) -------------------
+extern "C" int lcx_set_x_scale(lcx_session* s, double max_abs) {
+    S_REQUIRE_BOUND(s);
+    LCX_REQUIRE(s->L.S > 0, "only meaningful in the split modes");
+    LCX_REQUIRE(max_abs >= 0.0 && max_abs == max_abs, "max_abs must be a finite non-negative bound on |X~|");
+    int e = 0;
+    double scale = 1.0;
+    if (max_abs > 0.0) {
+        frexp(max_abs, &e);
+        scale = ldexp(1.0, e + 1);
+    }
+    LCX_CUDA(cudaMemcpyAsync(s->oz_xscale(), &scale, sizeof(double), cudaMemcpyHostToDevice, s->stream));
+    LCX_CUDA(cudaStreamSynchronize(s->stream));
+    return 0;
+}
+
+template <int S>
+static int oz_slice_block_t(lcx_session* s, const double* xt, long long row0, long long rows, long long ldx) {
+    const Layout& L = s->L;
+    dim3 grid((unsigned)rows, cdiv(L.ld8, 4 * 128));
+    oz::slice_rows_kernel<S><<<grid, 128, 0, s->stream>>>(xt, ldx, (int)rows, s->n, nullptr, s->oz_xscale(), s->xs() + row0 * L.ld8,
+                                                        L.ld8, s->Nl * L.ld8);
+    LAUNCHED(s);
+    LCX_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int lcx_slice_block(lcx_session* s, const double* xt, long long row0, long long rows, long long ldx) {
+    S_REQUIRE_BOUND(s);
+    LCX_REQUIRE(s->L.S > 0, "only meaningful in the split modes");
+    LCX_REQUIRE(xt != nullptr && row0 >= 0 && rows > 0 && row0 + rows <= s->Nl && ldx >= s->n, "bad row block");
+    switch (s->L.S) {
+        case 3: return oz_slice_block_t<3>(s, xt, row0, rows, ldx);
+        case 4: return oz_slice_block_t<4>(s, xt, row0, rows, ldx);
+        case 5: return oz_slice_block_t<5>(s, xt, row0, rows, ldx);
+        case 6: return oz_slice_block_t<6>(s, xt, row0, rows, ldx);
+    }
+    return fail(LCX_ERR_STATE, "lcx_slice_block", "bad digit count");
 }
 
 extern "C" int lcx_array_info(lcx_session* s, int array_id, int set, long long* offset, long long* rows, long long* cols,
@@ -572,28 +615,33 @@ extern "C" int lcx_colstats_mean(lcx_session* s, const double* sum, const double
 
 template <typename T>
 static int colstats_sqdev_t(lcx_session* s, const T* x, long long N, int n, long long ldx, int has_marker, double marker,
-                            const double* mean, double* sq, double* scratch) {
+                            const double* mean, double* sq, double* maxdev, double* scratch) {
     const int slabs = cdiv(N, kSlabRows);
     const long long ldp = round_up(n, 16);
+    double* pmax = maxdev ? scratch + (long long)slabs * ldp : nullptr;
     dim3 grid(cdiv(n, 32), slabs), block(32, 8);
     colstats_sqdev_kernel<T><<<grid, block, 0, s->stream>>>(x, N, n, ldx, kSlabRows, has_marker, marker, marker != marker,
-                                                          mean, scratch, ldp);
+                                                          mean, scratch, pmax, ldp);
     LAUNCHED(s);
     combine_slabs_kernel<<<cdiv(n, 256), 256, 0, s->stream>>>(scratch, slabs, ldp, sq, n);
     LAUNCHED(s);
+    if (maxdev) {
+        combine_slabs_max_kernel<<<cdiv(n, 256), 256, 0, s->stream>>>(pmax, slabs, ldp, maxdev, n);
+        LAUNCHED(s);
+    }
     LCX_CUDA(cudaGetLastError());
     return 0;
 }
 
 extern "C" int lcx_colstats_sqdev(lcx_session* s, const void* x, int dtype, long long n_rows, int n_vars, long long ldx,
-                                  int has_marker, double marker, const double* mean, double* sq, double* scratch,
-                                  long long scratch_doubles) {
+                                  int has_marker, double marker, const double* mean, double* sq, double* maxdev,
+                                  double* scratch, long long scratch_doubles) {
     LCX_REQUIRE(s && x && mean && sq && scratch, "null argument");
     LCX_REQUIRE(n_rows > 0 && n_vars > 0 && ldx >= n_vars, "bad shape");
     LCX_REQUIRE(scratch_doubles >= lcx_colstats_scratch_doubles(n_rows, n_vars), "scratch too small");
     LCX_CUDA(cudaSetDevice(s->device));
-    if (dtype == LCX_F32) return colstats_sqdev_t<float>(s, (const float*)x, n_rows, n_vars, ldx, has_marker, marker, mean, sq, scratch);
-    if (dtype == LCX_F64) return colstats_sqdev_t<double>(s, (const double*)x, n_rows, n_vars, ldx, has_marker, marker, mean, sq, scratch);
+    if (dtype == LCX_F32) return colstats_sqdev_t<float>(s, (const float*)x, n_rows, n_vars, ldx, has_marker, marker, mean, sq, maxdev, scratch);
+    if (dtype == LCX_F64) return colstats_sqdev_t<double>(s, (const double*)x, n_rows, n_vars, ldx, has_marker, marker, mean, sq, maxdev, scratch);
     return fail(LCX_ERR_ARG, "lcx_colstats_sqdev", "unknown dtype");
 }
 

@@ -51,12 +51,14 @@ template <typename T>
 __global__ void __launch_bounds__(256) colstats_sqdev_kernel(const T* __restrict__ x, long long N, int n, long long ldx,
                                                              int rows_per_slab, int has_marker, double marker,
                                                              int marker_is_nan, const double* __restrict__ mean,
-                                                             double* __restrict__ part, long long ldp) {
-    __shared__ double rs[8][32];
+                                                             double* __restrict__ part, double* __restrict__ part_max,
+                                                             long long ldp) {
+    // part_max (optional): per-slab max |x - mean| -- bounds |X~| before X~ exists (streamed digit slicing)
+    __shared__ double rs[8][32], rm[8][32];
     const int i = blockIdx.x * 32 + threadIdx.x;
     const long long r0 = (long long)blockIdx.y * rows_per_slab;
     const long long r1 = min(N, r0 + rows_per_slab);
-    double s = 0.0;
+    double s = 0.0, mx = 0.0;
     if (i < n) {
         const double mu = mean[i];
         for (long long r = r0 + threadIdx.y; r < r1; r += 8) {
@@ -64,16 +66,33 @@ __global__ void __launch_bounds__(256) colstats_sqdev_kernel(const T* __restrict
             if (!is_missing(v, has_marker, marker, marker_is_nan)) {
                 const double d = (double)v - mu;
                 s += d * d;
+                mx = fmax(mx, fabs(d));
             }
         }
     }
     rs[threadIdx.y][threadIdx.x] = s;
+    rm[threadIdx.y][threadIdx.x] = mx;
     __syncthreads();
     if (threadIdx.y == 0 && i < n) {
-        double a = 0.0;
+        double a = 0.0, b = 0.0;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) a += rs[k][threadIdx.x];
+        for (int k = 0; k < 8; ++k) {
+            a += rs[k][threadIdx.x];
+            b = fmax(b, rm[k][threadIdx.x]);
+        }
         part[(long long)blockIdx.y * ldp + i] = a;
+        if (part_max) part_max[(long long)blockIdx.y * ldp + i] = b;
+    }
+}
+
+// out[i] = max_slab part[slab][i]
+__global__ void combine_slabs_max_kernel(const double* __restrict__ part, int slabs, long long ldp, double* __restrict__ out,
+                                         int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        double a = 0.0;
+        for (int s = 0; s < slabs; ++s) a = fmax(a, part[(long long)s * ldp + i]);
+        out[i] = a;
     }
 }
 

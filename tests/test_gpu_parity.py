@@ -240,6 +240,15 @@ def test_fit_fast_mode_fixed_budget(name):
     np.testing.assert_array_equal(mdl.clusters(), ref.clusters())
 
 
+@pytest.mark.parametrize("name", ["syn_400x300x10_f64", "outliers_missing_f64", "standard_missing_f64"])
+def test_streamed_preparation_matches_golden(name):
+    """Row-block streaming (three passes over the raw input, X~ never materialised in fp64; lcx_set_x_scale +
+    lcx_slice_block) must give the same fit as the one-shot path -- this is the path the 1M x 20k target uses."""
+    z, mdl, x = _fit(name, precision="fp64_split", stream_rows=96)
+    assert mdl._sess.xt is None
+    _check_fit(z, mdl, x, RTOL)
+
+
 def test_synthetic_4000x2000x20_fp64_split():
     z, mdl, x = _fit("syn_4000x2000x20_f64", precision="fp64_split")
     _check_fit(z, mdl, x, RTOL)
