@@ -185,9 +185,12 @@ static Layout make_layout(long long Nl, int n, int m, int precision) {
         if (part > L.slot[I_PART][0].cols) {  // grow the split-K partial buffer (it is the last big slot before these)
             put1(I_PART, 1, part, part);
         }
-        put1(I_XS, 1, cdiv((long long)L.S * Nl * L.ld8, 8), cdiv((long long)L.S * Nl * L.ld8, 8));
-        put1(I_AS, 1, cdiv((long long)L.S * mn * L.ld8, 8), cdiv((long long)L.S * mn * L.ld8, 8));
-        put1(I_YS, 1, cdiv((long long)L.S * Nl * L.ldy8, 8), cdiv((long long)L.S * Nl * L.ldy8, 8));
+        const long long xs8 = ((long long)L.S * Nl * L.ld8 + 7) / 8;   // int8 planes counted in doubles (64-bit sizes:
+        const long long as8 = ((long long)L.S * mn * L.ld8 + 7) / 8;   // the target shape has 1.5e10 doubles of planes)
+        const long long ys8 = ((long long)L.S * Nl * L.ldy8 + 7) / 8;
+        put1(I_XS, 1, xs8, xs8);
+        put1(I_AS, 1, as8, as8);
+        put1(I_YS, 1, ys8, ys8);
         put1(I_AMAX, 1, kAmaxCtas, kAmaxCtas);
     }
     L.total = cur;
