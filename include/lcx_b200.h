@@ -183,6 +183,9 @@ int lcx_direction_ns(lcx_session* s, double eps, double* tangent);
 /* one backtracking trial (:320-321): set 1 <- moments of ws + eta*update.
  * exact = 0: through the linearity of _sig (no pass over X);  exact = 1: from X~ like the reference. */
 int lcx_trial_ns(lcx_session* s, double eps, double eta, int exact, double* tc, double* max_uj);
+/* direction + first (linear) trial at `eta` enqueued back to back with ONE host synchronisation; the trial is
+ * speculative -- discard it when tangent >= 0 (:306-311) */
+int lcx_direction_trial_ns(lcx_session* s, double eps, double eta, double* tangent, double* tc, double* max_uj);
 int lcx_accept_trial(lcx_session* s);                                            /* set 0 <-> set 1 (:333-334)   */
 /* _calculate_moments_syn (:336-373) for set 0; host output TC */
 int lcx_moments_syn(lcx_session* s, double* tc, double* additivity);

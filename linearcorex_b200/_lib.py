@@ -62,6 +62,7 @@ SIGNATURES = {
     "lcx_details_ns": (_i, [_p, _pd, _pd]),
     "lcx_direction_ns": (_i, [_p, _d, _pd]),
     "lcx_trial_ns": (_i, [_p, _d, _d, _i, _pd, _pd]),
+    "lcx_direction_trial_ns": (_i, [_p, _d, _d, _pd, _pd, _pd]),
     "lcx_accept_trial": (_i, [_p]),
     "lcx_moments_syn": (_i, [_p, _pd, _pd]),
     "lcx_update_syn": (_i, [_p, _d, _pd, _pd]),

@@ -596,7 +596,12 @@ class Corex(object):
         sess = self._sess
         lib = sess.lib
         tcv, muj, tang = C.c_double(), C.c_double(), C.c_double()
-        _lib.check(lib.lcx_direction_ns(sess.h, float(self.eps), C.byref(tang)), "lcx_direction_ns")
+        first_rc = None
+        if self.exact_trials:
+            _lib.check(lib.lcx_direction_ns(sess.h, float(self.eps), C.byref(tang)), "lcx_direction_ns")
+        else:  # direction and the eta = 1 trial share one host synchronisation (the trial is discarded if tangent >= 0)
+            first_rc = _lib.check(lib.lcx_direction_trial_ns(sess.h, float(self.eps), 1.0, C.byref(tang), C.byref(tcv),
+                                                             C.byref(muj)), "lcx_direction_trial_ns")
         tangent = tang.value
         rec.update(tangent=tangent, eta=0.0, trials=0, quick_fails=0)
         if tangent >= 0:  # :306-311
@@ -613,8 +618,11 @@ class Corex(object):
                 if self.verbose:
                     print('Warning: step size becoming too small')
                 break
-            rc = _lib.check(lib.lcx_trial_ns(sess.h, float(self.eps), eta, int(self.exact_trials), C.byref(tcv),
-                                             C.byref(muj)), "lcx_trial_ns")
+            if first_rc is not None:
+                rc, first_rc = first_rc, None
+            else:
+                rc = _lib.check(lib.lcx_trial_ns(sess.h, float(self.eps), eta, int(self.exact_trials), C.byref(tcv),
+                                                 C.byref(muj)), "lcx_trial_ns")
             last_rc = rc
             rec["trials"] += 1
             if rc == _lib.QUICK_FAIL:  # TEST 1 (:322-326)

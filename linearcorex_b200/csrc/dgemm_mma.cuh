@@ -232,26 +232,64 @@ __global__ void __launch_bounds__(256, 1) dgemm_mma_kernel(const GemmArgs p) {
     }
 }
 
-// Fixed-order reduction of split-K partials: out[i] = sum_z part[z*stride + i]  (deterministic).
-// Only the valid rows x cols region (leading dimension ld, even) is read or written.
-__global__ void reduce_splits_kernel(const double* __restrict__ part, int splits, long long stride,
-                                     double* __restrict__ out, int rows, int cols, long long ld) {
-    const int c2 = (blockIdx.x * blockDim.x + threadIdx.x) * 2;
-    const int r = blockIdx.y;
-    if (r >= rows) return;
+// Fixed-order reduction of split-K partials: out = sum_z part[z]  (deterministic: the association order depends only on
+// LANES, never on timing).  Only the valid rows x cols region (leading dimension ld, even) is read or written.
+// LANES threads share one output pair: lane q adds splits q, q+LANES, ... in order, then the lanes are combined by a
+// fixed shuffle tree.  LANES = 8 is used for small outputs with many splits (the m x m products), 1 otherwise.
+template <int LANES>
+__global__ void __launch_bounds__(256) reduce_splits_kernel(const double* __restrict__ part, int splits, long long stride,
+                                                            double* __restrict__ out, int rows, int cpairs, int cols,
+                                                            long long ld, double diag_value, double* __restrict__ diag_out) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long p = t / LANES;
+    const int q = (int)(t % LANES);
+    const bool live = p < (long long)rows * cpairs;
+    const int r = live ? (int)(p / cpairs) : 0;
+    const int c2 = live ? (int)(p % cpairs) * 2 : 0;
     const long long o = (long long)r * ld + c2;
-    if (c2 + 1 < cols) {
-        double2 acc = *reinterpret_cast<const double2*>(part + o);
-        for (int z = 1; z < splits; ++z) {
-            const double2 v = *reinterpret_cast<const double2*>(part + (long long)z * stride + o);
-            acc.x += v.x;
-            acc.y += v.y;
+    const bool two = c2 + 1 < cols;
+    double ax = 0.0, ay = 0.0;
+    if (live) {
+        int z = q;
+        for (; z + 3 * LANES < splits; z += 4 * LANES) {  // four independent loads in flight
+            const double* b0 = part + (long long)z * stride + o;
+            const double* b1 = b0 + (long long)LANES * stride;
+            const double* b2 = b1 + (long long)LANES * stride;
+            const double* b3 = b2 + (long long)LANES * stride;
+            if (two) {
+                const double2 v0 = *reinterpret_cast<const double2*>(b0), v1 = *reinterpret_cast<const double2*>(b1);
+                const double2 v2 = *reinterpret_cast<const double2*>(b2), v3 = *reinterpret_cast<const double2*>(b3);
+                ax += v0.x; ay += v0.y; ax += v1.x; ay += v1.y; ax += v2.x; ay += v2.y; ax += v3.x; ay += v3.y;
+            } else {
+                const double v0 = *b0, v1 = *b1, v2 = *b2, v3 = *b3;
+                ax += v0; ax += v1; ax += v2; ax += v3;
+            }
         }
-        *reinterpret_cast<double2*>(out + o) = acc;
-    } else if (c2 < cols) {
-        double a = part[o];
-        for (int z = 1; z < splits; ++z) a += part[(long long)z * stride + o];
-        out[o] = a;
+        for (; z < splits; z += LANES) {
+            const double* b0 = part + (long long)z * stride + o;
+            if (two) {
+                const double2 v = *reinterpret_cast<const double2*>(b0);
+                ax += v.x; ay += v.y;
+            } else {
+                ax += *b0;
+            }
+        }
+    }
+    if (LANES > 1) {
+#pragma unroll
+        for (int w = LANES / 2; w > 0; w >>= 1) {
+            ax += __shfl_down_sync(0xffffffffu, ax, w, LANES);
+            ay += __shfl_down_sync(0xffffffffu, ay, w, LANES);
+        }
+    }
+    if (live && q == 0) {
+        // optional np.fill_diagonal fused into the combine (square outputs): keep the raw diagonal, store diag_value
+        if (diag_out != nullptr) {
+            if (c2 == r) { diag_out[r] = ax; ax = diag_value; }
+            if (two && c2 + 1 == r) { diag_out[r] = ay; ay = diag_value; }
+        }
+        if (two) *reinterpret_cast<double2*>(out + o) = make_double2(ax, ay);
+        else out[o] = ax;
     }
 }
 
@@ -288,7 +326,7 @@ inline GemmPlan plan_gemm(int M, int N, int K, int sms, int max_splits, bool all
     int best_s = 1;
     if (allow_split && max_splits > 1) {
         double best_score = -1.0;
-        const int smax = (int)min((long long)max_splits, (long long)max(1, ktiles / 8));
+        const int smax = (int)min((long long)max_splits, (long long)max(1, ktiles / 4));
         for (int s = 1; s <= smax; ++s) {
             const long long ctas = tiles * s;
             const long long waves = (ctas + sms - 1) / sms;
@@ -349,9 +387,17 @@ inline int launch_gemm(GemmLayout lay, const GemmPlan& pl, GemmArgs a, cudaStrea
 }
 
 inline int launch_reduce_splits(const double* part, int splits, long long stride, double* out, int rows, int cols,
-                                long long ld, cudaStream_t st) {
-    LCX_REQUIRE(rows <= 65535, "split-K reduction supports at most 65535 output rows");
-    reduce_splits_kernel<<<dim3(cdiv((cols + 1) / 2, 128), rows), 128, 0, st>>>(part, splits, stride, out, rows, cols, ld);
+                                long long ld, cudaStream_t st, double* diag_out = nullptr, double diag_value = 0.0) {
+    const int cpairs = (cols + 1) / 2;
+    const long long outputs = (long long)rows * cpairs;
+    if (outputs <= 0) return 0;
+    if (outputs <= 65536 && splits >= 16) {
+        reduce_splits_kernel<8><<<cdiv(outputs * 8, 256), 256, 0, st>>>(part, splits, stride, out, rows, cpairs, cols, ld, diag_value,
+                                                                      diag_out);
+    } else {
+        reduce_splits_kernel<1><<<cdiv(outputs, 256), 256, 0, st>>>(part, splits, stride, out, rows, cpairs, cols, ld, diag_value,
+                                                                  diag_out);
+    }
     LCX_CUDA(cudaGetLastError());
     return 0;
 }

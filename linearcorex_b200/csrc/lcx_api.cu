@@ -73,7 +73,8 @@ struct Layout {
     // split-integer modes (ozaki_i8.cuh)
     int S;                       // digits per operand, 0 = DMMA mode
     long long ld8, ldy8;         // byte leading dimensions of the X~/A and Y slices
-    int oz_splits, oz_chunk;     // split-K of the second contraction
+    int oz_splits, oz_chunk;     // split-K of the second contraction (over samples)
+    int oz1_splits, oz1_chunk;   // split-K of the first contraction (over variables), only when row tiles are scarce
     int ystat_slabs;
 };
 
@@ -181,7 +182,20 @@ static Layout make_layout(long long Nl, int n, int m, int precision) {
         }
         L.oz_chunk = (int)round_up(cdiv(Nl, best), oz::kBK);
         L.oz_splits = cdiv(Nl, L.oz_chunk);
-        const long long part = (long long)L.oz_splits * mn * L.ld;
+        {   // first contraction: same cost model over its (row tile x factor tile) grid
+            const long long tiles1 = (long long)cdiv(Nl, oz::kBM) * cdiv(m, oz::kBN);
+            const int kblocks1 = cdiv(n, oz::kBK);
+            int b1 = 1;
+            double c1best = 1e300;
+            for (int sp = 1; sp <= max(1, min(8, kblocks1 / 16)); ++sp) {
+                const long long waves = (tiles1 * sp + kSMs - 1) / kSMs;
+                const double cost = (double)waves * (ceil((double)kblocks1 / sp) + 16.0) + (sp > 1 ? 4.0 * sp : 0.0);
+                if (cost < c1best - 1e-9) { c1best = cost; b1 = sp; }
+            }
+            L.oz1_chunk = (int)round_up(cdiv(n, b1), oz::kBK);
+            L.oz1_splits = cdiv(n, L.oz1_chunk);
+        }
+        const long long part = max((long long)L.oz_splits * mn * L.ld, L.oz1_splits > 1 ? (long long)L.oz1_splits * Nl * L.ldy : 0LL);
         if (part > L.slot[I_PART][0].cols) {  // grow the split-K partial buffer (it is the last big slot before these)
             put1(I_PART, 1, part, part);
         }
@@ -430,10 +444,18 @@ static int oz_pair_t(lcx_session* s, const double* A, double* svec, cudaEvent_t*
     {
         oz::GemmParams p;
         memset(&p, 0, sizeof(p));
-        p.C = Y; p.ldc = L.ldy; p.col_scale = s->oz_cscale();
-        p.rows = (int)s->Nl; p.cols = m; p.k_total = n; p.k_chunk = (int)round_up(n, oz::kBK);
-        LCX_TRY((oz::launch_oz_gemm<S, true>(s->map_x_k1, s->map_a_k1, p, dim3(cdiv(m, oz::kBN), cdiv(s->Nl, oz::kBM), 1), s->stream)));
+        const bool split1 = L.oz1_splits > 1;
+        p.C = split1 ? s->ptr(I_PART) : Y;
+        p.ldc = L.ldy; p.c_split_stride = split1 ? s->Nl * L.ldy : 0;
+        p.col_scale = s->oz_cscale();
+        p.rows = (int)s->Nl; p.cols = m; p.k_total = n; p.k_chunk = L.oz1_chunk;
+        LCX_TRY((oz::launch_oz_gemm<S, true>(s->map_x_k1, s->map_a_k1, p, dim3(cdiv(m, oz::kBN), cdiv(s->Nl, oz::kBM), L.oz1_splits),
+                                             s->stream)));
         LAUNCHED(s);
+        if (split1) {
+            LCX_TRY(launch_reduce_splits(s->ptr(I_PART), L.oz1_splits, s->Nl * L.ldy, Y, (int)s->Nl, m, L.ldy, s->stream));
+            LAUNCHED(s);
+        }
     }
     if (ev) LCX_CUDA(cudaEventRecord(ev[1], s->stream));
     if (ev) LCX_CUDA(cudaEventRecord(ev[3], s->stream));
@@ -750,6 +772,30 @@ static int run_gemm(lcx_session* s, GemmLayout lay, const GemmPlan& pl, GemmArgs
     return 0;
 }
 
+// m x m product over the variables (ry, H): split-K GEMM whose fixed-order combine also performs np.fill_diagonal
+// (raw diagonal -> diag_out if given, diag_value stored) -- one launch less than combine + diag kernel.
+static int run_square_gemm(lcx_session* s, GemmArgs a, double diag_value, double* diag_out) {
+    const Layout& L = s->L;
+    const int m = s->m;
+    const long long out_count = (long long)m * L.ldm;
+    if (L.plan_mm.splits > 1) {
+        double* final_c = a.C;
+        a.C = s->ptr(I_PART);
+        a.c_split_stride = out_count;
+        LCX_TRY(launch_gemm(kLayoutKK, L.plan_mm, a, s->stream));
+        LAUNCHED(s);
+        LCX_TRY(launch_reduce_splits(s->ptr(I_PART), L.plan_mm.splits, out_count, final_c, m, m, L.ldm, s->stream,
+                                     diag_out ? diag_out : s->ptr(I_F), diag_value));
+        LAUNCHED(s);
+    } else {
+        double* final_c = a.C;
+        LCX_TRY(run_gemm(s, kLayoutKK, L.plan_mm, a, s->ptr(I_PART), out_count));
+        diag_fix_kernel<<<cdiv(m, 128), 128, 0, s->stream>>>(final_c, L.ldm, m, diag_value, diag_out);
+        LAUNCHED(s);
+    }
+    return 0;
+}
+
 // Y = X~ A^T (+ colsq into D's tail), D = X~^T Y summed over splits, then the rank all-reduce.
 static int xpair(lcx_session* s, const double* A, bool want_colsq) {
     const Layout& L = s->L;
@@ -834,9 +880,7 @@ static int moments_tail(lcx_session* s, int set, double c1, double e2, int uj_mo
         a.A = W; a.B = rho; a.C = ry;
         a.M = m; a.N = m; a.K = n;
         a.lda = L.ld; a.ldb = L.ld; a.ldc = L.ldm;
-        LCX_TRY(run_gemm(s, kLayoutKK, L.plan_mm, a, s->ptr(I_PART), (long long)m * L.ldm));
-        diag_fix_kernel<<<cdiv(m, 128), 128, 0, s->stream>>>(ry, L.ldm, m, 1.0, s->ptr(I_UJDIAG));
-        LAUNCHED(s);
+        LCX_TRY(run_square_gemm(s, a, 1.0, s->ptr(I_UJDIAG)));
     }
     {   // Qij = ry rinv  (:266)
         GemmArgs a;
@@ -997,8 +1041,7 @@ extern "C" int lcx_moments_ns(lcx_session* s, double eps, int check_uj, double* 
     return (check_uj && s->mailbox[1] >= 1.0) ? LCX_QUICK_FAIL : LCX_OK;
 }
 
-extern "C" int lcx_direction_ns(lcx_session* s, double eps, double* tangent) {
-    S_REQUIRE_BOUND(s);
+static int enqueue_direction(lcx_session* s, double eps) {
     const Layout& L = s->L;
     const int m = s->m, n = s->n;
     const double c1 = (1.0 - eps * eps) / (double)s->Nt, e2 = eps * eps;
@@ -1018,9 +1061,7 @@ extern "C" int lcx_direction_ns(lcx_session* s, double eps, double* tangent) {
         a.A = T; a.B = rinv; a.C = H;
         a.M = m; a.N = m; a.K = n;
         a.lda = L.ld; a.ldb = L.ld; a.ldc = L.ldm;
-        LCX_TRY(run_gemm(s, kLayoutKK, L.plan_mm, a, s->ptr(I_PART), (long long)m * L.ldm));
-        diag_fix_kernel<<<cdiv(m, 128), 128, 0, s->stream>>>(H, L.ldm, m, 0.0, nullptr);
-        LAUNCHED(s);
+        LCX_TRY(run_square_gemm(s, a, 0.0, nullptr));
     }
     {   // grad = G0 + H W (:300), in place over G0
         GemmArgs a;
@@ -1040,13 +1081,18 @@ extern "C" int lcx_direction_ns(lcx_session* s, double eps, double* tangent) {
     sum_partials_kernel<<<1, 256, 0, s->stream>>>(s->ptr(I_SPART), (int)(g2.x * g2.y), s->ptr(LCX_A_SCALARS) + 2);
     LAUNCHED(s);
     LCX_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int lcx_direction_ns(lcx_session* s, double eps, double* tangent) {
+    S_REQUIRE_BOUND(s);
+    LCX_TRY(enqueue_direction(s, eps));
     LCX_TRY(read_mailbox(s));
     if (tangent) *tangent = s->mailbox[2];
     return 0;
 }
 
-extern "C" int lcx_trial_ns(lcx_session* s, double eps, double eta, int exact, double* tc, double* max_uj) {
-    S_REQUIRE_BOUND(s);
+static int enqueue_trial(lcx_session* s, double eps, double eta, int exact) {
     const Layout& L = s->L;
     const int m = s->m, n = s->n;
     const double c1 = (1.0 - eps * eps) / (double)s->Nt, e2 = eps * eps;
@@ -1063,7 +1109,27 @@ extern "C" int lcx_trial_ns(lcx_session* s, double eps, double eta, int exact, d
         LAUNCHED(s);
         LCX_TRY(moments_tail(s, 1, c1, e2, 1));
     }
+    return 0;
+}
+
+extern "C" int lcx_trial_ns(lcx_session* s, double eps, double eta, int exact, double* tc, double* max_uj) {
+    S_REQUIRE_BOUND(s);
+    LCX_TRY(enqueue_trial(s, eps, eta, exact));
     LCX_TRY(read_mailbox(s));
+    if (tc) *tc = s->mailbox[0];
+    if (max_uj) *max_uj = s->mailbox[1];
+    return (s->mailbox[1] >= 1.0) ? LCX_QUICK_FAIL : LCX_OK;
+}
+
+// Direction (:292-305) and the first backtracking trial at `eta` (:320-321) enqueued back to back, ONE host
+// synchronisation for update_tangent, TC and max uj.  The trial is speculative: if update_tangent >= 0 the caller
+// discards it (the reference returns before trying, :306-311).  Linear trials only (an exact trial costs a pass pair).
+extern "C" int lcx_direction_trial_ns(lcx_session* s, double eps, double eta, double* tangent, double* tc, double* max_uj) {
+    S_REQUIRE_BOUND(s);
+    LCX_TRY(enqueue_direction(s, eps));
+    LCX_TRY(enqueue_trial(s, eps, eta, 0));
+    LCX_TRY(read_mailbox(s));
+    if (tangent) *tangent = s->mailbox[2];
     if (tc) *tc = s->mailbox[0];
     if (max_uj) *max_uj = s->mailbox[1];
     return (s->mailbox[1] >= 1.0) ? LCX_QUICK_FAIL : LCX_OK;
@@ -1204,9 +1270,7 @@ extern "C" int lcx_update_syn(lcx_session* s, double eta, double* tc, double* ad
         a.A = Rm; a.B = s->ptr(LCX_A_XZ); a.C = H;
         a.M = m; a.N = m; a.K = n;
         a.lda = L.ld; a.ldb = L.ld; a.ldc = L.ldm;
-        LCX_TRY(run_gemm(s, kLayoutKK, L.plan_mm, a, s->ptr(I_PART), (long long)m * L.ldm));
-        diag_fix_kernel<<<cdiv(m, 128), 128, 0, s->stream>>>(H, L.ldm, m, 0.0, nullptr);
-        LAUNCHED(s);
+        LCX_TRY(run_square_gemm(s, a, 0.0, nullptr));
     }
     {   // S = H W (:381)
         GemmArgs a;
