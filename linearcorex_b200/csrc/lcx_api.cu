@@ -236,7 +236,8 @@ struct lcx_session {
     far::Peers peers;
     unsigned long long ar_calls;
     // split-integer modes: TMA descriptors over the digit slices
-    CUtensorMap map_x_k1, map_a_k1, map_y_k2, map_x_k2;
+    CUtensorMap map_x_k1, map_a_k1, map_a_k1_tail, map_y_k2, map_x_k2;
+    int oz_bn_tail;   // width of the last factor tile of the first contraction (multiple of 16)
     int8_t* xs() const { return (int8_t*)(ws + L.slot[I_XS][0].off); }
     int8_t* as() const { return (int8_t*)(ws + L.slot[I_AS][0].off); }
     int8_t* ys() const { return (int8_t*)(ws + L.slot[I_YS][0].off); }
@@ -422,6 +423,9 @@ static int oz_prepare(lcx_session* s, bool streamed) {
     // (MN-major: inner = variables, rows = samples); A slices K-major; Y slices MN-major (inner = factors).
     LCX_TRY(oz::make_slice_map(&s->map_x_k1, s->xs(), s->n, s->Nl, L.S, L.ld8, s->Nl * L.ld8, oz::kBK, oz::kBM, false));
     LCX_TRY(oz::make_slice_map(&s->map_a_k1, s->as(), s->n, s->m, L.S, L.ld8, (long long)s->m * L.ld8, oz::kBK, oz::kBN, false));
+    s->oz_bn_tail = (int)round_up(s->m - (cdiv(s->m, oz::kBN) - 1) * oz::kBN, 16);
+    LCX_TRY(oz::make_slice_map(&s->map_a_k1_tail, s->as(), s->n, s->m, L.S, L.ld8, (long long)s->m * L.ld8, oz::kBK, s->oz_bn_tail,
+                               false));
     LCX_TRY(oz::make_slice_map(&s->map_y_k2, s->ys(), L.ldy8, s->Nl, L.S, L.ldy8, s->Nl * L.ldy8, oz::kBM, oz::kBK, true));
     LCX_TRY(oz::make_slice_map(&s->map_x_k2, s->xs(), s->n, s->Nl, L.S, L.ld8, s->Nl * L.ld8, oz::kBN, oz::kBK, false));
     return 0;
@@ -449,8 +453,9 @@ static int oz_pair_t(lcx_session* s, const double* A, double* svec, cudaEvent_t*
         p.ldc = L.ldy; p.c_split_stride = split1 ? s->Nl * L.ldy : 0;
         p.col_scale = s->oz_cscale();
         p.rows = (int)s->Nl; p.cols = m; p.k_total = n; p.k_chunk = L.oz1_chunk;
-        LCX_TRY((oz::launch_oz_gemm<S, true>(s->map_x_k1, s->map_a_k1, p, dim3(cdiv(m, oz::kBN), cdiv(s->Nl, oz::kBM), L.oz1_splits),
-                                             s->stream)));
+        p.bn_tail = s->oz_bn_tail;
+        LCX_TRY((oz::launch_oz_gemm<S, true>(s->map_x_k1, s->map_a_k1, s->map_a_k1_tail, p,
+                                             dim3(cdiv(m, oz::kBN), cdiv(s->Nl, oz::kBM), L.oz1_splits), s->stream)));
         LAUNCHED(s);
         if (split1) {
             LCX_TRY(launch_reduce_splits(s->ptr(I_PART), L.oz1_splits, s->Nl * L.ldy, Y, (int)s->Nl, m, L.ldy, s->stream));
@@ -482,7 +487,8 @@ static int oz_pair_t(lcx_session* s, const double* A, double* svec, cudaEvent_t*
         p.ldc = L.ld; p.c_split_stride = split ? (long long)m * L.ld : 0;
         p.row_scale = s->oz_dscale();
         p.rows = m; p.cols = n; p.k_total = (int)s->Nl; p.k_chunk = L.oz_chunk;
-        LCX_TRY((oz::launch_oz_gemm<S, false>(s->map_y_k2, s->map_x_k2, p, dim3(cdiv(n, oz::kBN), cdiv(m, oz::kBM), L.oz_splits), s->stream)));
+        LCX_TRY((oz::launch_oz_gemm<S, false>(s->map_y_k2, s->map_x_k2, s->map_x_k2, p,
+                                              dim3(cdiv(n, oz::kBN), cdiv(m, oz::kBM), L.oz_splits), s->stream)));
         LAUNCHED(s);
         LCX_TRY(combine_and_allreduce(s, split ? s->ptr(I_PART) : D, split ? L.oz_splits : 1, (long long)m * L.ld, m, n, L.ld, D, svec,
                                       want_tail ? m : 0));

@@ -120,6 +120,8 @@ struct GemmParams {
     int rows, cols;              // valid output extent
     int k_total;                 // contraction length
     int k_chunk;                 // contraction range per blockIdx.z (multiple of kBK)
+    int bn_tail;                 // K-major only: width (multiple of 16, <= 64) of the LAST N tile, loaded through mapBt;
+                                 // 0 or 64 = full width.  m = 100 factors -> tiles of 64 + 48 instead of 64 + 64
 };
 
 // KMAJOR = true : A tile = [128 rows][64 B of K]  (SW64), B tile = [64 rows][64 B of K]  (SW64); tensor maps are
@@ -128,9 +130,10 @@ struct GemmParams {
 //                 (M or N, K rows, slice); TMA coordinates (m0 or n0, k0, s).
 template <int S, bool KMAJOR>
 __global__ void __launch_bounds__(kThreads, 1)
-oz_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const GemmParams p) {
+oz_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+               const __grid_constant__ CUtensorMap mapBt, const GemmParams p) {
     constexpr int A_BYTES = kBM * kBK;          // 8 KB per slice either way
-    constexpr int B_BYTES = kBN * kBK;          // 4 KB per slice
+    constexpr int B_BYTES = kBN * kBK;          // 4 KB per slice (full-width tile)
     constexpr int STAGE_BYTES = S * (A_BYTES + B_BYTES);
     constexpr uint32_t TMEM_COLS = (S * kBN <= 128) ? 128 : (S * kBN <= 256 ? 256 : 512);
     static_assert(S * kBN <= 512, "accumulators exceed TMEM");
@@ -147,10 +150,16 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     const int kbeg = blockIdx.z * p.k_chunk;
     const int kend = min(p.k_total, kbeg + p.k_chunk);
     const int num_kb = (kend > kbeg) ? (kend - kbeg + kBK - 1) / kBK : 0;
+    // width of this CTA's N tile: the last tile of the K-major contraction may be narrower (fewer padded factor columns
+    // = proportionally fewer tensor cycles and operand bytes); digit planes of B are then packed at bn * 64 bytes
+    const bool tail = KMAJOR && p.bn_tail > 0 && p.bn_tail < kBN && n_tile == (int)gridDim.x - 1;
+    const int bn = tail ? p.bn_tail : kBN;
+    const int b_bytes = bn * kBK;
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&mapBt) : "memory");
         for (int i = 0; i < kStages; ++i) {
             mbar_init(&full_bar[i], 1);
             mbar_init(&empty_bar[i], 1);
@@ -173,13 +182,13 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 mbar_wait(&empty_bar[st], ph ^ 1);
                 uint8_t* sa = smem + st * STAGE_BYTES;
                 uint8_t* sb = sa + S * A_BYTES;
-                mbar_expect_tx(&full_bar[st], STAGE_BYTES);
+                mbar_expect_tx(&full_bar[st], S * (A_BYTES + b_bytes));
                 const int k0 = kbeg + kb * kBK;
 #pragma unroll
                 for (int s = 0; s < S; ++s) {
                     if (KMAJOR) {
                         tma_load_3d(sa + s * A_BYTES, &mapA, &full_bar[st], k0, m_tile * kBM, s);
-                        tma_load_3d(sb + s * B_BYTES, &mapB, &full_bar[st], k0, n_tile * kBN, s);
+                        tma_load_3d(sb + s * b_bytes, tail ? &mapBt : &mapB, &full_bar[st], k0, n_tile * kBN, s);
                     } else {
                         tma_load_3d(sa + s * A_BYTES, &mapA, &full_bar[st], m_tile * kBM, k0, s);
                         tma_load_3d(sb + s * B_BYTES, &mapB, &full_bar[st], n_tile * kBN, k0, s);
@@ -205,16 +214,16 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 for (int kk = 0; kk < kBK / 32; ++kk) {
 #pragma unroll
                     for (int ka = 0; ka < S; ++ka) {
-#pragma unroll
-                        for (int q0 = 0; q0 < S - ka; q0 += 4) {
-                            const int cnt = (S - ka - q0) < 4 ? (S - ka - q0) : 4;  // B digit planes in this instruction
-                            const uint32_t idesc = make_idesc_i8(kBM, kBN * cnt, KMAJOR ? 0 : 1, KMAJOR ? 0 : 1);
+                        const int cmax = 256 / bn;  // digit planes of B per instruction (N <= 256)
+                        for (int q0 = 0; q0 < S - ka; q0 += cmax) {
+                            const int cnt = (S - ka - q0) < cmax ? (S - ka - q0) : cmax;
+                            const uint32_t idesc = make_idesc_i8(kBM, bn * cnt, KMAJOR ? 0 : 1, KMAJOR ? 0 : 1);
                             uint64_t da, db;
                             if (KMAJOR) {
                                 // rows at 64 B pitch, 8-row swizzle atoms of 512 B (SBO); a K step is +32 B inside the
                                 // span; the next B plane starts 8 atoms further, i.e. N simply continues.
                                 da = make_smem_desc(sa + ka * A_BYTES + kk * 32, 16, 512, 4);
-                                db = make_smem_desc(sb + q0 * B_BYTES + kk * 32, 16, 512, 4);
+                                db = make_smem_desc(sb + q0 * b_bytes + kk * 32, 16, 512, 4);
                             } else {
                                 // A: K rows of 128 B (SW128, atoms of 8 rows = 1 KB); a K step is 32 rows = 4 KB
                                 // B: K rows of 64 B  (SW64,  atoms of 8 rows = 512 B); a K step is 32 rows = 2 KB;
@@ -223,7 +232,7 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                                 db = make_smem_desc(sb + q0 * B_BYTES + kk * 2048, 4096, 512, 4);
                             }
                             const uint32_t acc = (kb > 0 || kk > 0 || ka > 0) ? 1u : 0u;
-                            umma_i8(tmem_base + (uint32_t)(ka + q0) * kBN, da, db, idesc, acc);
+                            umma_i8(tmem_base + (uint32_t)((ka + q0) * bn), da, db, idesc, acc);
                         }
                     }
                 }
@@ -242,17 +251,17 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         const double rs = (p.row_scale != nullptr && row < p.rows) ? p.row_scale[row] : 1.0;
         const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
 #pragma unroll 1
-        for (int c0 = 0; c0 < kBN; c0 += 16) {
+        for (int c0 = 0; c0 < bn; c0 += 16) {
             double acc[16];
             if (num_kb > 0) {
                 uint32_t r[16];
-                tmem_ld16(lane_addr + (uint32_t)((S - 1) * kBN + c0), r);
+                tmem_ld16(lane_addr + (uint32_t)((S - 1) * bn + c0), r);
                 tmem_ld_wait();
 #pragma unroll
                 for (int j = 0; j < 16; ++j) acc[j] = (double)(int)r[j];
 #pragma unroll
                 for (int g = S - 2; g >= 0; --g) {
-                    tmem_ld16(lane_addr + (uint32_t)(g * kBN + c0), r);
+                    tmem_ld16(lane_addr + (uint32_t)(g * bn + c0), r);
                     tmem_ld_wait();
 #pragma unroll
                     for (int j = 0; j < 16; ++j) acc[j] = acc[j] * 0.0078125 + (double)(int)r[j];  // 2^-7 per group
@@ -482,7 +491,8 @@ inline int make_slice_map(CUtensorMap* map, const void* base, long long inner, l
 }
 
 template <int S, bool KMAJOR>
-inline int launch_oz_gemm(const CUtensorMap& mapA, const CUtensorMap& mapB, const GemmParams& p, dim3 grid, cudaStream_t st) {
+inline int launch_oz_gemm(const CUtensorMap& mapA, const CUtensorMap& mapB, const CUtensorMap& mapBt, const GemmParams& p,
+                          dim3 grid, cudaStream_t st) {
     constexpr int SMEM = kStages * S * (kBM * kBK + kBN * kBK) + 1024;
     static bool configured = false;
     auto kern = oz_gemm_kernel<S, KMAJOR>;
@@ -490,7 +500,7 @@ inline int launch_oz_gemm(const CUtensorMap& mapA, const CUtensorMap& mapB, cons
         LCX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
         configured = true;
     }
-    kern<<<grid, kThreads, SMEM, st>>>(mapA, mapB, p);
+    kern<<<grid, kThreads, SMEM, st>>>(mapA, mapB, mapBt, p);
     LCX_CUDA(cudaGetLastError());
     return 0;
 }
