@@ -128,6 +128,40 @@ struct GemmParams {
 //                 (K, rows, slice); TMA coordinates (k0, row0, s).
 // KMAJOR = false: A tile = [64 K rows][128 B of M] (SW128), B tile = [64 K rows][64 B of N] (SW64); tensor maps are
 //                 (M or N, K rows, slice); TMA coordinates (m0 or n0, k0, s).
+// All MMAs of one 64-deep K block for a tile of compile-time width BN (multiple of 16, <= 64).
+template <int S, bool KMAJOR, int BN>
+__device__ __forceinline__ void issue_kblock(uint32_t sa, uint32_t sb, uint32_t tmem_base, bool first_block) {
+    constexpr int A_BYTES = kBM * kBK;
+    constexpr int B_BYTES = BN * kBK;        // digit planes of B are packed at the tile's own width
+    constexpr int CMAX = 256 / BN;           // digit planes of B per instruction (N <= 256)
+#pragma unroll
+    for (int kk = 0; kk < kBK / 32; ++kk) {
+#pragma unroll
+        for (int ka = 0; ka < S; ++ka) {
+#pragma unroll
+            for (int q0 = 0; q0 < S - ka; q0 += CMAX) {
+                const int cnt = (S - ka - q0) < CMAX ? (S - ka - q0) : CMAX;
+                const uint32_t idesc = make_idesc_i8(kBM, BN * cnt, KMAJOR ? 0 : 1, KMAJOR ? 0 : 1);
+                uint64_t da, db;
+                if (KMAJOR) {
+                    // rows at 64 B pitch, 8-row swizzle atoms of 512 B (SBO); a K step is +32 B inside the span; the next
+                    // B plane starts BN/8 atoms further, i.e. N simply continues.
+                    da = make_smem_desc(sa + ka * A_BYTES + kk * 32, 16, 512, 4);
+                    db = make_smem_desc(sb + q0 * B_BYTES + kk * 32, 16, 512, 4);
+                } else {
+                    // A: K rows of 128 B (SW128, atoms of 8 rows = 1 KB); a K step is 32 rows = 4 KB
+                    // B: K rows of 64 B  (SW64,  atoms of 8 rows = 512 B); a K step is 32 rows = 2 KB;
+                    //    the next 64 columns of N are the next digit plane, 4 KB further (LBO).
+                    da = make_smem_desc(sa + ka * A_BYTES + kk * 4096, 8192, 1024, 2);
+                    db = make_smem_desc(sb + q0 * B_BYTES + kk * 2048, 4096, 512, 4);
+                }
+                const uint32_t acc = (!first_block || kk > 0 || ka > 0) ? 1u : 0u;
+                umma_i8(tmem_base + (uint32_t)((ka + q0) * BN), da, db, idesc, acc);
+            }
+        }
+    }
+}
+
 template <int S, bool KMAJOR>
 __global__ void __launch_bounds__(kThreads, 1)
 oz_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
@@ -201,8 +235,9 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         if (lane == 0) {
             // Digit ka of A meets digits 0..S-1-ka of B, landing in groups ka..S-1 = CONSECUTIVE TMEM columns, and
             // the B digit planes are consecutive in shared memory, so those S-ka products are issued as one wide
-            // MMA (N = 64 (S-ka), at most 256 per instruction): A is re-read from shared memory 8 times per K step
+            // MMA (N = bn (S-ka), at most 256 per instruction): A is re-read from shared memory 8 times per K step
             // instead of 21 -- the narrow 128x64 form is shared-memory-bandwidth bound (6 KB of operands per 32 cycles).
+            // The issue sequence is fully unrolled per tile width (one elected thread issues everything).
             for (int kb = 0; kb < num_kb; ++kb) {
                 const int st = kb % kStages;
                 const uint32_t ph = (kb / kStages) & 1;
@@ -210,32 +245,10 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 tc_fence_after();
                 const uint32_t sa = smem_u32(smem + st * STAGE_BYTES);
                 const uint32_t sb = sa + S * A_BYTES;
-#pragma unroll
-                for (int kk = 0; kk < kBK / 32; ++kk) {
-#pragma unroll
-                    for (int ka = 0; ka < S; ++ka) {
-                        const int cmax = 256 / bn;  // digit planes of B per instruction (N <= 256)
-                        for (int q0 = 0; q0 < S - ka; q0 += cmax) {
-                            const int cnt = (S - ka - q0) < cmax ? (S - ka - q0) : cmax;
-                            const uint32_t idesc = make_idesc_i8(kBM, bn * cnt, KMAJOR ? 0 : 1, KMAJOR ? 0 : 1);
-                            uint64_t da, db;
-                            if (KMAJOR) {
-                                // rows at 64 B pitch, 8-row swizzle atoms of 512 B (SBO); a K step is +32 B inside the
-                                // span; the next B plane starts 8 atoms further, i.e. N simply continues.
-                                da = make_smem_desc(sa + ka * A_BYTES + kk * 32, 16, 512, 4);
-                                db = make_smem_desc(sb + q0 * b_bytes + kk * 32, 16, 512, 4);
-                            } else {
-                                // A: K rows of 128 B (SW128, atoms of 8 rows = 1 KB); a K step is 32 rows = 4 KB
-                                // B: K rows of 64 B  (SW64,  atoms of 8 rows = 512 B); a K step is 32 rows = 2 KB;
-                                //    the next 64 columns of N are the next digit plane, 4 KB further (LBO).
-                                da = make_smem_desc(sa + ka * A_BYTES + kk * 4096, 8192, 1024, 2);
-                                db = make_smem_desc(sb + q0 * B_BYTES + kk * 2048, 4096, 512, 4);
-                            }
-                            const uint32_t acc = (kb > 0 || kk > 0 || ka > 0) ? 1u : 0u;
-                            umma_i8(tmem_base + (uint32_t)((ka + q0) * bn), da, db, idesc, acc);
-                        }
-                    }
-                }
+                if (bn == 64) issue_kblock<S, KMAJOR, 64>(sa, sb, tmem_base, kb == 0);
+                else if (bn == 48) issue_kblock<S, KMAJOR, 48>(sa, sb, tmem_base, kb == 0);
+                else if (bn == 32) issue_kblock<S, KMAJOR, 32>(sa, sb, tmem_base, kb == 0);
+                else issue_kblock<S, KMAJOR, 16>(sa, sb, tmem_base, kb == 0);
                 umma_commit(&empty_bar[st]);  // frees the stage once these MMAs have read it
             }
             umma_commit(&tmem_full_bar);
