@@ -431,6 +431,11 @@ static int oz_prepare(lcx_session* s, bool streamed) {
     return 0;
 }
 
+static int oz_cluster() {  // LCX_OZ_CLUSTER=1|2|4 overrides the cluster size of the split-integer contractions
+    const char* env = getenv("LCX_OZ_CLUSTER");
+    return env ? atoi(env) : 4;
+}
+
 template <int S>
 static int oz_pair_t(lcx_session* s, const double* A, double* svec, cudaEvent_t* ev, bool first_only, bool want_tail) {
     const Layout& L = s->L;
@@ -455,7 +460,7 @@ static int oz_pair_t(lcx_session* s, const double* A, double* svec, cudaEvent_t*
         p.rows = (int)s->Nl; p.cols = m; p.k_total = n; p.k_chunk = L.oz1_chunk;
         p.bn_tail = s->oz_bn_tail;
         LCX_TRY((oz::launch_oz_gemm<S, true>(s->map_x_k1, s->map_a_k1, s->map_a_k1_tail, p,
-                                             dim3(cdiv(m, oz::kBN), cdiv(s->Nl, oz::kBM), L.oz1_splits), s->stream)));
+                                             dim3(cdiv(m, oz::kBN), cdiv(s->Nl, oz::kBM), L.oz1_splits), s->stream, oz_cluster())));
         LAUNCHED(s);
         if (split1) {
             LCX_TRY(launch_reduce_splits(s->ptr(I_PART), L.oz1_splits, s->Nl * L.ldy, Y, (int)s->Nl, m, L.ldy, s->stream));
@@ -488,7 +493,7 @@ static int oz_pair_t(lcx_session* s, const double* A, double* svec, cudaEvent_t*
         p.row_scale = s->oz_dscale();
         p.rows = m; p.cols = n; p.k_total = (int)s->Nl; p.k_chunk = L.oz_chunk;
         LCX_TRY((oz::launch_oz_gemm<S, false>(s->map_y_k2, s->map_x_k2, s->map_x_k2, p,
-                                              dim3(cdiv(n, oz::kBN), cdiv(m, oz::kBM), L.oz_splits), s->stream)));
+                                              dim3(cdiv(n, oz::kBN), cdiv(m, oz::kBM), L.oz_splits), s->stream, oz_cluster())));
         LAUNCHED(s);
         LCX_TRY(combine_and_allreduce(s, split ? s->ptr(I_PART) : D, split ? L.oz_splits : 1, (long long)m * L.ld, m, n, L.ld, D, svec,
                                       want_tail ? m : 0));

@@ -61,6 +61,31 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, u
         "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
         : "memory");
 }
+// Multicast variant: the box lands at the same shared-memory offset in every CTA of `mask` and completes the same-offset
+// mbarrier in each of them.
+__device__ __forceinline__ void tma_load_3d_mc(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
+                                               uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%4, %5, %6}], "
+        "[%2], %3;" ::"r"(smem_u32(dst)),
+        "l"(map), "r"(smem_u32(bar)), "h"(mask), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                     smem_u32(bar)),
+                 "h"(mask)
+                 : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t cols) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
@@ -120,6 +145,7 @@ struct GemmParams {
     int rows, cols;              // valid output extent
     int k_total;                 // contraction length
     int k_chunk;                 // contraction range per blockIdx.z (multiple of kBK)
+    int n_tiles;                 // number of real N tiles (gridDim.x may be padded up to a multiple of the cluster size)
     int bn_tail;                 // K-major only: width (multiple of 16, <= 64) of the LAST N tile, loaded through mapBt;
                                  // 0 or 64 = full width.  m = 100 factors -> tiles of 64 + 48 instead of 64 + 64
 };
@@ -162,7 +188,12 @@ __device__ __forceinline__ void issue_kblock(uint32_t sa, uint32_t sb, uint32_t 
     }
 }
 
-template <int S, bool KMAJOR>
+// CL = thread-block cluster size along the N tiles (1, 2 or 4).  The CL CTAs of a cluster share the M-side operand
+// (X~ planes in the first contraction, Y planes in the second): each CTA fetches S/CL of its digit planes and TMA
+// multicasts them into every CTA of the cluster, which divides the L2 -> SM traffic of that operand by CL (the kernel
+// ran at the L2 throughput cap without it: 18 GB per launch at config 3).  A stage is released to the producers only
+// when every CTA of the cluster has finished reading it (multicast tcgen05.commit on all empty barriers).
+template <int S, bool KMAJOR, int CL>
 __global__ void __launch_bounds__(kThreads, 1)
 oz_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                const __grid_constant__ CUtensorMap mapBt, const GemmParams p) {
@@ -186,7 +217,9 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     const int num_kb = (kend > kbeg) ? (kend - kbeg + kBK - 1) / kBK : 0;
     // width of this CTA's N tile: the last tile of the K-major contraction may be narrower (fewer padded factor columns
     // = proportionally fewer tensor cycles and operand bytes); digit planes of B are then packed at bn * 64 bytes
-    const bool tail = KMAJOR && p.bn_tail > 0 && p.bn_tail < kBN && n_tile == (int)gridDim.x - 1;
+    const bool tail = KMAJOR && p.bn_tail > 0 && p.bn_tail < kBN && n_tile == p.n_tiles - 1;
+    const uint32_t crank = (CL > 1) ? cluster_ctarank() : 0u;
+    constexpr uint16_t kMask = (uint16_t)((1u << CL) - 1u);
     const int bn = tail ? p.bn_tail : kBN;
     const int b_bytes = bn * kBK;
 
@@ -196,7 +229,7 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         asm volatile("prefetch.tensormap [%0];" ::"l"(&mapBt) : "memory");
         for (int i = 0; i < kStages; ++i) {
             mbar_init(&full_bar[i], 1);
-            mbar_init(&empty_bar[i], 1);
+            mbar_init(&empty_bar[i], CL);  // one arrival per CTA of the cluster (multicast commit)
         }
         mbar_init(&tmem_full_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -204,6 +237,7 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     if (warp == 1) tmem_alloc(&tmem_base_smem, TMEM_COLS);
     tc_fence_before();
     __syncthreads();
+    if (CL > 1) cluster_sync_all();  // peers may multicast into / arrive on this CTA's barriers only once they exist
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_smem;
 
@@ -220,13 +254,16 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 const int k0 = kbeg + kb * kBK;
 #pragma unroll
                 for (int s = 0; s < S; ++s) {
-                    if (KMAJOR) {
-                        tma_load_3d(sa + s * A_BYTES, &mapA, &full_bar[st], k0, m_tile * kBM, s);
-                        tma_load_3d(sb + s * b_bytes, tail ? &mapBt : &mapB, &full_bar[st], k0, n_tile * kBN, s);
-                    } else {
-                        tma_load_3d(sa + s * A_BYTES, &mapA, &full_bar[st], m_tile * kBM, k0, s);
-                        tma_load_3d(sb + s * B_BYTES, &mapB, &full_bar[st], n_tile * kBN, k0, s);
+                    // shared operand: plane s is fetched by cluster rank s % CL and multicast to all CL CTAs
+                    if (CL == 1) {
+                        if (KMAJOR) tma_load_3d(sa + s * A_BYTES, &mapA, &full_bar[st], k0, m_tile * kBM, s);
+                        else tma_load_3d(sa + s * A_BYTES, &mapA, &full_bar[st], m_tile * kBM, k0, s);
+                    } else if ((uint32_t)(s % CL) == crank) {
+                        if (KMAJOR) tma_load_3d_mc(sa + s * A_BYTES, &mapA, &full_bar[st], k0, m_tile * kBM, s, kMask);
+                        else tma_load_3d_mc(sa + s * A_BYTES, &mapA, &full_bar[st], m_tile * kBM, k0, s, kMask);
                     }
+                    if (KMAJOR) tma_load_3d(sb + s * b_bytes, tail ? &mapBt : &mapB, &full_bar[st], k0, n_tile * kBN, s);
+                    else tma_load_3d(sb + s * B_BYTES, &mapB, &full_bar[st], n_tile * kBN, k0, s);
                 }
             }
         }
@@ -249,7 +286,9 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 else if (bn == 48) issue_kblock<S, KMAJOR, 48>(sa, sb, tmem_base, kb == 0);
                 else if (bn == 32) issue_kblock<S, KMAJOR, 32>(sa, sb, tmem_base, kb == 0);
                 else issue_kblock<S, KMAJOR, 16>(sa, sb, tmem_base, kb == 0);
-                umma_commit(&empty_bar[st]);  // frees the stage once these MMAs have read it
+                // frees the stage (in every CTA of the cluster) once these MMAs have read it
+                if (CL == 1) umma_commit(&empty_bar[st]);
+                else umma_commit_mc(&empty_bar[st], kMask);
             }
             umma_commit(&tmem_full_bar);
         }
@@ -305,6 +344,7 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         tc_fence_before();
     }
     __syncthreads();
+    if (CL > 1) cluster_sync_all();  // nobody leaves while a peer can still multicast into it or arrive on its barriers
     if (warp == 1) {
         tc_fence_after();
         tmem_dealloc(tmem_base, TMEM_COLS);
@@ -503,19 +543,42 @@ inline int make_slice_map(CUtensorMap* map, const void* base, long long inner, l
     return 0;
 }
 
-template <int S, bool KMAJOR>
-inline int launch_oz_gemm(const CUtensorMap& mapA, const CUtensorMap& mapB, const CUtensorMap& mapBt, const GemmParams& p,
-                          dim3 grid, cudaStream_t st) {
+template <int S, bool KMAJOR, int CL>
+inline int launch_oz_gemm_cl(const CUtensorMap& mapA, const CUtensorMap& mapB, const CUtensorMap& mapBt, GemmParams p, dim3 grid,
+                             cudaStream_t st) {
     constexpr int SMEM = kStages * S * (kBM * kBK + kBN * kBK) + 1024;
     static bool configured = false;
-    auto kern = oz_gemm_kernel<S, KMAJOR>;
+    auto kern = oz_gemm_kernel<S, KMAJOR, CL>;
     if (!configured) {
         LCX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
         configured = true;
     }
-    kern<<<grid, kThreads, SMEM, st>>>(mapA, mapB, mapBt, p);
-    LCX_CUDA(cudaGetLastError());
+    p.n_tiles = (int)grid.x;
+    grid.x = (unsigned)round_up(grid.x, CL);  // padded tiles load zeros (TMA OOB fill) and store nothing
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = SMEM;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    LCX_CUDA(cudaLaunchKernelEx(&cfg, kern, mapA, mapB, mapBt, p));
     return 0;
+}
+
+// cluster = how many N tiles share the M-side operand through TMA multicast (clamped to 1, 2 or 4)
+template <int S, bool KMAJOR>
+inline int launch_oz_gemm(const CUtensorMap& mapA, const CUtensorMap& mapB, const CUtensorMap& mapBt, const GemmParams& p,
+                          dim3 grid, cudaStream_t st, int cluster) {
+    if (cluster >= 4 && grid.x >= 4) return launch_oz_gemm_cl<S, KMAJOR, 4>(mapA, mapB, mapBt, p, grid, st);
+    if (cluster >= 2 && grid.x >= 2) return launch_oz_gemm_cl<S, KMAJOR, 2>(mapA, mapB, mapBt, p, grid, st);
+    return launch_oz_gemm_cl<S, KMAJOR, 1>(mapA, mapB, mapBt, p, grid, st);
 }
 
 }  // namespace oz
