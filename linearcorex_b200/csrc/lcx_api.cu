@@ -76,7 +76,14 @@ struct Layout {
     int oz_splits, oz_chunk;     // split-K of the second contraction (over samples)
     int oz1_splits, oz1_chunk;   // split-K of the first contraction (over variables), only when row tiles are scarce
     int ystat_slabs;
+    int radix;                   // 128: 7-bit signed digits (|d| <= 64); 254: full int8 range (|d| <= 127)
+    int oz_kmax;                 // longest contraction one int32 accumulator group may see: 2^31 / ((R/2)^2 S)
 };
+
+static int radix_for() {
+    const char* env = getenv("LCX_SPLIT_RADIX");
+    return (env && atoi(env) == 254) ? 254 : 128;
+}
 
 static int digits_for(int precision) {
     if (precision == LCX_PRECISION_FP64) return 0;
@@ -93,6 +100,12 @@ static Layout make_layout(long long Nl, int n, int m, int precision) {
     Layout L;
     memset(&L, 0, sizeof(L));
     L.S = digits_for(precision);
+    L.radix = radix_for();
+    if (L.S > 0) {
+        const long long half = L.radix / 2;
+        L.oz_kmax = (int)(((1LL << 31) / (half * half * L.S)) / 64 * 64);
+        if (L.oz_kmax > 65536) L.oz_kmax = 65536;
+    }
     L.ld = round_up(n, 16);
     L.ldm = round_up(m, 16);
     L.ldy = round_up(m, 8);
@@ -172,7 +185,7 @@ static Layout make_layout(long long Nl, int n, int m, int precision) {
         // of ~16 blocks) + the partial-buffer round trip; measured at 12.5k and 100k rows per GPU
         int best = 1;
         double best_cost = 1e300;
-        const int smin = cdiv(Nl, 65536), smax = (int)min(64LL, (long long)max(1, kblocks / 8));
+        const int smin = cdiv(Nl, L.oz_kmax), smax = (int)min(64LL, (long long)max(1, kblocks / 8));
         for (int sp = smin; sp <= max(smin, smax); ++sp) {
             const long long ctas = tiles * sp;
             const long long waves = (ctas + kSMs - 1) / kSMs;
@@ -185,9 +198,10 @@ static Layout make_layout(long long Nl, int n, int m, int precision) {
         {   // first contraction: same cost model over its (row tile x factor tile) grid
             const long long tiles1 = (long long)cdiv(Nl, oz::kBM) * cdiv(m, oz::kBN);
             const int kblocks1 = cdiv(n, oz::kBK);
-            int b1 = 1;
+            int b1 = cdiv(n, L.oz_kmax);
             double c1best = 1e300;
-            for (int sp = 1; sp <= max(1, min(8, kblocks1 / 16)); ++sp) {
+            const int s1min = cdiv(n, L.oz_kmax);  // int32 exactness of every accumulator group
+            for (int sp = s1min; sp <= max(s1min, min(8, kblocks1 / 16)); ++sp) {
                 const long long waves = (tiles1 * sp + kSMs - 1) / kSMs;
                 const double cost = (double)waves * (ceil((double)kblocks1 / sp) + 16.0) + (sp > 1 ? 4.0 * sp : 0.0);
                 if (cost < c1best - 1e-9) { c1best = cost; b1 = sp; }
@@ -403,7 +417,7 @@ static int oz_slice_x_t(lcx_session* s) {
     LAUNCHED(s);
     dim3 grid((unsigned)s->Nl, cdiv(L.ld8, 4 * 128));
     oz::slice_rows_kernel<S><<<grid, 128, 0, s->stream>>>(s->xt, s->ldx, (int)s->Nl, s->n, nullptr, s->oz_xscale(), s->xs(), L.ld8,
-                                                        s->Nl * L.ld8);
+                                                        s->Nl * L.ld8, (double)L.radix);
     LAUNCHED(s);
     LCX_CUDA(cudaGetLastError());
     return 0;
@@ -411,7 +425,7 @@ static int oz_slice_x_t(lcx_session* s) {
 
 static int oz_prepare(lcx_session* s, bool streamed) {
     const Layout& L = s->L;
-    LCX_REQUIRE(s->n <= 65536, "split-integer modes support at most 65536 variables per contraction (int32 exactness)");
+    LCX_REQUIRE(L.oz1_chunk <= L.oz_kmax && L.oz_chunk <= L.oz_kmax, "contraction chunk exceeds the int32-exact length");
     if (!streamed) switch (L.S) {
         case 3: LCX_TRY(oz_slice_x_t<3>(s)); break;
         case 4: LCX_TRY(oz_slice_x_t<4>(s)); break;
@@ -448,7 +462,7 @@ static int oz_pair_t(lcx_session* s, const double* A, double* svec, cudaEvent_t*
     oz::mul_scale_kernel<<<cdiv(m, 128), 128, 0, s->stream>>>(s->oz_xscale(), s->oz_ascale(), s->oz_cscale(), m);
     LAUNCHED(s);
     oz::slice_rows_kernel<S><<<dim3(m, cdiv(L.ld8, 4 * 128)), 128, 0, s->stream>>>(A, L.ld, m, n, s->oz_ascale(), nullptr, s->as(), L.ld8,
-                                                                              (long long)m * L.ld8);
+                                                                              (long long)m * L.ld8, (double)L.radix);
     LAUNCHED(s);
     {
         oz::GemmParams p;
@@ -457,6 +471,7 @@ static int oz_pair_t(lcx_session* s, const double* A, double* svec, cudaEvent_t*
         p.C = split1 ? s->ptr(I_PART) : Y;
         p.ldc = L.ldy; p.c_split_stride = split1 ? s->Nl * L.ldy : 0;
         p.col_scale = s->oz_cscale();
+        p.inv_radix = 1.0 / (double)L.radix;
         p.rows = (int)s->Nl; p.cols = m; p.k_total = n; p.k_chunk = L.oz1_chunk;
         p.bn_tail = s->oz_bn_tail;
         LCX_TRY((oz::launch_oz_gemm<S, true>(s->map_x_k1, s->map_a_k1, s->map_a_k1_tail, p,
@@ -481,7 +496,7 @@ static int oz_pair_t(lcx_session* s, const double* A, double* svec, cudaEvent_t*
         return 0;
     }
     oz::slice_cols_kernel<S><<<dim3((unsigned)cdiv(s->Nl, 8), cdiv(L.ldy8, 4 * 32)), dim3(32, 8), 0, s->stream>>>(
-        Y, L.ldy, s->Nl, m, s->oz_yscale(), s->ys(), L.ldy8, s->Nl * L.ldy8);
+        Y, L.ldy, s->Nl, m, s->oz_yscale(), s->ys(), L.ldy8, s->Nl * L.ldy8, (double)L.radix);
     LAUNCHED(s);
     // ---- D = (X~^T Y)^T, factor-major, split over samples ----
     {
@@ -491,6 +506,7 @@ static int oz_pair_t(lcx_session* s, const double* A, double* svec, cudaEvent_t*
         p.C = split ? s->ptr(I_PART) : D;
         p.ldc = L.ld; p.c_split_stride = split ? (long long)m * L.ld : 0;
         p.row_scale = s->oz_dscale();
+        p.inv_radix = 1.0 / (double)L.radix;
         p.rows = m; p.cols = n; p.k_total = (int)s->Nl; p.k_chunk = L.oz_chunk;
         LCX_TRY((oz::launch_oz_gemm<S, false>(s->map_y_k2, s->map_x_k2, s->map_x_k2, p,
                                               dim3(cdiv(n, oz::kBN), cdiv(m, oz::kBM), L.oz_splits), s->stream, oz_cluster())));
@@ -570,7 +586,7 @@ static int oz_slice_block_t(lcx_session* s, const double* xt, long long row0, lo
     const Layout& L = s->L;
     dim3 grid((unsigned)rows, cdiv(L.ld8, 4 * 128));
     oz::slice_rows_kernel<S><<<grid, 128, 0, s->stream>>>(xt, ldx, (int)rows, s->n, nullptr, s->oz_xscale(), s->xs() + row0 * L.ld8,
-                                                        L.ld8, s->Nl * L.ld8);
+                                                        L.ld8, s->Nl * L.ld8, (double)L.radix);
     LAUNCHED(s);
     LCX_CUDA(cudaGetLastError());
     return 0;

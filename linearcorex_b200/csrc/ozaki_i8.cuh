@@ -145,6 +145,7 @@ struct GemmParams {
     int rows, cols;              // valid output extent
     int k_total;                 // contraction length
     int k_chunk;                 // contraction range per blockIdx.z (multiple of kBK)
+    double inv_radix;            // 1 / R: group g carries weight R^-(g+2)
     int n_tiles;                 // number of real N tiles (gridDim.x may be padded up to a multiple of the cluster size)
     int bn_tail;                 // K-major only: width (multiple of 16, <= 64) of the LAST N tile, loaded through mapBt;
                                  // 0 or 64 = full width.  m = 100 factors -> tiles of 64 + 48 instead of 64 + 64
@@ -316,7 +317,7 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                     tmem_ld16(lane_addr + (uint32_t)(g * bn + c0), r);
                     tmem_ld_wait();
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) acc[j] = acc[j] * 0.0078125 + (double)(int)r[j];  // 2^-7 per group
+                    for (int j = 0; j < 16; ++j) acc[j] = acc[j] * p.inv_radix + (double)(int)r[j];  // 1/R per group
                 }
             } else {
 #pragma unroll
@@ -327,8 +328,8 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 #pragma unroll
                 for (int j = 0; j < 16; j += 2) {
                     const int col = col0 + j;
-                    // group g = 0 carries weight 2^-14 (digits k = l = 1)
-                    double v0 = acc[j] * 6.103515625e-05 * rs, v1 = acc[j + 1] * 6.103515625e-05 * rs;
+                    // group g = 0 carries weight R^-2 (digits k = l = 1)
+                    double v0 = acc[j] * (p.inv_radix * p.inv_radix) * rs, v1 = acc[j + 1] * (p.inv_radix * p.inv_radix) * rs;
                     if (p.col_scale != nullptr) {
                         if (col < p.cols) v0 *= p.col_scale[col];
                         if (col + 1 < p.cols) v1 *= p.col_scale[col + 1];
@@ -352,13 +353,14 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 }
 
 // ---- digit extraction -----------------------------------------------------------------------------
-// v = x * 2^-E in (-0.5, 0.5);  repeat: t = 128 v, d = rint(t), v = t - d   (all exact in binary64).
+// v = x * 2^-E in (-0.5, 0.5);  repeat: t = R v, d = rint(t), v = t - d.  |t| <= R/2, so |d| <= 64 for R = 128 (every step
+// exact in binary64) and |d| <= 127 for R = 254 (t = 254 v rounds at the 2^-53 level -- far below the last digit kept).
 template <int S>
-__device__ __forceinline__ void split_digits(double x, double inv_scale, int8_t (&d)[S]) {
+__device__ __forceinline__ void split_digits(double x, double inv_scale, double radix, int8_t (&d)[S]) {
     double v = x * inv_scale;
 #pragma unroll
     for (int k = 0; k < S; ++k) {
-        const double t = v * 128.0;
+        const double t = v * radix;
         const double r = rint(t);
         d[k] = (int8_t)(int)r;
         v = t - r;
@@ -378,7 +380,7 @@ __device__ __forceinline__ double pow2_above(double amax) {
 template <int S>
 __global__ void slice_rows_kernel(const double* __restrict__ in, long long ld_in, int rows, int cols,
                                   const double* __restrict__ row_scale, const double* __restrict__ one_scale,
-                                  int8_t* __restrict__ out, long long ld_out, long long slice_stride) {
+                                  int8_t* __restrict__ out, long long ld_out, long long slice_stride, double radix) {
     const long long r = blockIdx.x;  // rows on grid.x (up to 2^31 - 1), column blocks on grid.y
     const int c4 = (blockIdx.y * blockDim.x + threadIdx.x) * 4;
     if (r >= rows || c4 >= ld_out) return;
@@ -388,7 +390,7 @@ __global__ void slice_rows_kernel(const double* __restrict__ in, long long ld_in
     for (int j = 0; j < 4; ++j) {
         const int c = c4 + j;
         const double x = (c < cols) ? in[r * ld_in + c] : 0.0;
-        split_digits<S>(x, inv, d[j]);
+        split_digits<S>(x, inv, radix, d[j]);
     }
 #pragma unroll
     for (int k = 0; k < S; ++k) {
@@ -401,7 +403,7 @@ __global__ void slice_rows_kernel(const double* __restrict__ in, long long ld_in
 template <int S>
 __global__ void slice_cols_kernel(const double* __restrict__ in, long long ld_in, long long rows, int cols,
                                   const double* __restrict__ col_scale, int8_t* __restrict__ out, long long ld_out,
-                                  long long slice_stride) {
+                                  long long slice_stride, double radix) {
     const long long r = (long long)blockIdx.x * blockDim.y + threadIdx.y;
     const int c4 = (blockIdx.y * blockDim.x + threadIdx.x) * 4;
     if (r >= rows || c4 >= ld_out) return;
@@ -411,7 +413,7 @@ __global__ void slice_cols_kernel(const double* __restrict__ in, long long ld_in
         const int c = c4 + j;
         const double x = (c < cols) ? in[r * ld_in + c] : 0.0;
         const double inv = (c < cols) ? 1.0 / col_scale[c] : 1.0;
-        split_digits<S>(x, inv, d[j]);
+        split_digits<S>(x, inv, radix, d[j]);
     }
 #pragma unroll
     for (int k = 0; k < S; ++k) {
