@@ -210,7 +210,8 @@ def run_reference(args, shape):
 def workload_name(args, shape):
     return "%s: synthetic latent-factor data N=%d x n=%d, m=%d, %s mode" % (
         args.workload, shape[0], shape[1], shape[2],
-        {"fp64": "FP64 (DMMA)", "fp64_split": "FP64 (split-int8 x6 on tcgen05)", "fast": "fast (split-int8 x4)"}[args.precision])
+        {"fp64": "FP64 (DMMA)", "fp64_split": "FP64 (6 int8 radix-254 digit planes on tcgen05)",
+         "fp64_split5": "FP64 (5 int8 radix-254 digit planes on tcgen05)", "fast": "fast (3 int8 digit planes)"}[args.precision])
 
 
 # ----------------------------------------------------------------------------------------------------
@@ -303,7 +304,7 @@ def run_ours(args, shape):
     pair_flops = 4.0 * n_local * n_vars * n_factors           # K1 + K2 of one pass pair on this rank (FP64-equivalent)
     pair_ms = (k1.value + k2.value) / max(1, pairs.value)
     fp64_equiv = pair_flops / (pair_ms / 1e3) / 1e12 if pair_ms > 0 else 0.0
-    digits = {"fp64": 0, "fp64_split": 6, "fast": 4}[args.precision]
+    digits = {"fp64": 0, "fp64_split": 6, "fp64_split5": 5, "fast": 3}[args.precision]
     if os.environ.get("LCX_SPLIT_DIGITS") and digits:
         digits = int(os.environ["LCX_SPLIT_DIGITS"])
     if digits:
@@ -392,8 +393,9 @@ def run_ours(args, shape):
     line = {
         "metric": METRIC, "value": it_s, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-        "dtype": {"fp64": "f64", "fp64_split": "f64 (int8x6 split products, int32/f64 accumulation)",
-                  "fast": "int8x4 split products"}[args.precision], "data": "synthetic",
+        "dtype": {"fp64": "f64", "fp64_split": "f64 (6 int8 digit planes = 48 bits, exact int32 products, f64 recombination)",
+                  "fp64_split5": "f64 (5 int8 digit planes = 40 bits, exact int32 products, f64 recombination)",
+                  "fast": "3 int8 digit planes = 24 bits (fp32-equivalent), f64 elsewhere"}[args.precision], "data": "synthetic",
         "config": {"workload": workload_name(args, shape), "n_samples": n_total, "n_variables": n_vars,
                    "n_factors": n_factors, "rows_per_gpu": n_local, "parallelism": "sample-sharded x%d" % world, "exchange_per_pass_pair": exchange,
                    "l2": "inputs_exceed_l2 (X~ block is %.1f GB per GPU)"
@@ -443,7 +445,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="config3", choices=sorted(WORKLOADS))
-    ap.add_argument("--precision", default="fp64_split", choices=["fp64", "fp64_split", "fast"])
+    ap.add_argument("--precision", default="fp64_split", choices=["fp64", "fp64_split", "fp64_split5", "fast"])
     ap.add_argument("--gaussianize", default="standard")
     ap.add_argument("--rows", type=int, default=0)
     ap.add_argument("--vars", type=int, default=0)

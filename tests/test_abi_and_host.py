@@ -36,6 +36,7 @@ def test_layout_arithmetic_without_gpu():
     big = lib.lcx_workspace_doubles(100000, 10000, 100, 0)
     split = lib.lcx_workspace_doubles(100000, 10000, 100, 2)
     assert split > big + 6 * 100000 * 10000 // 8  # six int8 digit planes of X~
+    assert lib.lcx_workspace_doubles(100000, 10000, 100, 3) < split  # five planes
     assert 0 < small < big
     # config 3 workspace: Y (100000 x 104) + ~20 m x n arrays + split-K partials, well under 1 GB
     assert big * 8 < 1.0e9
