@@ -461,6 +461,11 @@ def main():
             shape[i] = v
     if args.workload == "config4":
         args.gaussianize = "outliers"
+    if args.traffic is None and args.workload == "config3" and args.gpus == 1 and not (args.rows or args.vars or args.factors):
+        # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
+        # `ncu --set full` captures (profiles/r01_oz_gemm_ncu_full_config3.csv, profiles/r01_dgemm_ncu_full_config3.csv):
+        # mean of the two contractions; algorithmic bytes are 6.09e9 (split, 6 planes) / 8.09e9 (DMMA) per launch
+        args.traffic = {"fp64_split": 6.31e9, "fp64": 8.17e9}.get(args.precision)
     if args.impl == "reference":
         run_reference(args, tuple(shape))
     else:
