@@ -16,9 +16,9 @@ device session raises.
 Extensions over the reference signature (all keyword-only in spirit, defaults keep reference
 behaviour):
   eliminate_synergy   README/docstring name of `discourage_overlap` (README.md:32)
-  precision           'fp64' (default): all arithmetic binary64 (DMMA tensor-core contractions), parity
-                      target = the reference's numpy float64 path.
-                      'fp64_split': the two X contractions run as exact int8 digit products on tcgen05
+  precision           'fp64': all arithmetic binary64 (DMMA tensor-core contractions), parity target = the
+                      reference's numpy float64 path.
+                      'fp64_split' (default): the two X contractions run as exact int8 digit products on tcgen05
                       (6 radix-254 digits = 48 bits below each row/column maximum -- truncation at the level of
                       binary64 rounding, measured parity 1e-11), everything else binary64.
                       'fp64_split5': 5 digits (40 bits), 30 % faster, parity 1e-9 on fits up to ~700 iterations.
@@ -184,7 +184,7 @@ class Corex(object):
 
     def __init__(self, n_hidden=10, max_iter=10000, tol=1e-5, anneal=True, missing_values=None,
                  discourage_overlap=True, gaussianize='standard', gpu=True, verbose=False, seed=None,
-                 eliminate_synergy=None, precision='fp64', exact_trials=False, input_dtype='float64',
+                 eliminate_synergy=None, precision='fp64_split', exact_trials=False, input_dtype='float64',
                  comm=None, device=None, stream_rows=None):
         self.m = n_hidden
         self.max_iter = max_iter

@@ -184,20 +184,21 @@ FIT_CASES = ["readme_demo_f64", "big5_l0_f64", "big5_l1_f64", "syn_400x300x10_f6
 @pytest.mark.parametrize("name", FIT_CASES)
 def test_full_fit_exact_trials(name):
     """Reference control flow step for step (a pass pair over X per trial, like linearcorex.py:321)."""
-    z, mdl, x = _fit(name, exact_trials=True)
+    z, mdl, x = _fit(name, exact_trials=True, precision="fp64")
     _check_fit(z, mdl, x, RTOL)
 
 
 @pytest.mark.parametrize("name", FIT_CASES)
 def test_full_fit_linear_trials(name):
-    """Default path: trials through the linearity of _sig -- same iterates to 1e-9, one X pass pair per iteration."""
-    z, mdl, x = _fit(name)
+    """Trials through the linearity of _sig -- same iterates to 1e-9, one X pass pair per iteration (DMMA contractions)."""
+    z, mdl, x = _fit(name, precision="fp64")
     _check_fit(z, mdl, x, RTOL)
 
 
 @pytest.mark.parametrize("name", ["syn_400x300x10_synergy_f64", "big5_syn_f64"])
-def test_full_fit_synergy(name):
-    z, mdl, x = _fit(name)
+@pytest.mark.parametrize("precision", ["fp64", "fp64_split"])
+def test_full_fit_synergy(name, precision):
+    z, mdl, x = _fit(name, precision=precision)
     _check_fit(z, mdl, x, 1e-8)
 
 
@@ -205,7 +206,7 @@ def test_toy_duplicate_columns_known_answer():
     """tests/data/test_data.csv (8 x 5, v1=v2=v3, v4=v5): exactly duplicated columns drive rho -> 1 and the
     reference itself into its "covariance is nearly singular" regime, where the trajectory is chaotic in the
     last bits.  Pinned: the early trajectory at 1e-9 and the known answer clusters == [0,0,0,1,1] up to labels."""
-    z, mdl, x = _fit("test_data_f64", exact_trials=True)
+    z, mdl, x = _fit("test_data_f64", exact_trials=True, precision="fp64")
     k = 12
     assert_close(np.asarray(mdl.history["TC"][:k]), z["history_TC"][:k], 1e-7, "early TC trajectory")
     c = mdl.clusters()
@@ -213,7 +214,7 @@ def test_toy_duplicate_columns_known_answer():
 
 
 SPLIT_CASES = ["readme_demo_f64", "big5_l0_f64", "syn_400x300x10_f64", "syn_60x400x8_f64", "outliers_missing_f64",
-               "standard_missing_f64", "adni_l1_f64"]
+               "standard_missing_f64", "adni_l1_f64", "big5_l1_f64", "adni_l2_f64"]  # the last two: n = 5 variables, m = 1
 
 
 @pytest.mark.parametrize("name", SPLIT_CASES)
@@ -273,14 +274,14 @@ def test_synthetic_4000x2000x20_fp64_split():
 def test_adni_layer0_missing_values():
     """566 x 200, 3.1 % missing, 30 factors, ~2400 iterations: long trajectories amplify rounding, so this one
     is held to the iteration count, TC at 1e-9 and cluster labels."""
-    z, mdl, x = _fit("adni_l0_f64")
+    z, mdl, x = _fit("adni_l0_f64", precision="fp64")
     assert abs(len(mdl.history["TC"]) - len(z["history_TC"])) <= 2
     assert_close(mdl.tc, z["m_TC"], 1e-8, "TC")
     assert np.mean(mdl.clusters() == z["clusters"]) > 0.99
 
 
 def test_synthetic_4000x2000x20():
-    z, mdl, x = _fit("syn_4000x2000x20_f64")
+    z, mdl, x = _fit("syn_4000x2000x20_f64", precision="fp64")
     _check_fit(z, mdl, x, RTOL)
     # planted structure: variable i belongs to group i mod 20
     c = mdl.clusters()
@@ -303,6 +304,23 @@ def test_layer_stacking_matches_reference_chain():
     upper = fit_layers(xa, [5, 1], seed=0)
     assert_close(upper[0].tc, za["m_TC"], RTOL, "adni layer 1 TC")
     assert_close(upper[1].tc, zb["m_TC"], 1e-7, "adni layer 2 TC")
+
+
+def test_refit_and_second_model_release_device_state():
+    """fit() twice on one object and a second model of another shape: sessions rebind cleanly."""
+    from linearcorex_b200 import Corex
+    z, kw, x = load_golden("syn_400x300x10_f64")
+    mdl = Corex(precision="fp64_split", **kw).fit(x)
+    w1 = mdl.ws.copy()
+    mdl.ws = np.zeros((0, 0))
+    np.random.seed(0)
+    mdl.history, mdl.trace, mdl.eps = {}, [], 0
+    mdl.fit(x)
+    assert_close(mdl.ws, w1, 1e-12, "refit")
+    z2, kw2, x2 = load_golden("big5_l0_f64")
+    other = Corex(**kw2).fit(x2)
+    assert_close(other.ws, z2["ws"], RTOL, "second model")
+    assert_close(mdl.transform(x), z["transform"], RTOL, "first model still transforms")
 
 
 def test_pickle_and_warm_start():
