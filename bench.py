@@ -208,6 +208,8 @@ def run_reference(args, shape):
 
 
 def workload_name(args, shape):
+    if args.impl == "reference":
+        return "%s: synthetic latent-factor data N=%d x n=%d, m=%d, FP64 mode" % (args.workload, shape[0], shape[1], shape[2])
     return "%s: synthetic latent-factor data N=%d x n=%d, m=%d, %s mode" % (
         args.workload, shape[0], shape[1], shape[2],
         {"fp64": "FP64 (DMMA)", "fp64_split": "FP64 (6 int8 radix-254 digit planes on tcgen05)",
