@@ -15,7 +15,9 @@ One JSON line on stdout (rank 0).  `value` = fit iterations per second with X~ r
 CUDA events around exactly K iterations, max over ranks.  `e2e` = the same metric through the public API
 (`Corex(...).fit(x_host)`) with the host->device copy of X, preprocessing, the fit, the final moment export
 and the device->host copies all inside the timed region.  `roofline` is for the dominant kernel (the two
-FP64 tensor-core contractions, >97 % of a step), timed live by CUDA events on the launching stream.
+contractions over X, 93 % of a step: `oz_gemm_kernel`, exact int8 digit-plane products on tcgen05 in the default
+FP64-faithful mode `fp64_split`; `dgemm_mma_kernel`, DMMA, with --precision fp64), timed live by CUDA events on the
+launching stream.
 `cpu_baseline` / `--impl reference` time oracle/corex_oracle.py (the numpy restatement of the reference;
 /root/reference does not exist on the GPU box) on a bounded row subsample with all host threads.
 """

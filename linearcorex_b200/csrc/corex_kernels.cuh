@@ -408,13 +408,6 @@ __global__ void __launch_bounds__(256) syn_qi_kernel(const double* __restrict__ 
     }
 }
 
-// D *= scale (elementwise over the valid m x n region)
-__global__ void scale_all_kernel(double* __restrict__ a, double scale, int m, int n, long long ld) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    const int j = blockIdx.y;
-    if (i < n && j < m) a[(long long)j * ld + i] *= scale;
-}
-
 // a[j][j] += v
 __global__ void diag_add_kernel(double* __restrict__ a, long long ld, int m, double v) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;

@@ -323,6 +323,21 @@ def test_refit_and_second_model_release_device_state():
     assert_close(mdl.transform(x), z["transform"], RTOL, "first model still transforms")
 
 
+@pytest.mark.parametrize("precision", ["fp64", "fp64_split"])
+def test_gaussianize_none_on_standardised_input(precision):
+    """gaussianize='none' skips the transformation (:407-408); the math assumes <X_i^2> = 1, so the input is standardised here."""
+    import corex_oracle as oc
+    from linearcorex_b200 import Corex
+    z, kw, x = load_golden("syn_400x300x10_f64")
+    xs, _, _ = oc.standardize(x.astype(np.float64), "standard", None)
+    kw = dict(kw, gaussianize="none", max_iter=6, tol=1e-12)
+    ref = oc.OracleCorex(work_dtype=np.float64, **kw).fit(xs)
+    mdl = Corex(precision=precision, **kw).fit(xs)
+    assert mdl.theta is None and len(mdl.history["TC"]) == len(ref.history["TC"])
+    assert_close(mdl.ws, ref.ws, RTOL, "ws")
+    assert_close(mdl.transform(xs), ref.transform(xs), RTOL, "transform")
+
+
 def test_pickle_and_warm_start():
     from linearcorex_b200 import Corex
     z, mdl, x = _fit("syn_400x300x10_f64")
