@@ -619,6 +619,24 @@ extern "C" int lcx_array_info(lcx_session* s, int array_id, int set, long long* 
     return 0;
 }
 
+// Where the int8 digit planes and their power-of-two scales live (split modes; for inspection and bit-exact tests).
+extern "C" int lcx_digit_planes_info(lcx_session* s, int which, long long* offset, int* digits, long long* rows,
+                                     long long* cols, long long* ld_bytes, long long* scale_offset, int* radix) {
+    S_REQUIRE_BOUND(s);
+    const Layout& L = s->L;
+    LCX_REQUIRE(L.S > 0, "no digit planes in the DMMA mode");
+    LCX_REQUIRE(which >= 0 && which <= 2, "which: 0 = X~, 1 = A (last small operand), 2 = Y");
+    const int slot = which == 0 ? I_XS : (which == 1 ? I_AS : I_YS);
+    if (offset) *offset = L.slot[slot][0].off;
+    if (digits) *digits = L.S;
+    if (rows) *rows = which == 1 ? s->m : s->Nl;
+    if (cols) *cols = which == 2 ? s->m : s->n;
+    if (ld_bytes) *ld_bytes = which == 2 ? L.ldy8 : L.ld8;
+    if (scale_offset) *scale_offset = L.slot[I_OZV][0].off + (which == 0 ? 0 : (which == 1 ? 16 : 16 + 2 * L.ldm));
+    if (radix) *radix = L.radix;
+    return 0;
+}
+
 // ---- preprocessing -----------------------------------------------------------------------------
 static const int kSlabRows = 4096;
 

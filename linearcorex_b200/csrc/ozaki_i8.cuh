@@ -360,10 +360,11 @@ __device__ __forceinline__ void split_digits(double x, double inv_scale, double 
     double v = x * inv_scale;
 #pragma unroll
     for (int k = 0; k < S; ++k) {
-        const double t = v * radix;
+        const double t = __dmul_rn(v, radix);  // no FMA contraction with the subtraction below: digits are then exactly
+                                               // what the same three binary64 operations give anywhere (numpy in the tests)
         const double r = rint(t);
         d[k] = (int8_t)(int)r;
-        v = t - r;
+        v = __dsub_rn(t, r);
     }
 }
 

@@ -132,3 +132,66 @@ def test_preprocess_matches_oracle(dev, dtype, mode, missing):
     xt2 = mdl.preprocess(x2)[:, :37].cpu().numpy()
     want2, _, _ = oc.standardize(x2.astype(np.float64), mode, missing, theta=theta)
     np.testing.assert_allclose(xt2, want2, rtol=1e-10, atol=1e-11)
+
+
+def _planes(sess, L, torch, which):
+    import ctypes as C
+    off, rows, cols, ldb, soff = (C.c_longlong() for _ in range(5))
+    digits, radix = C.c_int(), C.c_int()
+    L.check(sess.lib.lcx_digit_planes_info(sess.h, which, C.byref(off), C.byref(digits), C.byref(rows), C.byref(cols),
+                                           C.byref(ldb), C.byref(soff), C.byref(radix)))
+    S, R, nr, nc, ld = digits.value, radix.value, rows.value, cols.value, ldb.value
+    raw = sess.ws[off.value: off.value + (S * nr * ld + 7) // 8].view(torch.int8)[: S * nr * ld]
+    planes = raw.view(S, nr, ld)[:, :, :nc].cpu().numpy().astype(np.int64)
+    nscale = 1 if which == 0 else sess.m
+    scale = sess.ws[soff.value: soff.value + nscale].cpu().numpy()
+    return planes, scale, S, R
+
+
+@pytest.mark.parametrize("precision", ["fp64_split", "fast"])
+def test_digit_planes_bit_exact_against_numpy(precision):
+    """Integer work is held to bit-exactness: the device's int8 digit planes of X~, A and Y equal the numpy restatement of
+    the digit extraction (tests/test_split_scheme.py) digit for digit, and the recombined products are the exact integer sums."""
+    import torch
+    from linearcorex_b200 import _lib as L
+    from linearcorex_b200.corex import _DeviceSession
+    from test_split_scheme import pow2_above, split_digits
+    rng = np.random.RandomState(3)
+    N, n, m = 700, 333, 37
+    x = rng.randn(N, n)
+    x[5, 17] = -9.25
+    u = rng.randn(m, n) * rng.uniform(1e-3, 4.0, size=(m, 1))
+    sess = _DeviceSession(L.PRECISIONS[precision])
+    ld = sess.lib.lcx_ld(n)
+    xt = torch.zeros((N, ld), dtype=torch.float64, device="cuda")
+    xt[:, :n] = torch.from_numpy(x)
+    sess.bind(xt, N, n, m, None)
+    ud = torch.zeros((m, ld), dtype=torch.float64, device="cuda")
+    ud[:, :n] = torch.from_numpy(u)
+    od = torch.zeros_like(ud)
+    L.check(sess.lib.lcx_sig(sess.h, ud.data_ptr(), 0.0, od.data_ptr()))
+    torch.cuda.synchronize()
+    px, sx, S, R = _planes(sess, L, torch, 0)
+    pa, sa, _, _ = _planes(sess, L, torch, 1)
+    py, sy, _, _ = _planes(sess, L, torch, 2)
+    assert sx[0] == pow2_above(np.abs(x).max())
+    np.testing.assert_array_equal(sa, [pow2_above(np.abs(r).max()) for r in u])
+    for k, want in enumerate(split_digits(x, sx[0], S, R)):
+        np.testing.assert_array_equal(px[k], want)
+    for k, want in enumerate(split_digits(u, sa[:, None], S, R)):
+        np.testing.assert_array_equal(pa[k], want)
+    y_dev = sess.view(L.A_Y).cpu().numpy()
+    np.testing.assert_array_equal(sy, [pow2_above(np.abs(c).max()) for c in y_dev.T])
+    for k, want in enumerate(split_digits(y_dev, sy[None, :], S, R)):
+        np.testing.assert_array_equal(py[k], want)
+    # Y itself = the exact integer group sums recombined by the same Horner steps
+    groups = [np.zeros((N, m), dtype=np.int64) for _ in range(S)]
+    for k in range(S):
+        for l in range(S - k):
+            groups[k + l] += px[k] @ pa[l].T
+    acc = groups[S - 1].astype(np.float64)
+    for g in range(S - 2, -1, -1):
+        acc = acc * (1.0 / R) + groups[g]
+    want_y = acc * ((1.0 / R) * (1.0 / R)) * (sx[0] * sa)[None, :]
+    np.testing.assert_allclose(y_dev, want_y, rtol=4e-16, atol=0)
+    sess.close()
