@@ -710,6 +710,63 @@ class Corex(object):
     # ------------------------------------------------------------------------------------------
     # transform / invert / predict / get_covariance (:386-395, :431-455)
     # ------------------------------------------------------------------------------------------
+    def _transform_rows_for(self, x):
+        """Row-block size for a streamed transform (inputs that are row providers, or too large to preprocess at once)."""
+        torch = _torch()
+        if not isinstance(x, (np.ndarray, torch.Tensor, list, tuple)):
+            return int(self.stream_rows or 32768)
+        n_rows, n_vars = int(np.shape(x)[0]), int(np.shape(x)[1])
+        free, _total = torch.cuda.mem_get_info(self._session().device)
+        return int(self.stream_rows or 32768) if n_rows * self._session().lib.lcx_ld(n_vars) * 12 > 0.8 * free else 0
+
+    def _transform_streamed(self, x, rows):
+        """transform() in row blocks: preprocess (stored theta; imputation means of the new data from a first pass when a
+        missing marker is set, :389/:404) and project block by block into one (N, ldy) device tensor."""
+        torch = _torch()
+        sess = self._session()
+        lib = sess.lib
+        red = self._reducer()
+        N, n = int(np.shape(x)[0]), int(np.shape(x)[1])
+        ld, ldy = lib.lcx_ld(n), lib.lcx_ldy(self.m)
+        has_marker = self.missing_values is not None
+        marker = float(self.missing_values) if has_marker else 0.0
+        mode = _lib.GAUSS[self.gaussianize]
+        blocks = [(lo, min(N, lo + rows)) for lo in range(0, N, rows)]
+        vec = lambda: torch.zeros(n, dtype=torch.float64, device=sess.device)
+        impute = None
+        if has_marker:
+            nscr = lib.lcx_colstats_scratch_doubles(rows, n)
+            scratch = torch.empty(nscr, dtype=torch.float64, device=sess.device)
+            ssum, cnt, t1, t2, impute = vec(), vec(), vec(), vec(), vec()
+            for lo, hi in blocks:
+                xd = self._as_input(x[lo:hi])
+                dt = _lib.F32 if xd.dtype == torch.float32 else _lib.F64
+                _lib.check(lib.lcx_colstats_sum(sess.h, xd.data_ptr(), dt, hi - lo, n, xd.stride(0), 1, marker, t1.data_ptr(),
+                                                t2.data_ptr(), scratch.data_ptr(), nscr), "lcx_colstats_sum")
+                ssum += t1
+                cnt += t2
+            red.sum_(ssum)
+            red.sum_(cnt)
+            _lib.check(lib.lcx_colstats_mean(sess.h, ssum.data_ptr(), cnt.data_ptr(), impute.data_ptr(), n))
+        mean = sd = None
+        if mode != _lib.GAUSS['none']:
+            if self._theta_dev is None:
+                self._theta_dev = tuple(torch.as_tensor(np.asarray(t, dtype=np.float64), device=sess.device) for t in self.theta)
+            mean, sd = self._theta_dev
+        p = lambda t: t.data_ptr() if t is not None else None
+        wd = torch.zeros((self.m, ld), dtype=torch.float64, device=sess.device)
+        wd[:, :n].copy_(torch.from_numpy(np.ascontiguousarray(self.ws, dtype=np.float64)))
+        xt = torch.empty((rows, ld), dtype=torch.float64, device=sess.device)
+        y = torch.empty((N, ldy), dtype=torch.float64, device=sess.device)
+        for lo, hi in blocks:
+            xd = self._as_input(x[lo:hi])
+            dt = _lib.F32 if xd.dtype == torch.float32 else _lib.F64
+            _lib.check(lib.lcx_standardize(sess.h, xd.data_ptr(), dt, hi - lo, n, xd.stride(0), int(has_marker), marker, mode,
+                                           p(impute), p(mean), p(sd), xt.data_ptr(), ld), "lcx_standardize")
+            _lib.check(lib.lcx_project(sess.h, xt.data_ptr(), hi - lo, n, ld, wd.data_ptr(), ld, self.m,
+                                       y[lo:hi].data_ptr(), ldy, None, None, 0), "lcx_project")
+        return y
+
     def transform(self, x, details=False, return_device=False):
         """Y = preprocess(x) . ws^T (:386-395).  Returns an (N, m) float64 ndarray; with
         `details=True` also the full moments of `x` under the fitted weights.  `return_device=True`
@@ -717,9 +774,14 @@ class Corex(object):
         torch = _torch()
         sess = self._session()
         lib = sess.lib
-        xt = self.preprocess(x)
-        ns, nv = xt.shape[0], int(np.shape(x)[1])
+        nv = int(np.shape(x)[1])
         assert self.nv == nv, "Incorrect number of variables in input, %d instead of %d" % (nv, self.nv)
+        rows = self._transform_rows_for(x)
+        if rows and not details:
+            y = self._transform_streamed(x, rows)
+            return y[:, :self.m] if return_device else y[:, :self.m].cpu().numpy().copy()
+        xt = self.preprocess(x)
+        ns = xt.shape[0]
         w = np.ascontiguousarray(self.ws, dtype=np.float64)
         ld = lib.lcx_ld(nv)
         wd = torch.zeros((self.m, ld), dtype=torch.float64, device=sess.device)

@@ -266,6 +266,28 @@ def test_adni_layer0_fp64_split_long_trajectory():
     np.testing.assert_array_equal(mdl.clusters(), z["clusters"])
 
 
+class _Rows(object):
+    """Row provider with only `.shape` and row slicing (what a memmap / generator-backed source offers)."""
+
+    def __init__(self, a):
+        self.a, self.shape = a, a.shape
+
+    def __getitem__(self, sl):
+        return self.a[sl]
+
+
+@pytest.mark.parametrize("name", ["outliers_missing_f64", "syn_400x300x10_f64"])
+def test_streamed_fit_and_transform_from_row_provider(name):
+    from linearcorex_b200 import Corex
+    z, kw, x = load_golden(name)
+    mdl = Corex(precision="fp64_split", stream_rows=64, **kw).fit(_Rows(x))
+    assert_close(mdl.ws, z["ws"], RTOL, "ws")
+    y = mdl.transform(_Rows(x))
+    assert_close(y, z["transform"], RTOL, "streamed transform")
+    yd = mdl.transform(_Rows(x), return_device=True)
+    assert yd.is_cuda and tuple(yd.shape) == z["transform"].shape
+
+
 def test_synthetic_4000x2000x20_fp64_split():
     z, mdl, x = _fit("syn_4000x2000x20_f64", precision="fp64_split")
     _check_fit(z, mdl, x, RTOL)
