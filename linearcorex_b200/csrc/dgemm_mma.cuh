@@ -10,8 +10,9 @@
 // Shape of one CTA: 128 x (8*NT) output tile, 8 warps stacked along M (16 rows each, the full tile
 // width), K consumed in 16-wide slabs through a STAGES-deep cp.async ring.  The inner product is
 // DMMA.8x8x4 (mma.sync.m8n8k4.f64) -- on sm_100a every PTX f64 mma shape lowers to that SASS
-// instruction, so it is issued directly.  tcgen05 has no f64 kind; the fast mode (gemm_tf32x3.cuh)
-// is the tcgen05/TMEM path.
+// instruction, so it is issued directly.  tcgen05 has no f64 kind; the tcgen05/TMEM/TMA path is the
+// split-integer engine of ozaki_i8.cuh, which replaces this kernel for the two X contractions in the
+// default precision mode.
 //
 // Shared-memory tiles are padded so that the 8-byte fragment loads of a half-warp hit 16 distinct
 // bank pairs:  K-contiguous tiles use a row stride of 20 doubles, M/N-contiguous tiles a stride

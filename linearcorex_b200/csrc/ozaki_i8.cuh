@@ -4,22 +4,24 @@
 //   D = X~^T Y      (linearcorex.py:259 / :211)      MN-major x MN-major  operands
 //
 // tcgen05.mma has no f64 kind, but kind::i8 multiplies int8 digits exactly into int32 TMEM accumulators.
-// Each fp64 operand is written as a fixed-point number with S signed 7-bit digits ("slices"):
-//     v = 2^E * sum_{k=1..S} d_k 2^(-7k),   d_k in [-64, 64]
+// Each fp64 operand is written as a fixed-point number with S signed int8 digits ("planes") in radix R = 254:
+//     v = 2^E * sum_{k=1..S} d_k R^-k,   |d_k| <= 127          (R = 128, |d_k| <= 64, is the power-of-two variant)
 // with one exponent E for all of X~ (standardised data is bounded; chosen from max|X~|), one per factor
 // row of A and one per factor column of Y.  The product is then
-//     sum_i x_i a_i = 2^(Ex+Ea) * sum_{g=2..S+1} 2^(-7g) * P_g,   P_g = sum_{k+l=g} sum_i dx_k[i] da_l[i]
-// where every P_g is an exact int32 dot product (|d d'| <= 2^12, so 2^19 terms fit).  Pairs with k+l > S+1
-// are dropped (they sit below the digits that were truncated anyway).  S = 6 keeps 42 bits below the row/
-// column maximum -- the FP64-faithful mode, validated against FP64 at 1e-9 on every parity case; S = 3 is
-// the opt-in fast mode (21 bits, fp32-equivalent like 3xTF32 but at 3 bytes/element and int8 rates).
+//     sum_i x_i a_i = 2^(Ex+Ea) * sum_{g=2..S+1} R^-g * P_g,   P_g = sum_{k+l=g} sum_i dx_k[i] da_l[i]
+// where every P_g is an exact int32 dot product (|d d'| < 2^14; the host caps the contraction length seen by one
+// accumulator at 2^31 / (127^2 S) through split-K).  Pairs with k+l > S+1 are dropped (they sit below the digits that were
+// truncated anyway).  S = 6 keeps 48 bits below the row / column maximum -- truncation at the level of binary64
+// rounding, the FP64-faithful mode (measured parity 1e-11 or better on full fits); S = 5 keeps 40 bits; S = 3 is the
+// opt-in fast mode (24 bits: fp32-equivalent like 3xTF32, at 3 bytes per element and int8 rates).
 //
-// One CTA owns a 128 x 64 output tile and S accumulators of 64 TMEM columns (group g at column 64 (g-2)).
-// Warp 0 streams operand slices with TMA (cp.async.bulk.tensor, 64 B / 128 B swizzle) through a 3-stage
-// mbarrier ring; warp 1 issues the S(S+1)/2 tcgen05.mma per 32-deep K step and commits to the ring;
-// warps 2-5 drain TMEM (tcgen05.ld), recombine the groups in fp64 (Horner from the smallest weight) and
-// store.  The same row-major int8 image of X~ feeds both contractions: K-major as the M operand of the
-// first, MN-major as the N operand of the second, so X~ is stored once (S bytes per element, less than fp64).
+// One CTA owns a 128 x bn output tile (bn = 64, or narrower for the last factor tile) and S accumulators of bn TMEM
+// columns (group g at column bn g).  Warp 0 streams operand planes with TMA (cp.async.bulk.tensor, 64 B / 128 B
+// swizzle; the M-side planes are multicast across a cluster of 2 or 4 CTAs) through a 3-stage mbarrier ring; warp 1
+// issues the tcgen05.mma (digit k of A against digits 0..S-1-k of B as ONE wide instruction) and commits to the ring;
+// warps 2-5 drain TMEM (tcgen05.ld), recombine the groups in fp64 (Horner from the smallest weight) and store.  The
+// same row-major int8 image of X~ feeds both contractions: K-major as the M operand of the first, MN-major as the N
+// operand of the second, so X~ is stored once (S bytes per element, less than fp64).
 #pragma once
 #include <cuda.h>
 
