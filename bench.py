@@ -154,6 +154,11 @@ def time_reference_cpu(n_total, n_vars, n_factors, steps, warmup, flop_budget):
     Per-iteration cost is linear in N apart from the O(m n) / O(m^2 n) terms (<1 % here), SURVEY.md 8(d)."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import corex_oracle as oc
+    try:  # torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU arm must use every host core
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=os.cpu_count() or 1)
+    except Exception:
+        pass
     per_row = 11.0 * n_vars * n_factors  # ~ (4 + 4t) N n m flops per iteration at t ~ 1.7 trials
     rows = int(min(n_total, max(512, flop_budget / (per_row * (steps + warmup)))))
     x = make_rows(n_total, n_vars, n_factors, 0, rows).astype(np.float64)
