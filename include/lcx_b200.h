@@ -130,7 +130,8 @@ int lcx_bind(lcx_session* s, const double* xt, long long n_rows_local, long long
              long long ldx, int n_factors, double* workspace, long long workspace_doubles);
 /* Streamed binding for data whose fp64 X~ does not fit beside its digit planes (split modes only): call lcx_bind with
  * xt == NULL, then lcx_set_x_scale(max |X~|) once and lcx_slice_block for every row block [row0, row0 + rows) of X~
- * (any order, each row exactly once) before the first fit step. */
+ * (any order, each row exactly once) before the first fit step.  A NaN or infinite max_abs (non-finite data) sets a NaN
+ * scale: every product then comes out NaN, which is what the reference's float64 path does with such data. */
 int lcx_set_x_scale(lcx_session* s, double max_abs);
 int lcx_slice_block(lcx_session* s, const double* xt, long long row0, long long rows, long long ldx);
 /* Split modes: location of the int8 digit planes ([digits][rows][ld_bytes], offset in doubles from the workspace base) of

@@ -504,7 +504,7 @@ class Corex(object):
         self.theta = (mean.cpu().numpy().copy(), sd.cpu().numpy().copy())
         self.n_obs = cnt.cpu().numpy().astype(np.int64) if has_marker else int(n_total)
         zmax = float((maxdev / sd).max().item())
-        if self.gaussianize == 'outliers':
+        if self.gaussianize == 'outliers' and np.isfinite(zmax):
             zmax = min(zmax, 4.0) + float(np.tanh(max(zmax - 4.0, 0.0)))  # g() is monotone (:483-487)
         self.n_samples = int(n_total)
         self.timings["preprocess_s"] = time.perf_counter() - t0

@@ -46,6 +46,14 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 
+// |v| folded into a running maximum.  A NaN or an infinity turns the maximum into +inf and it stays there (fmax keeps
+// +inf), so non-finite input poisons the scale derived from the maximum -- and through it every output -- the way it
+// poisons numpy's float64 products in the reference, instead of being skipped by fmax's NaN rule.
+__device__ __forceinline__ double amax_acc(double mx, double v) {
+    const double a = fabs(v);
+    return (a <= 1.7976931348623157e308) ? fmax(mx, a) : __longlong_as_double(0x7ff0000000000000LL);
+}
+
 __device__ __forceinline__ double warp_max(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));

@@ -3,6 +3,7 @@
 // corex_kernels.cuh and preprocess_kernels.cuh.
 #include "../../include/lcx_b200.h"
 
+#include <float.h>
 #include <math.h>
 
 #include "common.cuh"
@@ -570,10 +571,12 @@ extern "C" int lcx_bind(lcx_session* s, const double* xt, long long n_rows_local
 extern "C" int lcx_set_x_scale(lcx_session* s, double max_abs) {
     S_REQUIRE_BOUND(s);
     LCX_REQUIRE(s->L.S > 0, "only meaningful in the split modes");
-    LCX_REQUIRE(max_abs >= 0.0 && max_abs == max_abs, "max_abs must be a finite non-negative bound on |X~|");
+    LCX_REQUIRE(!(max_abs < 0.0), "max_abs must be a non-negative bound on |X~|");
     int e = 0;
     double scale = 1.0;
-    if (max_abs > 0.0) {
+    if (!(max_abs <= DBL_MAX)) {
+        scale = NAN;  // non-finite data: every product comes out NaN, as in the reference's float64 path
+    } else if (max_abs > 0.0) {
         frexp(max_abs, &e);
         scale = ldexp(1.0, e + 1);
     }

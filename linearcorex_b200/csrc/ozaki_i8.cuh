@@ -372,7 +372,8 @@ __device__ __forceinline__ void split_digits(double x, double inv_scale, double 
 
 // Power-of-two scale 2^E with max * 2^-E < 0.5 (so the first digit stays within [-64, 64]).
 __device__ __forceinline__ double pow2_above(double amax) {
-    if (!(amax > 0.0) || !isfinite(amax)) return 1.0;
+    if (!(amax <= 1.7976931348623157e308)) return __longlong_as_double(0x7ff8000000000000LL);  // non-finite data: NaN out
+    if (!(amax > 0.0)) return 1.0;
     int e;
     frexp(amax, &e);       // amax = f * 2^e, f in [0.5, 1)
     return ldexp(1.0, e + 1);
@@ -430,7 +431,7 @@ __global__ void row_scale_kernel(const double* __restrict__ a, long long ld, int
     __shared__ double scratch[8];
     const double* ra = a + (long long)blockIdx.x * ld;
     double mx = 0.0;
-    for (int i = threadIdx.x; i < cols; i += 256) mx = fmax(mx, fabs(ra[i]));
+    for (int i = threadIdx.x; i < cols; i += 256) mx = lcx::amax_acc(mx, ra[i]);
     mx = block_max_256(mx, scratch);
     if (threadIdx.x == 0) scale[blockIdx.x] = pow2_above(mx);
 }
@@ -446,7 +447,7 @@ __global__ void __launch_bounds__(256) y_stats_kernel(const double* __restrict__
     if (c < cols) {
         for (long long r = r0 + threadIdx.y; r < r1; r += 8) {
             const double v = y[r * ldy + c];
-            mx = fmax(mx, fabs(v));
+            mx = lcx::amax_acc(mx, v);
             sq += v * v;
         }
     }
@@ -502,7 +503,7 @@ __global__ void __launch_bounds__(256) absmax_partial_kernel(const double* __res
     double mx = 0.0;
     for (long long r = blockIdx.x; r < rows; r += gridDim.x) {
         const double* xr = x + r * ld;
-        for (int c = threadIdx.x; c < cols; c += 256) mx = fmax(mx, fabs(xr[c]));
+        for (int c = threadIdx.x; c < cols; c += 256) mx = lcx::amax_acc(mx, xr[c]);
     }
     mx = block_max_256(mx, scratch);
     if (threadIdx.x == 0) part[blockIdx.x] = mx;

@@ -66,7 +66,7 @@ __global__ void __launch_bounds__(256) colstats_sqdev_kernel(const T* __restrict
             if (!is_missing(v, has_marker, marker, marker_is_nan)) {
                 const double d = (double)v - mu;
                 s += d * d;
-                mx = fmax(mx, fabs(d));
+                mx = amax_acc(mx, d);
             }
         }
     }
