@@ -135,8 +135,9 @@ int lcx_bind(lcx_session* s, const double* xt, long long n_rows_local, long long
 int lcx_set_x_scale(lcx_session* s, double max_abs);
 int lcx_slice_block(lcx_session* s, const double* xt, long long row0, long long rows, long long ldx);
 /* Split modes: location of the int8 digit planes ([digits][rows][ld_bytes], offset in doubles from the workspace base) of
- * which = 0: X~, 1: the last small operand A (W or grad), 2: Y; and of their scales (1 value for X~, one per factor
- * otherwise).  For inspection and the bit-exact digit tests. */
+ * which = 0: X~ (rows = local samples, cols = variables), 1: the last small operand A (W or grad; rows = factors,
+ * cols = variables), 2: Y, stored transposed (rows = factors, cols = local samples); and of their scales (1 value for
+ * X~, one per factor otherwise).  For inspection and the bit-exact digit tests. */
 int lcx_digit_planes_info(lcx_session* s, int which, long long* offset, int* digits, long long* rows, long long* cols,
                           long long* ld_bytes, long long* scale_offset, int* radix);
 /* Offset (in doubles, from the workspace base), rows, cols and leading dimension of an array. */

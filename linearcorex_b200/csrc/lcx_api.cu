@@ -54,7 +54,7 @@ enum {
     I_STATUS,           // 2 doubles (int status of the inverse)
     I_XS,               // split modes: int8 digit slices of X~   [S][N_local][ld8]
     I_AS,               //              int8 digit slices of A    [S][m][ld8]
-    I_YS,               //              int8 digit slices of Y    [S][N_local][ldy8]
+    I_YS,               //              int8 digit slices of Y, transposed  [S][m][ldk8]
     I_OZV,              //              scales: x(16) | a(ldm) | c(ldm) | y(ldm) | d(ldm)
     I_YSTAT,            //              per-slab column max / sum of squares of Y
     I_AMAX,             //              per-CTA partial max |X~|
@@ -73,7 +73,7 @@ struct Layout {
     int nstrips;
     // split-integer modes (ozaki_i8.cuh)
     int S;                       // digits per operand, 0 = DMMA mode
-    long long ld8, ldy8;         // byte leading dimensions of the X~/A and Y slices
+    long long ld8, ldk8;         // byte leading dimensions of the X~/A slices and of the transposed Y slices (samples)
     int oz_splits, oz_chunk;     // split-K of the second contraction (over samples)
     int oz1_splits, oz1_chunk;   // split-K of the first contraction (over variables), only when row tiles are scarce
     int ystat_slabs;
@@ -179,10 +179,10 @@ static Layout make_layout(long long Nl, int n, int m, int precision) {
     put1(I_YSTAT, (long long)L.ystat_slabs * 2, m, L.ldm);
     if (L.S > 0) {
         L.ld8 = round_up(n, 128);
-        L.ldy8 = round_up(m, 128);
-        // second contraction: 128 x 64 tiles over (factors x variables), split over samples to fill whole waves;
-        // at most 65536 samples per split keeps every int32 accumulator exact (<= 6 * 2^16 * 2^12 < 2^31)
-        const long long tiles = (long long)cdiv(n, oz::kBN) * cdiv(m, oz::kBM);
+        L.ldk8 = round_up(Nl, 128);
+        // second contraction: 128 x 64 tiles over (variables x factors), split over samples to fill whole waves;
+        // at most oz_kmax samples per split keeps every int32 accumulator exact
+        const long long tiles = (long long)cdiv(n, oz::kBM) * cdiv(m, oz::kBN);
         const int kblocks = cdiv(Nl, oz::kBK);
         // time model in units of one 64-deep K block: waves x (K blocks per CTA + fixed prologue/TMEM-drain/store cost
         // of ~16 blocks) + the partial-buffer round trip; measured at 12.5k and 100k rows per GPU
@@ -218,7 +218,7 @@ static Layout make_layout(long long Nl, int n, int m, int precision) {
         }
         const long long xs8 = ((long long)L.S * Nl * L.ld8 + 7) / 8;   // int8 planes counted in doubles (64-bit sizes:
         const long long as8 = ((long long)L.S * mn * L.ld8 + 7) / 8;   // the target shape has 1.5e10 doubles of planes)
-        const long long ys8 = ((long long)L.S * Nl * L.ldy8 + 7) / 8;
+        const long long ys8 = ((long long)L.S * mn * L.ldk8 + 7) / 8;
         put1(I_XS, 1, xs8, xs8);
         put1(I_AS, 1, as8, as8);
         put1(I_YS, 1, ys8, ys8);
@@ -253,7 +253,7 @@ struct lcx_session {
     far::Peers peers;
     unsigned long long ar_calls;
     // split-integer modes: TMA descriptors over the digit slices
-    CUtensorMap map_x_k1, map_a_k1, map_a_k1_tail, map_y_k2, map_x_k2;
+    CUtensorMap map_x_k1, map_a_k1, map_a_k1_tail, map_x_k2, map_y_k2, map_y_k2_tail;
     int oz_bn_tail;   // width of the last factor tile of the first contraction (multiple of 16)
     int8_t* xs() const { return (int8_t*)(ws + L.slot[I_XS][0].off); }
     int8_t* as() const { return (int8_t*)(ws + L.slot[I_AS][0].off); }
@@ -435,15 +435,18 @@ static int oz_prepare(lcx_session* s, bool streamed) {
         case 6: LCX_TRY(oz_slice_x_t<6>(s)); break;
         default: return fail(LCX_ERR_STATE, "oz_prepare", "bad digit count");
     }
-    // X~ slices as the M operand of Y = X~ A^T (K-major: inner = variables) and as the N operand of D = X~^T Y
-    // (MN-major: inner = variables, rows = samples); A slices K-major; Y slices MN-major (inner = factors).
+    // X~ slices as the M operand of Y = X~ A^T (K-major: inner = variables, 64 B boxes) and as the M operand of
+    // D = X~^T Y (MN-major: inner = variables, 128 B boxes over 64 sample rows); the factor-side operands are K-major:
+    // A slices (inner = variables) and the transposed Y slices (inner = samples).
     LCX_TRY(oz::make_slice_map(&s->map_x_k1, s->xs(), s->n, s->Nl, L.S, L.ld8, s->Nl * L.ld8, oz::kBK, oz::kBM, false));
     LCX_TRY(oz::make_slice_map(&s->map_a_k1, s->as(), s->n, s->m, L.S, L.ld8, (long long)s->m * L.ld8, oz::kBK, oz::kBN, false));
     s->oz_bn_tail = (int)round_up(s->m - (cdiv(s->m, oz::kBN) - 1) * oz::kBN, 16);
     LCX_TRY(oz::make_slice_map(&s->map_a_k1_tail, s->as(), s->n, s->m, L.S, L.ld8, (long long)s->m * L.ld8, oz::kBK, s->oz_bn_tail,
                                false));
-    LCX_TRY(oz::make_slice_map(&s->map_y_k2, s->ys(), L.ldy8, s->Nl, L.S, L.ldy8, s->Nl * L.ldy8, oz::kBM, oz::kBK, true));
-    LCX_TRY(oz::make_slice_map(&s->map_x_k2, s->xs(), s->n, s->Nl, L.S, L.ld8, s->Nl * L.ld8, oz::kBN, oz::kBK, false));
+    LCX_TRY(oz::make_slice_map(&s->map_x_k2, s->xs(), s->n, s->Nl, L.S, L.ld8, s->Nl * L.ld8, oz::kBM, oz::kBK, true));
+    LCX_TRY(oz::make_slice_map(&s->map_y_k2, s->ys(), s->Nl, s->m, L.S, L.ldk8, (long long)s->m * L.ldk8, oz::kBK, oz::kBN, false));
+    LCX_TRY(oz::make_slice_map(&s->map_y_k2_tail, s->ys(), s->Nl, s->m, L.S, L.ldk8, (long long)s->m * L.ldk8, oz::kBK,
+                               s->oz_bn_tail, false));
     return 0;
 }
 
@@ -497,21 +500,23 @@ static int oz_pair_t(lcx_session* s, const double* A, double* svec, cudaEvent_t*
         LCX_CUDA(cudaGetLastError());
         return 0;
     }
-    oz::slice_cols_kernel<S><<<dim3((unsigned)cdiv(s->Nl, 8), cdiv(L.ldy8, 4 * 32)), dim3(32, 8), 0, s->stream>>>(
-        Y, L.ldy, s->Nl, m, s->oz_yscale(), s->ys(), L.ldy8, s->Nl * L.ldy8, (double)L.radix);
+    oz::slice_cols_t_kernel<S><<<dim3((unsigned)cdiv(s->Nl, 128), cdiv(m, 32)), dim3(32, 8), 0, s->stream>>>(
+        Y, L.ldy, s->Nl, m, s->oz_yscale(), s->ys(), L.ldk8, (long long)m * L.ldk8, (double)L.radix);
     LAUNCHED(s);
-    // ---- D = (X~^T Y)^T, factor-major, split over samples ----
+    // ---- D = (X~^T Y)^T: tiles of 128 variables x 64 factors, stored factor-major, split over samples ----
     {
         oz::GemmParams p;
         memset(&p, 0, sizeof(p));
         const bool split = L.oz_splits > 1;
         p.C = split ? s->ptr(I_PART) : D;
         p.ldc = L.ld; p.c_split_stride = split ? (long long)m * L.ld : 0;
-        p.row_scale = s->oz_dscale();
+        p.col_scale = s->oz_dscale();
         p.inv_radix = 1.0 / (double)L.radix;
-        p.rows = m; p.cols = n; p.k_total = (int)s->Nl; p.k_chunk = L.oz_chunk;
-        LCX_TRY((oz::launch_oz_gemm<S, false>(s->map_y_k2, s->map_x_k2, s->map_x_k2, p,
-                                              dim3(cdiv(n, oz::kBN), cdiv(m, oz::kBM), L.oz_splits), s->stream, oz_cluster())));
+        p.rows = n; p.cols = m; p.k_total = (int)s->Nl; p.k_chunk = L.oz_chunk;
+        p.bn_tail = s->oz_bn_tail;
+        p.trans_out = 1;
+        LCX_TRY((oz::launch_oz_gemm<S, false>(s->map_x_k2, s->map_y_k2, s->map_y_k2_tail, p,
+                                              dim3(cdiv(m, oz::kBN), cdiv(n, oz::kBM), L.oz_splits), s->stream, oz_cluster())));
         LAUNCHED(s);
         LCX_TRY(combine_and_allreduce(s, split ? s->ptr(I_PART) : D, split ? L.oz_splits : 1, (long long)m * L.ld, m, n, L.ld, D, svec,
                                       want_tail ? m : 0));
@@ -632,9 +637,9 @@ extern "C" int lcx_digit_planes_info(lcx_session* s, int which, long long* offse
     const int slot = which == 0 ? I_XS : (which == 1 ? I_AS : I_YS);
     if (offset) *offset = L.slot[slot][0].off;
     if (digits) *digits = L.S;
-    if (rows) *rows = which == 1 ? s->m : s->Nl;
-    if (cols) *cols = which == 2 ? s->m : s->n;
-    if (ld_bytes) *ld_bytes = which == 2 ? L.ldy8 : L.ld8;
+    if (rows) *rows = which == 0 ? s->Nl : s->m;          // the Y planes are stored transposed: [factor][sample]
+    if (cols) *cols = which == 2 ? s->Nl : s->n;
+    if (ld_bytes) *ld_bytes = which == 2 ? L.ldk8 : L.ld8;
     if (scale_offset) *scale_offset = L.slot[I_OZV][0].off + (which == 0 ? 0 : (which == 1 ? 16 : 16 + 2 * L.ldm));
     if (radix) *radix = L.radix;
     return 0;

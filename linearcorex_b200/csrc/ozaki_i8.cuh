@@ -1,7 +1,7 @@
 // Split-integer ("Ozaki") emulation of the two FP64 X contractions on the 5th-generation tensor cores.
 //
-//   Y = X~ A^T      (linearcorex.py:247 / :210)      K-major  x K-major   operands
-//   D = X~^T Y      (linearcorex.py:259 / :211)      MN-major x MN-major  operands
+//   Y = X~ A^T      (linearcorex.py:247 / :210)      M = samples,   X~ K-major;   N = factors, A planes K-major
+//   D = X~^T Y      (linearcorex.py:259 / :211)      M = variables, X~ MN-major;  N = factors, Y^T planes K-major
 //
 // tcgen05.mma has no f64 kind, but kind::i8 multiplies int8 digits exactly into int32 TMEM accumulators.
 // Each fp64 operand is written as a fixed-point number with S signed int8 digits ("planes") in radix R = 254:
@@ -20,8 +20,10 @@
 // swizzle; the M-side planes are multicast across a cluster of 2 or 4 CTAs) through a 3-stage mbarrier ring; warp 1
 // issues the tcgen05.mma (digit k of A against digits 0..S-1-k of B as ONE wide instruction) and commits to the ring;
 // warps 2-5 drain TMEM (tcgen05.ld), recombine the groups in fp64 (Horner from the smallest weight) and store.  The
-// same row-major int8 image of X~ feeds both contractions: K-major as the M operand of the first, MN-major as the N
-// operand of the second, so X~ is stored once (S bytes per element, less than fp64).
+// same row-major int8 image of X~ feeds both contractions as their M operand: K-major in the first, MN-major in the
+// second (128 samples or 128 variables per tile: no padded rows either way), so X~ is stored once (S bytes per element,
+// less than fp64).  The factor-side operand is K-major in both (A planes [S][m][n]; Y planes stored transposed,
+// [S][m][N_local]), which is what lets its digit planes sit back to back in shared memory for the wide instructions.
 #pragma once
 #include <cuda.h>
 
@@ -149,14 +151,15 @@ struct GemmParams {
     int k_chunk;                 // contraction range per blockIdx.z (multiple of kBK)
     double inv_radix;            // 1 / R: group g carries weight R^-(g+2)
     int n_tiles;                 // number of real N tiles (gridDim.x may be padded up to a multiple of the cluster size)
-    int bn_tail;                 // K-major only: width (multiple of 16, <= 64) of the LAST N tile, loaded through mapBt;
+    int bn_tail;                 // width (multiple of 16, <= 64) of the LAST N tile, loaded through mapBt;
                                  // 0 or 64 = full width.  m = 100 factors -> tiles of 64 + 48 instead of 64 + 64
+    int trans_out;               // 1: store C[col][row] (the second contraction writes (X~^T Y)^T factor-major)
 };
 
-// KMAJOR = true : A tile = [128 rows][64 B of K]  (SW64), B tile = [64 rows][64 B of K]  (SW64); tensor maps are
-//                 (K, rows, slice); TMA coordinates (k0, row0, s).
-// KMAJOR = false: A tile = [64 K rows][128 B of M] (SW128), B tile = [64 K rows][64 B of N] (SW64); tensor maps are
-//                 (M or N, K rows, slice); TMA coordinates (m0 or n0, k0, s).
+// The N-side (factor) operand is always K-major: B tile = [64 rows][64 B of K] (SW64), tensor map (K, rows, slice),
+// TMA coordinates (k0, n0, s).  The M-side operand is
+// KMAJOR = true : A tile = [128 rows][64 B of K]   (SW64),  tensor map (K, rows, slice),      coordinates (k0, m0, s);
+// KMAJOR = false: A tile = [64 K rows][128 B of M] (SW128), tensor map (M, K rows, slice),    coordinates (m0, k0, s).
 // All MMAs of one 64-deep K block for a tile of compile-time width BN (multiple of 16, <= 64).
 template <int S, bool KMAJOR, int BN>
 __device__ __forceinline__ void issue_kblock(uint32_t sa, uint32_t sb, uint32_t tmem_base, bool first_block) {
@@ -170,20 +173,13 @@ __device__ __forceinline__ void issue_kblock(uint32_t sa, uint32_t sb, uint32_t 
 #pragma unroll
             for (int q0 = 0; q0 < S - ka; q0 += CMAX) {
                 const int cnt = (S - ka - q0) < CMAX ? (S - ka - q0) : CMAX;
-                const uint32_t idesc = make_idesc_i8(kBM, BN * cnt, KMAJOR ? 0 : 1, KMAJOR ? 0 : 1);
-                uint64_t da, db;
-                if (KMAJOR) {
-                    // rows at 64 B pitch, 8-row swizzle atoms of 512 B (SBO); a K step is +32 B inside the span; the next
-                    // B plane starts BN/8 atoms further, i.e. N simply continues.
-                    da = make_smem_desc(sa + ka * A_BYTES + kk * 32, 16, 512, 4);
-                    db = make_smem_desc(sb + q0 * B_BYTES + kk * 32, 16, 512, 4);
-                } else {
-                    // A: K rows of 128 B (SW128, atoms of 8 rows = 1 KB); a K step is 32 rows = 4 KB
-                    // B: K rows of 64 B  (SW64,  atoms of 8 rows = 512 B); a K step is 32 rows = 2 KB;
-                    //    the next 64 columns of N are the next digit plane, 4 KB further (LBO).
-                    da = make_smem_desc(sa + ka * A_BYTES + kk * 4096, 8192, 1024, 2);
-                    db = make_smem_desc(sb + q0 * B_BYTES + kk * 2048, 4096, 512, 4);
-                }
+                const uint32_t idesc = make_idesc_i8(kBM, BN * cnt, KMAJOR ? 0 : 1, 0);
+                // K-major: rows at 64 B pitch, 8-row swizzle atoms of 512 B (SBO); a K step is +32 B inside the span; the
+                // next B plane starts BN/8 atoms further, i.e. N simply continues.
+                // MN-major A: K rows of 128 B (SW128, atoms of 8 rows = 1 KB); a K step is 32 rows = 4 KB.
+                const uint64_t da = KMAJOR ? make_smem_desc(sa + ka * A_BYTES + kk * 32, 16, 512, 4)
+                                           : make_smem_desc(sa + ka * A_BYTES + kk * 4096, 8192, 1024, 2);
+                const uint64_t db = make_smem_desc(sb + q0 * B_BYTES + kk * 32, 16, 512, 4);
                 const uint32_t acc = (!first_block || kk > 0 || ka > 0) ? 1u : 0u;
                 umma_i8(tmem_base + (uint32_t)((ka + q0) * BN), da, db, idesc, acc);
             }
@@ -192,7 +188,7 @@ __device__ __forceinline__ void issue_kblock(uint32_t sa, uint32_t sb, uint32_t 
 }
 
 // CL = thread-block cluster size along the N tiles (1, 2 or 4).  The CL CTAs of a cluster share the M-side operand
-// (X~ planes in the first contraction, Y planes in the second): each CTA fetches S/CL of its digit planes and TMA
+// (the X~ planes, in both contractions): each CTA fetches S/CL of its digit planes and TMA
 // multicasts them into every CTA of the cluster, which divides the L2 -> SM traffic of that operand by CL (the kernel
 // ran at the L2 throughput cap without it: 18 GB per launch at config 3).  A stage is released to the producers only
 // when every CTA of the cluster has finished reading it (multicast tcgen05.commit on all empty barriers).
@@ -218,9 +214,9 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     const int kbeg = blockIdx.z * p.k_chunk;
     const int kend = min(p.k_total, kbeg + p.k_chunk);
     const int num_kb = (kend > kbeg) ? (kend - kbeg + kBK - 1) / kBK : 0;
-    // width of this CTA's N tile: the last tile of the K-major contraction may be narrower (fewer padded factor columns
+    // width of this CTA's N tile: the last factor tile may be narrower (fewer padded factor columns
     // = proportionally fewer tensor cycles and operand bytes); digit planes of B are then packed at bn * 64 bytes
-    const bool tail = KMAJOR && p.bn_tail > 0 && p.bn_tail < kBN && n_tile == p.n_tiles - 1;
+    const bool tail = p.bn_tail > 0 && p.bn_tail < kBN && n_tile == p.n_tiles - 1;
     const uint32_t crank = (CL > 1) ? cluster_ctarank() : 0u;
     constexpr uint16_t kMask = (uint16_t)((1u << CL) - 1u);
     const int bn = tail ? p.bn_tail : kBN;
@@ -265,8 +261,7 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                         if (KMAJOR) tma_load_3d_mc(sa + s * A_BYTES, &mapA, &full_bar[st], k0, m_tile * kBM, s, kMask);
                         else tma_load_3d_mc(sa + s * A_BYTES, &mapA, &full_bar[st], m_tile * kBM, k0, s, kMask);
                     }
-                    if (KMAJOR) tma_load_3d(sb + s * b_bytes, tail ? &mapBt : &mapB, &full_bar[st], k0, n_tile * kBN, s);
-                    else tma_load_3d(sb + s * B_BYTES, &mapB, &full_bar[st], n_tile * kBN, k0, s);
+                    tma_load_3d(sb + s * b_bytes, tail ? &mapBt : &mapB, &full_bar[st], k0, n_tile * kBN, s);
                 }
             }
         }
@@ -336,7 +331,10 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                         if (col < p.cols) v0 *= p.col_scale[col];
                         if (col + 1 < p.cols) v1 *= p.col_scale[col + 1];
                     }
-                    if (col + 1 < p.cols) {
+                    if (p.trans_out) {  // a warp's 32 rows are 32 consecutive doubles of one output row: coalesced
+                        if (col < p.cols) C[(long long)col * p.ldc + row] = v0;
+                        if (col + 1 < p.cols) C[(long long)(col + 1) * p.ldc + row] = v1;
+                    } else if (col + 1 < p.cols) {
                         *reinterpret_cast<double2*>(C + (long long)row * p.ldc + col) = make_double2(v0, v1);
                     } else if (col < p.cols) {
                         C[(long long)row * p.ldc + col] = v0;
@@ -403,26 +401,41 @@ __global__ void slice_rows_kernel(const double* __restrict__ in, long long ld_in
     }
 }
 
-// Same with one scale per column (Y for the second contraction: exponent per factor).
+// Digit planes of Y (N x ldy, row-major fp64) with one scale per column (exponent per factor), written TRANSPOSED:
+// out[s][c][r], samples contiguous -- the K-major factor-side operand of the second contraction.  One CTA of 32 x 8
+// threads turns a 128-row x 32-column block of Y around through shared memory (coalesced 256 B reads of Y, 128 B
+// writes per digit plane and factor).
 template <int S>
-__global__ void slice_cols_kernel(const double* __restrict__ in, long long ld_in, long long rows, int cols,
-                                  const double* __restrict__ col_scale, int8_t* __restrict__ out, long long ld_out,
-                                  long long slice_stride, double radix) {
-    const long long r = (long long)blockIdx.x * blockDim.y + threadIdx.y;
-    const int c4 = (blockIdx.y * blockDim.x + threadIdx.x) * 4;
-    if (r >= rows || c4 >= ld_out) return;
-    int8_t d[4][S];
+__global__ void __launch_bounds__(256) slice_cols_t_kernel(const double* __restrict__ in, long long ld_in, long long rows,
+                                                           int cols, const double* __restrict__ col_scale,
+                                                           int8_t* __restrict__ out, long long ld_out, long long slice_stride,
+                                                           double radix) {
+    constexpr int PITCH = 132;  // 33 words: the 32 columns of one row land in different banks
+    __shared__ __align__(4) int8_t t[S][32][PITCH];
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const long long r0 = (long long)blockIdx.x * 128;
+    const int c0 = blockIdx.y * 32;
+    const int c = c0 + tx;
+    const double inv = (c < cols) ? 1.0 / col_scale[c] : 1.0;
+#pragma unroll 4
+    for (int i = 0; i < 16; ++i) {
+        const int rr = ty + 8 * i;
+        const long long r = r0 + rr;
+        const double x = (c < cols && r < rows) ? in[r * ld_in + c] : 0.0;
+        int8_t d[S];
+        split_digits<S>(x, inv, radix, d);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const int c = c4 + j;
-        const double x = (c < cols) ? in[r * ld_in + c] : 0.0;
-        const double inv = (c < cols) ? 1.0 / col_scale[c] : 1.0;
-        split_digits<S>(x, inv, radix, d[j]);
+        for (int k = 0; k < S; ++k) t[k][tx][rr] = d[k];
     }
-#pragma unroll
-    for (int k = 0; k < S; ++k) {
-        char4 v = make_char4(d[0][k], d[1][k], d[2][k], d[3][k]);
-        *reinterpret_cast<char4*>(out + (long long)k * slice_stride + r * ld_out + c4) = v;
+    __syncthreads();
+    const int tid = ty * 32 + tx;
+    const int w = tid & 31;        // 4-byte word of the 128-byte row
+    if (r0 + 4 * w >= ld_out) return;
+    for (int idx = tid >> 5; idx < S * 32; idx += 8) {
+        const int k = idx >> 5, cc = idx & 31;
+        if (c0 + cc < cols)
+            *reinterpret_cast<uint32_t*>(out + (long long)k * slice_stride + (long long)(c0 + cc) * ld_out + r0 + 4 * w) =
+                *reinterpret_cast<const uint32_t*>(&t[k][cc][4 * w]);
     }
 }
 

@@ -183,7 +183,7 @@ def test_digit_planes_bit_exact_against_numpy(precision):
     y_dev = sess.view(L.A_Y).cpu().numpy()
     np.testing.assert_array_equal(sy, [pow2_above(np.abs(c).max()) for c in y_dev.T])
     for k, want in enumerate(split_digits(y_dev, sy[None, :], S, R)):
-        np.testing.assert_array_equal(py[k], want)
+        np.testing.assert_array_equal(py[k].T, want)  # the Y planes are stored factor-major (K-major for the 2nd contraction)
     # Y itself = the exact integer group sums recombined by the same Horner steps
     groups = [np.zeros((N, m), dtype=np.int64) for _ in range(S)]
     for k in range(S):
@@ -195,4 +195,16 @@ def test_digit_planes_bit_exact_against_numpy(precision):
     want_y = acc * ((1.0 / R) * (1.0 / R)) * (sx[0] * sa)[None, :]
     # (binary64 recombination: the device may fuse the multiply-adds, so this part is held to a few ulps of the column scale)
     assert np.all(np.abs(y_dev - want_y) <= 1e-14 * np.abs(want_y).max(axis=0))
+    # second contraction: D = (X~^T Y)^T from the exact integer group sums of the X~ and Y digits
+    groups = [np.zeros((m, n), dtype=np.int64) for _ in range(S)]
+    for k in range(S):
+        for l in range(S - k):
+            groups[k + l] += py[k] @ px[l]
+    acc = groups[S - 1].astype(np.float64)
+    for g in range(S - 2, -1, -1):
+        acc = acc * (1.0 / R) + groups[g]
+    want_d = acc * ((1.0 / R) * (1.0 / R)) * (sx[0] * sy)[:, None]
+    d_dev = sess.view(L.A_D).cpu().numpy()
+    # (split over samples: the per-split Horner sums are added in binary64, hence a few ulps of the row scale)
+    assert np.all(np.abs(d_dev - want_d) <= 1e-13 * np.abs(want_d).max(axis=1, keepdims=True))
     sess.close()
