@@ -196,6 +196,10 @@ static Layout make_layout(long long Nl, int n, int m, int precision) {
             const double cost = (double)waves * (kb + 16.0) + (sp > 1 ? 1.5 * sp : 0.0);
             if (cost < best_cost - 1e-9) { best_cost = cost; best = sp; }
         }
+        if (const char* env = getenv("LCX_OZ_SPLITS")) {  // experiment override; never below the int32-exact minimum
+            const int v = atoi(env);
+            if (v >= smin && v <= kblocks) best = v;
+        }
         L.oz_chunk = (int)round_up(cdiv(Nl, best), oz::kBK);
         L.oz_splits = cdiv(Nl, L.oz_chunk);
         {   // first contraction: same cost model over its (row tile x factor tile) grid
