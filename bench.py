@@ -118,6 +118,10 @@ class ClockSampler(object):
             self.nv = pynvml
             self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
             self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            # first queries outside the timed region: NVML's first call per handle can take ~0.1 s, and it holds a
+            # driver lock that stalls kernel launches of this process for that long
+            pynvml.nvmlDeviceGetClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
         except Exception:
             self.nv = None
 
