@@ -208,3 +208,38 @@ def test_digit_planes_bit_exact_against_numpy(precision):
     # (split over samples: the per-split Horner sums are added in binary64, hence a few ulps of the row scale)
     assert np.all(np.abs(d_dev - want_d) <= 1e-13 * np.abs(want_d).max(axis=1, keepdims=True))
     sess.close()
+
+
+SIG_SHAPES = [(1, 1, 1), (63, 5, 1), (64, 127, 16), (65, 128, 17), (200, 129, 48), (700, 1000, 64), (513, 333, 65),
+              (1000, 257, 100), (129, 64, 112), (300, 2049, 128), (4100, 130, 130), (2500, 70, 200)]
+
+
+@pytest.mark.parametrize("precision,tol", [("fp64", 1e-13), ("fp64_split", 5e-11), ("fp64_split5", 1e-8), ("fast", 5e-4)])
+@pytest.mark.parametrize("N,n,m", SIG_SHAPES)
+def test_pass_pair_over_tile_edges(precision, tol, N, n, m):
+    """`_sig` (:196-213) = one pass pair over X~ at shapes straddling every tile edge of both contractions (128-row and
+    128-variable M tiles, 64-wide factor tiles with 16..64-wide tails, padded cluster slots), against numpy float64.
+    The tolerances are the digit budgets (48 / 40 / 24 bits below the operand maxima) with margin; a tiling bug is O(1)."""
+    import torch
+    from linearcorex_b200 import _lib as L
+    from linearcorex_b200.corex import _DeviceSession
+    rng = np.random.RandomState(N * 7 + n * 3 + m)
+    x = rng.randn(N, n)
+    u = rng.randn(m, n) * rng.uniform(0.1, 3.0, size=(m, 1))
+    eps = 0.36
+    sess = _DeviceSession(L.PRECISIONS[precision])
+    ld = sess.lib.lcx_ld(n)
+    xt = torch.zeros((N, ld), dtype=torch.float64, device="cuda")
+    xt[:, :n] = torch.from_numpy(x)
+    sess.bind(xt, N, n, m, None)
+    ud = torch.zeros((m, ld), dtype=torch.float64, device="cuda")
+    ud[:, :n] = torch.from_numpy(u)
+    od = torch.full((m, ld), float("nan"), dtype=torch.float64, device="cuda")
+    L.check(sess.lib.lcx_sig(sess.h, ud.data_ptr(), eps, od.data_ptr()))
+    torch.cuda.synchronize()
+    got = od[:, :n].cpu().numpy()
+    y = x @ u.T
+    want = (1 - eps ** 2) * (x.T @ y).T / N + eps ** 2 * u
+    scale = (1 - eps ** 2) * (np.abs(x).T @ np.abs(y)).T / N + eps ** 2 * np.abs(u)
+    assert np.all(np.abs(got - want) <= tol * scale.max(axis=1, keepdims=True)), np.abs(got - want).max()
+    sess.close()
