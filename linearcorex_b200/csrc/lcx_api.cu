@@ -182,7 +182,7 @@ static Layout make_layout(long long Nl, int n, int m, int precision) {
         L.ldk8 = round_up(Nl, 128);
         // second contraction: 128 x 64 tiles over (variables x factors), split over samples to fill whole waves;
         // at most oz_kmax samples per split keeps every int32 accumulator exact
-        const long long tiles = (long long)cdiv(n, oz::kBM) * cdiv(m, oz::kBN);
+        const long long tiles = (long long)cdiv(n, oz::kBM) * cdiv(m, oz::bn_max(L.S));
         const int kblocks = cdiv(Nl, oz::kBK);
         // time model in units of one 64-deep K block: waves x (K blocks per CTA + fixed prologue/TMEM-drain/store cost
         // of ~16 blocks) + the partial-buffer round trip; measured at 12.5k and 100k rows per GPU
@@ -203,7 +203,7 @@ static Layout make_layout(long long Nl, int n, int m, int precision) {
         L.oz_chunk = (int)round_up(cdiv(Nl, best), oz::kBK);
         L.oz_splits = cdiv(Nl, L.oz_chunk);
         {   // first contraction: same cost model over its (row tile x factor tile) grid
-            const long long tiles1 = (long long)cdiv(Nl, oz::kBM) * cdiv(m, oz::kBN);
+            const long long tiles1 = (long long)cdiv(Nl, oz::kBM) * cdiv(m, oz::bn_max(L.S));
             const int kblocks1 = cdiv(n, oz::kBK);
             int b1 = cdiv(n, L.oz_kmax);
             double c1best = 1e300;
@@ -443,12 +443,13 @@ static int oz_prepare(lcx_session* s, bool streamed) {
     // D = X~^T Y (MN-major: inner = variables, 128 B boxes over 64 sample rows); the factor-side operands are K-major:
     // A slices (inner = variables) and the transposed Y slices (inner = samples).
     LCX_TRY(oz::make_slice_map(&s->map_x_k1, s->xs(), s->n, s->Nl, L.S, L.ld8, s->Nl * L.ld8, oz::kBK, oz::kBM, false));
-    LCX_TRY(oz::make_slice_map(&s->map_a_k1, s->as(), s->n, s->m, L.S, L.ld8, (long long)s->m * L.ld8, oz::kBK, oz::kBN, false));
-    s->oz_bn_tail = (int)round_up(s->m - (cdiv(s->m, oz::kBN) - 1) * oz::kBN, 16);
+    const int bnm = oz::bn_max(L.S);
+    LCX_TRY(oz::make_slice_map(&s->map_a_k1, s->as(), s->n, s->m, L.S, L.ld8, (long long)s->m * L.ld8, oz::kBK, bnm, false));
+    s->oz_bn_tail = (int)round_up(s->m - (cdiv(s->m, bnm) - 1) * bnm, 16);
     LCX_TRY(oz::make_slice_map(&s->map_a_k1_tail, s->as(), s->n, s->m, L.S, L.ld8, (long long)s->m * L.ld8, oz::kBK, s->oz_bn_tail,
                                false));
     LCX_TRY(oz::make_slice_map(&s->map_x_k2, s->xs(), s->n, s->Nl, L.S, L.ld8, s->Nl * L.ld8, oz::kBM, oz::kBK, true));
-    LCX_TRY(oz::make_slice_map(&s->map_y_k2, s->ys(), s->Nl, s->m, L.S, L.ldk8, (long long)s->m * L.ldk8, oz::kBK, oz::kBN, false));
+    LCX_TRY(oz::make_slice_map(&s->map_y_k2, s->ys(), s->Nl, s->m, L.S, L.ldk8, (long long)s->m * L.ldk8, oz::kBK, bnm, false));
     LCX_TRY(oz::make_slice_map(&s->map_y_k2_tail, s->ys(), s->Nl, s->m, L.S, L.ldk8, (long long)s->m * L.ldk8, oz::kBK,
                                s->oz_bn_tail, false));
     return 0;
@@ -456,7 +457,7 @@ static int oz_prepare(lcx_session* s, bool streamed) {
 
 static int oz_cluster() {  // LCX_OZ_CLUSTER=1|2|4 overrides the cluster size of the split-integer contractions
     const char* env = getenv("LCX_OZ_CLUSTER");
-    return env ? atoi(env) : 4;
+    return env ? atoi(env) : 2;  // pairs: multicast does not lower the bytes delivered per SM, and clusters of 4 fit only 132 SMs
 }
 
 template <int S>
@@ -484,7 +485,7 @@ static int oz_pair_t(lcx_session* s, const double* A, double* svec, cudaEvent_t*
         p.rows = (int)s->Nl; p.cols = m; p.k_total = n; p.k_chunk = L.oz1_chunk;
         p.bn_tail = s->oz_bn_tail;
         LCX_TRY((oz::launch_oz_gemm<S, true>(s->map_x_k1, s->map_a_k1, s->map_a_k1_tail, p,
-                                             dim3(cdiv(m, oz::kBN), cdiv(s->Nl, oz::kBM), L.oz1_splits), s->stream, oz_cluster())));
+                                             dim3(cdiv(m, oz::bn_max(S)), cdiv(s->Nl, oz::kBM), L.oz1_splits), s->stream, oz_cluster())));
         LAUNCHED(s);
         if (split1) {
             LCX_TRY(launch_reduce_splits(s->ptr(I_PART), L.oz1_splits, s->Nl * L.ldy, Y, (int)s->Nl, m, L.ldy, s->stream));
@@ -520,7 +521,7 @@ static int oz_pair_t(lcx_session* s, const double* A, double* svec, cudaEvent_t*
         p.bn_tail = s->oz_bn_tail;
         p.trans_out = 1;
         LCX_TRY((oz::launch_oz_gemm<S, false>(s->map_x_k2, s->map_y_k2, s->map_y_k2_tail, p,
-                                              dim3(cdiv(m, oz::kBN), cdiv(n, oz::kBM), L.oz_splits), s->stream, oz_cluster())));
+                                              dim3(cdiv(m, oz::bn_max(S)), cdiv(n, oz::kBM), L.oz_splits), s->stream, oz_cluster())));
         LAUNCHED(s);
         LCX_TRY(combine_and_allreduce(s, split ? s->ptr(I_PART) : D, split ? L.oz_splits : 1, (long long)m * L.ld, m, n, L.ld, D, svec,
                                       want_tail ? m : 0));

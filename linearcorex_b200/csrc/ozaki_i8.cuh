@@ -33,9 +33,15 @@ namespace lcx {
 namespace oz {
 
 constexpr int kBM = 128;      // output rows per CTA (UMMA M)
-constexpr int kBN = 64;       // output cols per CTA (UMMA N)
 constexpr int kBK = 64;       // contraction depth per pipeline stage (two UMMA K=32 steps)
-constexpr int kStages = 3;
+// Output columns per CTA (UMMA N per digit plane).  S group accumulators of bn columns must fit the 512 TMEM columns:
+// 64 for S = 5, 6; 128 for S <= 4, where one CTA then owns all of m <= 128 factors and the X~ tile is delivered to one
+// SM instead of two (the kernels are bound by operand delivery into the SMs).
+__host__ __device__ constexpr int bn_max(int S) { return S <= 4 ? 128 : 64; }
+// Pipeline depth: as many stages of S (8 KB + bn_max 64 B) planes as fit in 220 KB, at most 4.
+__host__ __device__ constexpr int stages_for(int S) {
+    return (220 * 1024) / (S * (kBM * kBK + bn_max(S) * kBK)) >= 4 ? 4 : (220 * 1024) / (S * (kBM * kBK + bn_max(S) * kBK));
+}
 constexpr int kThreads = 192; // warp 0 TMA, warp 1 MMA, warps 2..5 epilogue
 
 // ---- PTX wrappers ----------------------------------------------------------------------------------
@@ -151,8 +157,8 @@ struct GemmParams {
     int k_chunk;                 // contraction range per blockIdx.z (multiple of kBK)
     double inv_radix;            // 1 / R: group g carries weight R^-(g+2)
     int n_tiles;                 // number of real N tiles (gridDim.x may be padded up to a multiple of the cluster size)
-    int bn_tail;                 // width (multiple of 16, <= 64) of the LAST N tile, loaded through mapBt;
-                                 // 0 or 64 = full width.  m = 100 factors -> tiles of 64 + 48 instead of 64 + 64
+    int bn_tail;                 // width (multiple of 16, <= bn_max(S)) of the LAST N tile, loaded through mapBt;
+                                 // 0 or bn_max = full width.  m = 100 factors, S = 6 -> tiles of 64 + 48 instead of 64 + 64
     int trans_out;               // 1: store C[col][row] (the second contraction writes (X~^T Y)^T factor-major)
 };
 
@@ -160,7 +166,7 @@ struct GemmParams {
 // TMA coordinates (k0, n0, s).  The M-side operand is
 // KMAJOR = true : A tile = [128 rows][64 B of K]   (SW64),  tensor map (K, rows, slice),      coordinates (k0, m0, s);
 // KMAJOR = false: A tile = [64 K rows][128 B of M] (SW128), tensor map (M, K rows, slice),    coordinates (m0, k0, s).
-// All MMAs of one 64-deep K block for a tile of compile-time width BN (multiple of 16, <= 64).
+// All MMAs of one 64-deep K block for a tile of compile-time width BN (multiple of 16, <= bn_max(S)).
 template <int S, bool KMAJOR, int BN>
 __device__ __forceinline__ void issue_kblock(uint32_t sa, uint32_t sb, uint32_t tmem_base, bool first_block) {
     constexpr int A_BYTES = kBM * kBK;
@@ -196,11 +202,14 @@ template <int S, bool KMAJOR, int CL>
 __global__ void __launch_bounds__(kThreads, 1)
 oz_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                const __grid_constant__ CUtensorMap mapBt, const GemmParams p) {
+    constexpr int kBN = bn_max(S);
+    constexpr int kStages = stages_for(S);
     constexpr int A_BYTES = kBM * kBK;          // 8 KB per slice either way
-    constexpr int B_BYTES = kBN * kBK;          // 4 KB per slice (full-width tile)
+    constexpr int B_BYTES = kBN * kBK;          // 4 KB (8 KB) per slice (full-width tile)
     constexpr int STAGE_BYTES = S * (A_BYTES + B_BYTES);
     constexpr uint32_t TMEM_COLS = (S * kBN <= 128) ? 128 : (S * kBN <= 256 ? 256 : 512);
     static_assert(S * kBN <= 512, "accumulators exceed TMEM");
+    static_assert(kStages >= 2, "pipeline needs two stages");
 
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -280,7 +289,16 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 tc_fence_after();
                 const uint32_t sa = smem_u32(smem + st * STAGE_BYTES);
                 const uint32_t sb = sa + S * A_BYTES;
-                if (bn == 64) issue_kblock<S, KMAJOR, 64>(sa, sb, tmem_base, kb == 0);
+                bool wide = false;
+                if constexpr (kBN > 64) {
+                    wide = bn > 64;
+                    if (bn == 128) issue_kblock<S, KMAJOR, 128>(sa, sb, tmem_base, kb == 0);
+                    else if (bn == 112) issue_kblock<S, KMAJOR, 112>(sa, sb, tmem_base, kb == 0);
+                    else if (bn == 96) issue_kblock<S, KMAJOR, 96>(sa, sb, tmem_base, kb == 0);
+                    else if (bn == 80) issue_kblock<S, KMAJOR, 80>(sa, sb, tmem_base, kb == 0);
+                }
+                if (wide) {
+                } else if (bn == 64) issue_kblock<S, KMAJOR, 64>(sa, sb, tmem_base, kb == 0);
                 else if (bn == 48) issue_kblock<S, KMAJOR, 48>(sa, sb, tmem_base, kb == 0);
                 else if (bn == 32) issue_kblock<S, KMAJOR, 32>(sa, sb, tmem_base, kb == 0);
                 else issue_kblock<S, KMAJOR, 16>(sa, sb, tmem_base, kb == 0);
@@ -565,7 +583,7 @@ inline int make_slice_map(CUtensorMap* map, const void* base, long long inner, l
 template <int S, bool KMAJOR, int CL>
 inline int launch_oz_gemm_cl(const CUtensorMap& mapA, const CUtensorMap& mapB, const CUtensorMap& mapBt, GemmParams p, dim3 grid,
                              cudaStream_t st) {
-    constexpr int SMEM = kStages * S * (kBM * kBK + kBN * kBK) + 1024;
+    constexpr int SMEM = stages_for(S) * S * (kBM * kBK + bn_max(S) * kBK) + 1024;
     static bool configured = false;
     auto kern = oz_gemm_kernel<S, KMAJOR, CL>;
     if (!configured) {
