@@ -438,6 +438,10 @@ def run_ours(args, shape):
                      "kernel": rl_kernel,
                      "algorithmic_ops_per_pair": pair_ops, "fp64_equivalent_tflops": fp64_equiv,
                      "share_of_step": pair_ms * pairs.value / ms if ms > 0 else None,
+                     "limiter": ("operand delivery into the SMs: ncu l1tex__m_xbar2l1tex_read_bytes = 17.4 GB per launch at "
+                                 "9.7-9.9 TB/s (~6200 B/clk chip-wide) with the tensor pipe 72-73 % active; TMEM (6 int32 group "
+                                 "accumulators x 64 columns) fixes the 128 x 64 tile and with it the bytes per MAC "
+                                 "(profiles/r01_oz_gemm_ncu_full_config3.csv, DESIGN.md 4)") if digits == 6 else None,
                      "peak_source": rl_source},
         "clocks": clocks.summary(),
         "e2e": e2e,
