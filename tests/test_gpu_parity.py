@@ -226,7 +226,7 @@ def test_full_fit_fp64_split(name):
 
 @pytest.mark.parametrize("name", ["syn_400x300x10_f64", "big5_l0_f64", "outliers_missing_f64"])
 def test_fit_fast_mode_fixed_budget(name):
-    """Opt-in fast mode (4 digits): 1e-4 on W / TCs at a fixed iteration budget (near convergence the
+    """Opt-in fast mode (3 digits = 24 bits): 1e-4 on W / TCs at a fixed iteration budget (near convergence the
     stopping iteration itself is precision dependent, so the comparison is made at equal iteration counts)."""
     import corex_oracle as oc
     from linearcorex_b200 import Corex
