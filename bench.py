@@ -226,7 +226,8 @@ def workload_name(args, shape):
     return "%s: synthetic latent-factor data N=%d x n=%d, m=%d, %s mode" % (
         args.workload, shape[0], shape[1], shape[2],
         {"fp64": "FP64 (DMMA)", "fp64_split": "FP64 (6 int8 radix-254 digit planes on tcgen05)",
-         "fp64_split5": "FP64 (5 int8 radix-254 digit planes on tcgen05)", "fast": "fast (3 int8 digit planes)"}[args.precision])
+         "fp64_split5": "FP64 (5 int8 radix-254 digit planes on tcgen05)",
+         "fp64_split7": "FP64 (7 int8 radix-254 digit planes on tcgen05)", "fast": "fast (3 int8 digit planes)"}[args.precision])
 
 
 # ----------------------------------------------------------------------------------------------------
@@ -319,7 +320,7 @@ def run_ours(args, shape):
     pair_flops = 4.0 * n_local * n_vars * n_factors           # K1 + K2 of one pass pair on this rank (FP64-equivalent)
     pair_ms = (k1.value + k2.value) / max(1, pairs.value)
     fp64_equiv = pair_flops / (pair_ms / 1e3) / 1e12 if pair_ms > 0 else 0.0
-    digits = {"fp64": 0, "fp64_split": 6, "fp64_split5": 5, "fast": 3}[args.precision]
+    digits = {"fp64": 0, "fp64_split": 6, "fp64_split5": 5, "fp64_split7": 7, "fast": 3}[args.precision]
     if os.environ.get("LCX_SPLIT_DIGITS") and digits:
         digits = int(os.environ["LCX_SPLIT_DIGITS"])
     if digits:
@@ -425,6 +426,7 @@ def run_ours(args, shape):
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": {"fp64": "f64", "fp64_split": "f64 (6 int8 digit planes = 48 bits, exact int32 products, f64 recombination)",
                   "fp64_split5": "f64 (5 int8 digit planes = 40 bits, exact int32 products, f64 recombination)",
+                  "fp64_split7": "f64 (7 int8 digit planes = 56 bits, exact int32 products, f64 recombination)",
                   "fast": "3 int8 digit planes = 24 bits (fp32-equivalent), f64 elsewhere"}[args.precision], "data": "synthetic",
         "config": {"workload": workload_name(args, shape), "n_samples": n_total, "n_variables": n_vars,
                    "n_factors": n_factors, "rows_per_gpu": n_local, "parallelism": "sample-sharded x%d" % world, "exchange_per_pass_pair": exchange,
@@ -479,7 +481,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="config3", choices=sorted(WORKLOADS))
-    ap.add_argument("--precision", default="fp64_split", choices=["fp64", "fp64_split", "fp64_split5", "fast"])
+    ap.add_argument("--precision", default="fp64_split", choices=["fp64", "fp64_split", "fp64_split5", "fp64_split7", "fast"])
     ap.add_argument("--gaussianize", default="standard")
     ap.add_argument("--rows", type=int, default=0)
     ap.add_argument("--vars", type=int, default=0)

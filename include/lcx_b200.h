@@ -50,6 +50,9 @@ extern "C" {
                                       1e-11 or better against the reference's float64 path), everything else binary64 */
 #define LCX_PRECISION_FP64_SPLIT5 3 /* the same with 5 digits = 40 bits: 30 % faster, parity 1e-9 on fits of up to ~700
                                        iterations (2e-9 on the 2400-iteration adni fixture) */
+#define LCX_PRECISION_FP64_SPLIT7 4 /* 7 digits = 56 bits, finer than binary64's 53-bit significand: for ill-conditioned fits
+                                       (pure-noise data, extreme outliers) where the 48-bit mode's perturbation is amplified
+                                       past 1e-9; 28 instead of 21 plane products, two pipeline stages */
 
 /* input dtypes of raw X */
 #define LCX_F32 0

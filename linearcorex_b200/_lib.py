@@ -9,10 +9,10 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "liblcx_b200.so")
 
 OK, QUICK_FAIL = 0, 1
-PRECISION_FP64, PRECISION_FAST, PRECISION_FP64_SPLIT, PRECISION_FP64_SPLIT5 = 0, 1, 2, 3
+PRECISION_FP64, PRECISION_FAST, PRECISION_FP64_SPLIT, PRECISION_FP64_SPLIT5, PRECISION_FP64_SPLIT7 = 0, 1, 2, 3, 4
 PRECISIONS = {"fp64": PRECISION_FP64, "fast": PRECISION_FAST, "fp64_split": PRECISION_FP64_SPLIT,
-              "fp64_split5": PRECISION_FP64_SPLIT5}
-SPLIT_DIGITS = {"fast": 3, "fp64_split": 6, "fp64_split5": 5}
+              "fp64_split5": PRECISION_FP64_SPLIT5, "fp64_split7": PRECISION_FP64_SPLIT7}
+SPLIT_DIGITS = {"fast": 3, "fp64_split": 6, "fp64_split5": 5, "fp64_split7": 7}
 F32, F64 = 0, 1
 GAUSS = {"standard": 0, "outliers": 1, "none": 2}
 

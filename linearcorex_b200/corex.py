@@ -22,6 +22,9 @@ behaviour):
                       (6 radix-254 digits = 48 bits below each row/column maximum -- truncation at the level of
                       binary64 rounding, measured parity 1e-11), everything else binary64.
                       'fp64_split5': 5 digits (40 bits), 30 % faster, parity 1e-9 on fits up to ~700 iterations.
+                      'fp64_split7': 7 digits (56 bits, finer than binary64's significand), ~1.4x the cost of the
+                      default; for ill-conditioned fits (pure-noise data, extreme outliers) that amplify the 48-bit
+                      mode's perturbation past 1e-9.
                       'fast': 3 digits (24 bits, fp32-equivalent products; opt-in, 1e-4 tolerance).
   exact_trials        False (default): backtracking trials are evaluated through the linearity of
                       `_sig` (rho(W + eta U) = rho(W) + eta _sig(U)) -- one pass pair over X per

@@ -89,9 +89,10 @@ static int radix_for() {
 static int digits_for(int precision) {
     if (precision == LCX_PRECISION_FP64) return 0;
     const char* env = getenv("LCX_SPLIT_DIGITS");
-    if (env && atoi(env) >= 3 && atoi(env) <= 6) return atoi(env);
+    if (env && atoi(env) >= 3 && atoi(env) <= 7) return atoi(env);
     if (precision == LCX_PRECISION_FAST) return 3;          // 24 bits: fp32-equivalent products
     if (precision == LCX_PRECISION_FP64_SPLIT5) return 5;   // 40 bits
+    if (precision == LCX_PRECISION_FP64_SPLIT7) return 7;   // 56 bits: finer than binary64's own 53-bit significand
     return 6;                                               // 48 bits: truncation at the level of binary64 rounding
 }
 constexpr int kYStatRows = 512;
@@ -298,7 +299,7 @@ extern "C" const char* lcx_last_error(void) { return g_err; }
 
 extern "C" int lcx_session_create(lcx_session** out, int device, int precision) {
     LCX_REQUIRE(out != nullptr, "out is null");
-    LCX_REQUIRE(precision >= LCX_PRECISION_FP64 && precision <= LCX_PRECISION_FP64_SPLIT5, "unknown precision mode");
+    LCX_REQUIRE(precision >= LCX_PRECISION_FP64 && precision <= LCX_PRECISION_FP64_SPLIT7, "unknown precision mode");
     LCX_CUDA(cudaSetDevice(device));
     cudaDeviceProp prop;
     LCX_CUDA(cudaGetDeviceProperties(&prop, device));
@@ -409,7 +410,7 @@ extern "C" long long lcx_ld(int n_vars) { return round_up(n_vars, 16); }
 extern "C" long long lcx_ldy(int n_factors) { return round_up(n_factors, 8); }
 
 extern "C" long long lcx_workspace_doubles(long long n_rows_local, int n_vars, int n_factors, int precision) {
-    if (n_rows_local < 0 || n_vars <= 0 || n_factors <= 0 || precision < 0 || precision > 3) return -1;
+    if (n_rows_local < 0 || n_vars <= 0 || n_factors <= 0 || precision < 0 || precision > LCX_PRECISION_FP64_SPLIT7) return -1;
     return make_layout(n_rows_local, n_vars, n_factors, precision).total;
 }
 
@@ -437,6 +438,7 @@ static int oz_prepare(lcx_session* s, bool streamed) {
         case 4: LCX_TRY(oz_slice_x_t<4>(s)); break;
         case 5: LCX_TRY(oz_slice_x_t<5>(s)); break;
         case 6: LCX_TRY(oz_slice_x_t<6>(s)); break;
+        case 7: LCX_TRY(oz_slice_x_t<7>(s)); break;
         default: return fail(LCX_ERR_STATE, "oz_prepare", "bad digit count");
     }
     // X~ slices as the M operand of Y = X~ A^T (K-major: inner = variables, 64 B boxes) and as the M operand of
@@ -536,6 +538,7 @@ static int oz_pair(lcx_session* s, const double* A, double* svec, cudaEvent_t* e
         case 4: return oz_pair_t<4>(s, A, svec, ev, first_only, want_tail);
         case 5: return oz_pair_t<5>(s, A, svec, ev, first_only, want_tail);
         case 6: return oz_pair_t<6>(s, A, svec, ev, first_only, want_tail);
+        case 7: return oz_pair_t<7>(s, A, svec, ev, first_only, want_tail);
     }
     return fail(LCX_ERR_STATE, "oz_pair", "bad digit count");
 }
@@ -615,6 +618,7 @@ extern "C" int lcx_slice_block(lcx_session* s, const double* xt, long long row0,
         case 4: return oz_slice_block_t<4>(s, xt, row0, rows, ldx);
         case 5: return oz_slice_block_t<5>(s, xt, row0, rows, ldx);
         case 6: return oz_slice_block_t<6>(s, xt, row0, rows, ldx);
+        case 7: return oz_slice_block_t<7>(s, xt, row0, rows, ldx);
     }
     return fail(LCX_ERR_STATE, "lcx_slice_block", "bad digit count");
 }

@@ -148,7 +148,7 @@ def _planes(sess, L, torch, which):
     return planes, scale, S, R
 
 
-@pytest.mark.parametrize("precision", ["fp64_split", "fast"])
+@pytest.mark.parametrize("precision", ["fp64_split", "fast", "fp64_split7"])
 def test_digit_planes_bit_exact_against_numpy(precision):
     """Integer work is held to bit-exactness: the device's int8 digit planes of X~, A and Y equal the numpy restatement of
     the digit extraction (tests/test_split_scheme.py) digit for digit, and the recombined products are the exact integer sums."""
@@ -214,7 +214,7 @@ SIG_SHAPES = [(1, 1, 1), (63, 5, 1), (64, 127, 16), (65, 128, 17), (200, 129, 48
               (1000, 257, 100), (129, 64, 112), (300, 2049, 128), (4100, 130, 130), (2500, 70, 200)]
 
 
-@pytest.mark.parametrize("precision,tol", [("fp64", 1e-13), ("fp64_split", 5e-11), ("fp64_split5", 1e-8), ("fast", 5e-4)])
+@pytest.mark.parametrize("precision,tol", [("fp64", 1e-13), ("fp64_split7", 1e-12), ("fp64_split", 5e-11), ("fp64_split5", 1e-8), ("fast", 5e-4)])
 @pytest.mark.parametrize("N,n,m", SIG_SHAPES)
 def test_pass_pair_over_tile_edges(precision, tol, N, n, m):
     """`_sig` (:196-213) = one pass pair over X~ at shapes straddling every tile edge of both contractions (128-row and

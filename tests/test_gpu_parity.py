@@ -257,6 +257,13 @@ def test_full_fit_fp64_split5(name):
     _check_fit(z, mdl, x, RTOL)
 
 
+@pytest.mark.parametrize("name", ["big5_l0_f64", "syn_400x300x10_f64", "standard_missing_f64", "adni_l1_f64"])
+def test_full_fit_fp64_split7(name):
+    """7 digits (56 bits, finer than binary64's significand): the mode for ill-conditioned fits."""
+    z, mdl, x = _fit(name, precision="fp64_split7")
+    _check_fit(z, mdl, x, RTOL)
+
+
 def test_adni_layer0_fp64_split_long_trajectory():
     """2414 iterations with 3 % missing data: the 48-bit split mode tracks the reference's float64 path to 1e-10."""
     z, mdl, x = _fit("adni_l0_f64", precision="fp64_split")
