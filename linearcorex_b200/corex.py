@@ -562,7 +562,11 @@ class Corex(object):
         delta = np.abs(self.tc - last_tc)
         rec["TC"] = self.tc
         self.trace.append(rec)
-        self.history["TC"] = self.history.get("TC", []) + [self.tc]
+        self.history.setdefault("TC", []).append(self.tc)  # (the reference rebuilds the list every iteration, :170)
+        if self.verbose:  # :172-174 -- quick moments carry neither key (0 / zeros); the synergy moments carry both
+            self.history.setdefault("additivity", []).append(self.moments.get("additivity", 0))
+            tcs = np.zeros(self.m) if self.discourage_overlap else sess.host(_lib.A_TCS, squeeze=True)
+            self.history.setdefault("TCs", []).append(tcs)
         if self.verbose > 1:
             print("TC={:.3f}\tadd={:.3f}\tdelta={:.6f}".format(self.tc, self.moments.get("additivity", 0), delta))
         return True, delta

@@ -168,3 +168,22 @@ def test_transform_of_one_row_and_of_unseen_rows(precision):
     assert_close(mdl.transform(fresh[:1]), ref.transform(fresh[:1]), 1e-9, "transform one row")
     lab = mdl.transform(fresh, details=True)
     assert lab[0].shape == (33, 3)
+
+
+@pytest.mark.parametrize("overlap", [True, False])
+def test_verbose_history_keys(overlap, capsys):
+    """update_records (:166-175): with verbose set, `history` also carries per-iteration additivity and TCs -- zeros from
+    the quick non-synergy moments (which have neither key), real values from the synergy moments."""
+    from linearcorex_b200 import Corex
+    x = _data((80, 7))
+    mdl = Corex(n_hidden=2, verbose=1, discourage_overlap=overlap, **BUDGET).fit(x)
+    capsys.readouterr()
+    n_it = len(mdl.history["TC"])
+    assert n_it > 0 and len(mdl.history["additivity"]) == n_it and len(mdl.history["TCs"]) == n_it
+    assert all(np.shape(t) == (2,) for t in mdl.history["TCs"])
+    if overlap:
+        assert not np.any(mdl.history["additivity"]) and not np.any(mdl.history["TCs"])
+    else:
+        assert np.all(np.isfinite(mdl.history["TCs"])) and np.any(mdl.history["TCs"])
+    quiet = Corex(n_hidden=2, discourage_overlap=overlap, **BUDGET).fit(x)
+    assert sorted(quiet.history) == ["TC"] and np.array_equal(quiet.ws, mdl.ws)
