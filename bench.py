@@ -319,6 +319,7 @@ def run_ours(args, shape):
     n_local = hi - lo
     pair_flops = 4.0 * n_local * n_vars * n_factors           # K1 + K2 of one pass pair on this rank (FP64-equivalent)
     pair_ms = (k1.value + k2.value) / max(1, pairs.value)
+    k1_ms, k2_ms = k1.value / max(1, pairs.value), k2.value / max(1, pairs.value)  # each includes its digit-slicing kernels
     fp64_equiv = pair_flops / (pair_ms / 1e3) / 1e12 if pair_ms > 0 else 0.0
     digits = {"fp64": 0, "fp64_split": 6, "fp64_split5": 5, "fp64_split7": 7, "fast": 3}[args.precision]
     if os.environ.get("LCX_SPLIT_DIGITS") and digits:
@@ -421,6 +422,16 @@ def run_ours(args, shape):
         # would understate the CPU path's steady-state rate (1.3-1.9 trials per iteration)
         cpu = time_reference_cpu(n_total, n_vars, n_factors, steps=3, warmup=5, flop_budget=3e12)
         cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    delivered = None
+    if digits:
+        # operand tiles landing in shared memory per launch (what ncu reports as l1tex__m_xbar2l1tex_read_bytes): per
+        # 128-row M tile and 64-deep K block every factor tile receives the S planes of the X~ tile plus its own factor planes
+        bn = 128 if digits <= 4 else 64
+        per_block = digits * 64 * (128 * -(-n_factors // bn) + 16 * -(-n_factors // 16))
+        k1 = -(-n_local // 128) * -(-n_vars // 64) * per_block
+        k2 = -(-n_vars // 128) * -(-n_local // 64) * per_block
+        delivered = {"bytes_per_launch": [k1, k2],
+                     "tb_per_s": [k1 / (k1_ms * 1e9) if k1_ms > 0 else None, k2 / (k2_ms * 1e9) if k2_ms > 0 else None]}
     line = {
         "metric": METRIC, "value": it_s, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -444,6 +455,7 @@ def run_ours(args, shape):
                                  "9.7-9.9 TB/s (~6200 B/clk chip-wide) with the tensor pipe 72-73 % active; TMEM (6 int32 group "
                                  "accumulators x 64 columns) fixes the 128 x 64 tile and with it the bytes per MAC "
                                  "(profiles/r01_oz_gemm_ncu_full_config3.csv, DESIGN.md 4)") if digits == 6 else None,
+                     "operand_delivery": delivered,
                      "peak_source": rl_source},
         "clocks": clocks.summary(),
         "e2e": e2e,
