@@ -13,11 +13,11 @@
 // accumulator at 2^31 / (127^2 S) through split-K).  Pairs with k+l > S+1 are dropped (they sit below the digits that were
 // truncated anyway).  S = 6 keeps 48 bits below the row / column maximum -- truncation at the level of binary64
 // rounding, the FP64-faithful mode (measured parity 1e-11 or better on full fits); S = 5 keeps 40 bits; S = 3 is the
-// opt-in fast mode (24 bits: fp32-equivalent like 3xTF32, at 3 bytes per element and int8 rates).
+// opt-in fast mode (24 bits: fp32-equivalent like 3xTF32, at 3 bytes per element and int8 rates); S = 7 keeps 56 bits.
 //
-// One CTA owns a 128 x bn output tile (bn = 64, or narrower for the last factor tile) and S accumulators of bn TMEM
-// columns (group g at column bn g).  Warp 0 streams operand planes with TMA (cp.async.bulk.tensor, 64 B / 128 B
-// swizzle; the M-side planes are multicast across a cluster of 2 or 4 CTAs) through a 3-stage mbarrier ring; warp 1
+// One CTA owns a 128 x bn output tile (bn = 64, 128 for S <= 4, or narrower for the last factor tile) and S accumulators
+// of bn TMEM columns (group g at column bn g).  Warp 0 streams operand planes with TMA (cp.async.bulk.tensor, 64 B /
+// 128 B swizzle; the X~ planes are multicast across the CTA pair that shares them) through a 2-4 stage mbarrier ring; warp 1
 // issues the tcgen05.mma (digit k of A against digits 0..S-1-k of B as ONE wide instruction) and commits to the ring;
 // warps 2-5 drain TMEM (tcgen05.ld), recombine the groups in fp64 (Horner from the smallest weight) and store.  The
 // same row-major int8 image of X~ feeds both contractions as their M operand: K-major in the first, MN-major in the
