@@ -280,7 +280,7 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             // Digit ka of A meets digits 0..S-1-ka of B, landing in groups ka..S-1 = CONSECUTIVE TMEM columns, and
             // the B digit planes are consecutive in shared memory, so those S-ka products are issued as one wide
             // MMA (N = bn (S-ka), at most 256 per instruction): A is re-read from shared memory 8 times per K step
-            // instead of 21 -- the narrow 128x64 form is shared-memory-bandwidth bound (6 KB of operands per 32 cycles).
+            // instead of 21 -- an N = 64 instruction occupies the tensor pipe for ~60 cycles while doing 32 cycles of work.
             // The issue sequence is fully unrolled per tile width (one elected thread issues everything).
             for (int kb = 0; kb < num_kb; ++kb) {
                 const int st = kb % kStages;
