@@ -243,3 +243,20 @@ def test_pass_pair_over_tile_edges(precision, tol, N, n, m):
     scale = (1 - eps ** 2) * (np.abs(x).T @ np.abs(y)).T / N + eps ** 2 * np.abs(u)
     assert np.all(np.abs(got - want) <= tol * scale.max(axis=1, keepdims=True)), np.abs(got - want).max()
     sess.close()
+
+
+def _random_shapes(count, seed=20241017):
+    rng = np.random.RandomState(seed)
+    out = []
+    for _ in range(count):
+        N = int(rng.choice([rng.randint(1, 70), rng.randint(70, 700), rng.randint(700, 6000)]))
+        n = int(rng.choice([rng.randint(1, 70), rng.randint(70, 700), rng.randint(700, 3000)]))
+        m = int(rng.choice([rng.randint(1, 20), rng.randint(20, 140), rng.randint(140, 300)]))
+        out.append((N, n, m))
+    return out
+
+
+@pytest.mark.parametrize("N,n,m", _random_shapes(24))
+def test_pass_pair_random_shapes_fp64_split(N, n, m):
+    """The same check as the tile-edge sweep on 24 seeded random shapes (default precision mode)."""
+    test_pass_pair_over_tile_edges("fp64_split", 5e-11, N, n, m)

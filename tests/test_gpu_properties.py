@@ -110,3 +110,18 @@ def test_config4_like_small_sample_path():
         err_tc = abs(mdl.tc - ref.tc) / abs(ref.tc)
         assert err_w < 1e-8 and err_tc < 1e-9, (precision, err_w, err_tc)
         np.testing.assert_allclose(mdl.moments["X_i Z_j"], ref.moments["X_i Z_j"], rtol=0, atol=1e-7 * np.abs(ref.moments["X_i Z_j"]).max())
+
+
+@pytest.mark.parametrize("precision", ["fp64", "fp64_split", "fast"])
+def test_run_to_run_bit_identical(precision):
+    """No float atomics anywhere: split-K partials and per-CTA reductions are combined in fixed order, so repeated fits of
+    the same data are bit-identical (shape chosen so that both contractions run split-K over several waves of CTAs)."""
+    import corex_oracle as oc
+    from linearcorex_b200 import Corex
+    x = oc.latent_factor_data(30000, 1500, 40, seed=4, snr=1.0, snr_spread=0.5)
+    fits = [Corex(n_hidden=40, seed=3, max_iter=4, tol=1e-12, precision=precision).fit(x) for _ in range(3)]
+    for other in fits[1:]:
+        assert np.array_equal(other.ws, fits[0].ws)
+        assert other.history["TC"] == fits[0].history["TC"]
+        for key, val in fits[0].moments.items():
+            assert np.array_equal(np.asarray(other.moments[key]), np.asarray(val)), key
