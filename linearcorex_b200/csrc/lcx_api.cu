@@ -661,6 +661,10 @@ extern "C" long long lcx_colstats_scratch_doubles(long long n_rows, int n_vars) 
     return 2LL * cdiv(n_rows, kSlabRows) * round_up(n_vars, 16) + 32;
 }
 
+// 16-byte row loads are possible when the base pointer and the leading dimension are multiples of 4 elements
+template <typename T>
+static bool vec4_ok(const T* x, long long ldx) { return ((uintptr_t)x % 16 == 0) && (ldx % 4 == 0); }
+
 template <typename T>
 static int colstats_sum_t(lcx_session* s, const T* x, long long N, int n, long long ldx, int has_marker, double marker,
                           double* sum, double* cnt, double* scratch) {
@@ -668,9 +672,13 @@ static int colstats_sum_t(lcx_session* s, const T* x, long long N, int n, long l
     const long long ldp = round_up(n, 16);
     double* ps = scratch;
     double* pc = scratch + (long long)slabs * ldp;
-    dim3 grid(cdiv(n, 32), slabs), block(32, 8);
-    colstats_sum_kernel<T><<<grid, block, 0, s->stream>>>(x, N, n, ldx, kSlabRows, has_marker, marker, marker != marker, ps,
-                                                        pc, ldp);
+    const dim3 block(32, 8);
+    if (vec4_ok(x, ldx))
+        colstats_sum_kernel<T, 4><<<dim3(cdiv(n, 128), slabs), block, 0, s->stream>>>(x, N, n, ldx, kSlabRows, has_marker, marker,
+                                                                                    marker != marker, ps, pc, ldp);
+    else
+        colstats_sum_kernel<T, 1><<<dim3(cdiv(n, 32), slabs), block, 0, s->stream>>>(x, N, n, ldx, kSlabRows, has_marker, marker,
+                                                                                   marker != marker, ps, pc, ldp);
     LAUNCHED(s);
     combine_slabs_kernel<<<cdiv(n, 256), 256, 0, s->stream>>>(ps, slabs, ldp, sum, n);
     LAUNCHED(s);
@@ -707,9 +715,13 @@ static int colstats_sqdev_t(lcx_session* s, const T* x, long long N, int n, long
     const int slabs = cdiv(N, kSlabRows);
     const long long ldp = round_up(n, 16);
     double* pmax = maxdev ? scratch + (long long)slabs * ldp : nullptr;
-    dim3 grid(cdiv(n, 32), slabs), block(32, 8);
-    colstats_sqdev_kernel<T><<<grid, block, 0, s->stream>>>(x, N, n, ldx, kSlabRows, has_marker, marker, marker != marker,
-                                                          mean, scratch, pmax, ldp);
+    const dim3 block(32, 8);
+    if (vec4_ok(x, ldx))
+        colstats_sqdev_kernel<T, 4><<<dim3(cdiv(n, 128), slabs), block, 0, s->stream>>>(x, N, n, ldx, kSlabRows, has_marker, marker,
+                                                                                      marker != marker, mean, scratch, pmax, ldp);
+    else
+        colstats_sqdev_kernel<T, 1><<<dim3(cdiv(n, 32), slabs), block, 0, s->stream>>>(x, N, n, ldx, kSlabRows, has_marker, marker,
+                                                                                     marker != marker, mean, scratch, pmax, ldp);
     LAUNCHED(s);
     combine_slabs_kernel<<<cdiv(n, 256), 256, 0, s->stream>>>(scratch, slabs, ldp, sq, n);
     LAUNCHED(s);
@@ -751,14 +763,22 @@ extern "C" int lcx_standardize(lcx_session* s, const void* x, int dtype, long lo
     LCX_REQUIRE(has_marker == 0 || impute != nullptr, "imputation means required when a missing marker is set");
     LCX_REQUIRE(n_rows > 0 && n_vars > 0 && ldx >= n_vars && ldo >= n_vars, "bad shape");
     LCX_CUDA(cudaSetDevice(s->device));
-    dim3 grid((unsigned)n_rows, cdiv(ldo, 256));
     const int nan_marker = marker != marker;
-    if (dtype == LCX_F32)
-        standardize_kernel<float><<<grid, 256, 0, s->stream>>>((const float*)x, n_rows, n_vars, ldx, has_marker, marker,
-                                                             nan_marker, gauss_mode, impute, mean, sd, out, ldo);
+    const bool v4 = (ldo % 4 == 0) && ((uintptr_t)out % 16 == 0) &&
+                    (dtype == LCX_F32 ? vec4_ok((const float*)x, ldx) : vec4_ok((const double*)x, ldx));
+    const dim3 grid((unsigned)n_rows, cdiv(ldo, v4 ? 1024 : 256));
+    if (dtype == LCX_F32 && v4)
+        standardize_kernel<float, 4><<<grid, 256, 0, s->stream>>>((const float*)x, n_rows, n_vars, ldx, has_marker, marker,
+                                                                nan_marker, gauss_mode, impute, mean, sd, out, ldo);
+    else if (dtype == LCX_F32)
+        standardize_kernel<float, 1><<<grid, 256, 0, s->stream>>>((const float*)x, n_rows, n_vars, ldx, has_marker, marker,
+                                                                nan_marker, gauss_mode, impute, mean, sd, out, ldo);
+    else if (dtype == LCX_F64 && v4)
+        standardize_kernel<double, 4><<<grid, 256, 0, s->stream>>>((const double*)x, n_rows, n_vars, ldx, has_marker, marker,
+                                                                 nan_marker, gauss_mode, impute, mean, sd, out, ldo);
     else if (dtype == LCX_F64)
-        standardize_kernel<double><<<grid, 256, 0, s->stream>>>((const double*)x, n_rows, n_vars, ldx, has_marker, marker,
-                                                              nan_marker, gauss_mode, impute, mean, sd, out, ldo);
+        standardize_kernel<double, 1><<<grid, 256, 0, s->stream>>>((const double*)x, n_rows, n_vars, ldx, has_marker, marker,
+                                                                 nan_marker, gauss_mode, impute, mean, sd, out, ldo);
     else
         return fail(LCX_ERR_ARG, "lcx_standardize", "unknown dtype");
     LAUNCHED(s);

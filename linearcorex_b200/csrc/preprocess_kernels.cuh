@@ -9,79 +9,122 @@
 
 namespace lcx {
 
-template <typename T>
-__device__ __forceinline__ bool is_missing(T v, int has_marker, double marker, int marker_is_nan) {
+// V consecutive elements of a row as doubles: one 16-byte load per 4 floats / 2 doubles when V == 4 (the caller
+// guarantees 16-byte alignment: base pointer, leading dimension and first column all multiples of 4 elements).
+template <typename T, int V>
+__device__ __forceinline__ void load_row_vec(const T* __restrict__ p, double (&o)[V]) {
+    if constexpr (V == 1) {
+        o[0] = (double)p[0];
+    } else if constexpr (sizeof(T) == 4) {
+        const float4 v = *reinterpret_cast<const float4*>(p);
+        o[0] = (double)v.x; o[1] = (double)v.y; o[2] = (double)v.z; o[3] = (double)v.w;
+    } else {
+        const double2 a = *reinterpret_cast<const double2*>(p), b = *reinterpret_cast<const double2*>(p + 2);
+        o[0] = a.x; o[1] = a.y; o[2] = b.x; o[3] = b.y;
+    }
+}
+
+__device__ __forceinline__ bool is_missing_d(double d, int has_marker, double marker, int marker_is_nan) {
     if (!has_marker) return false;
-    const double d = (double)v;
     return (d != d) || (!marker_is_nan && d == marker);  // NaN is always missing once a marker is set (:505)
 }
 
 // pass 1: part_sum[slab][i] = sum of observed x, part_cnt[slab][i] = number observed (finite, not missing)
-template <typename T>
+// Each thread owns V adjacent columns (V = 4: 16-byte loads) and every eighth row of the slab; a column's rows are
+// summed in the same order whatever V is, so the result does not depend on the vector width.
+template <typename T, int V>
 __global__ void __launch_bounds__(256) colstats_sum_kernel(const T* __restrict__ x, long long N, int n, long long ldx,
                                                            int rows_per_slab, int has_marker, double marker,
                                                            int marker_is_nan, double* __restrict__ part_sum,
                                                            double* __restrict__ part_cnt, long long ldp) {
-    __shared__ double rs[8][32], rc[8][32];
-    const int i = blockIdx.x * 32 + threadIdx.x;
+    __shared__ double rs[8][32 * V], rc[8][32 * V];
+    const int i0 = (blockIdx.x * 32 + threadIdx.x) * V;
     const long long r0 = (long long)blockIdx.y * rows_per_slab;
     const long long r1 = min(N, r0 + rows_per_slab);
-    double s = 0.0, c = 0.0;
-    if (i < n) {
+    double s[V], c[V];
+#pragma unroll
+    for (int j = 0; j < V; ++j) s[j] = c[j] = 0.0;
+    if (i0 < n) {
+#pragma unroll 2
         for (long long r = r0 + threadIdx.y; r < r1; r += 8) {
-            const T v = x[r * ldx + i];
-            const bool obs = has_marker ? (!is_missing(v, has_marker, marker, marker_is_nan) && isfinite((double)v)) : true;
-            if (obs) { s += (double)v; c += 1.0; }
+            double v[V];
+            load_row_vec<T, V>(x + r * ldx + i0, v);
+#pragma unroll
+            for (int j = 0; j < V; ++j) {
+                const bool obs = has_marker ? (!is_missing_d(v[j], has_marker, marker, marker_is_nan) && isfinite(v[j])) : true;
+                if (obs) { s[j] += v[j]; c[j] += 1.0; }
+            }
         }
     }
-    rs[threadIdx.y][threadIdx.x] = s;
-    rc[threadIdx.y][threadIdx.x] = c;
-    __syncthreads();
-    if (threadIdx.y == 0 && i < n) {
-        double a = 0.0, b = 0.0;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) { a += rs[k][threadIdx.x]; b += rc[k][threadIdx.x]; }
-        part_sum[(long long)blockIdx.y * ldp + i] = a;
-        part_cnt[(long long)blockIdx.y * ldp + i] = b;
+    for (int j = 0; j < V; ++j) {
+        rs[threadIdx.y][threadIdx.x * V + j] = s[j];
+        rc[threadIdx.y][threadIdx.x * V + j] = c[j];
+    }
+    __syncthreads();
+    for (int t = threadIdx.y * 32 + threadIdx.x; t < 32 * V; t += 256) {
+        const int i = blockIdx.x * 32 * V + t;
+        if (i < n) {
+            double a = 0.0, b = 0.0;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) { a += rs[k][t]; b += rc[k][t]; }
+            part_sum[(long long)blockIdx.y * ldp + i] = a;
+            part_cnt[(long long)blockIdx.y * ldp + i] = b;
+        }
     }
 }
 
 // pass 2: part[slab][i] = sum over observed rows of (x - mean_i)^2   (imputed entries contribute 0)
-template <typename T>
+template <typename T, int V>
 __global__ void __launch_bounds__(256) colstats_sqdev_kernel(const T* __restrict__ x, long long N, int n, long long ldx,
                                                              int rows_per_slab, int has_marker, double marker,
                                                              int marker_is_nan, const double* __restrict__ mean,
                                                              double* __restrict__ part, double* __restrict__ part_max,
                                                              long long ldp) {
     // part_max (optional): per-slab max |x - mean| -- bounds |X~| before X~ exists (streamed digit slicing)
-    __shared__ double rs[8][32], rm[8][32];
-    const int i = blockIdx.x * 32 + threadIdx.x;
+    __shared__ double rs[8][32 * V], rm[8][32 * V];
+    const int i0 = (blockIdx.x * 32 + threadIdx.x) * V;
     const long long r0 = (long long)blockIdx.y * rows_per_slab;
     const long long r1 = min(N, r0 + rows_per_slab);
-    double s = 0.0, mx = 0.0;
-    if (i < n) {
-        const double mu = mean[i];
+    double s[V], mx[V], mu[V];
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+        s[j] = mx[j] = 0.0;
+        mu[j] = (i0 + j < n) ? mean[i0 + j] : 0.0;
+    }
+    if (i0 < n) {
+#pragma unroll 2
         for (long long r = r0 + threadIdx.y; r < r1; r += 8) {
-            const T v = x[r * ldx + i];
-            if (!is_missing(v, has_marker, marker, marker_is_nan)) {
-                const double d = (double)v - mu;
-                s += d * d;
-                mx = amax_acc(mx, d);
+            double v[V];
+            load_row_vec<T, V>(x + r * ldx + i0, v);
+#pragma unroll
+            for (int j = 0; j < V; ++j) {
+                if (!is_missing_d(v[j], has_marker, marker, marker_is_nan)) {
+                    const double d = v[j] - mu[j];
+                    s[j] += d * d;
+                    mx[j] = amax_acc(mx[j], d);
+                }
             }
         }
     }
-    rs[threadIdx.y][threadIdx.x] = s;
-    rm[threadIdx.y][threadIdx.x] = mx;
-    __syncthreads();
-    if (threadIdx.y == 0 && i < n) {
-        double a = 0.0, b = 0.0;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            a += rs[k][threadIdx.x];
-            b = fmax(b, rm[k][threadIdx.x]);
+    for (int j = 0; j < V; ++j) {
+        rs[threadIdx.y][threadIdx.x * V + j] = s[j];
+        rm[threadIdx.y][threadIdx.x * V + j] = mx[j];
+    }
+    __syncthreads();
+    for (int t = threadIdx.y * 32 + threadIdx.x; t < 32 * V; t += 256) {
+        const int i = blockIdx.x * 32 * V + t;
+        if (i < n) {
+            double a = 0.0, b = 0.0;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                a += rs[k][t];
+                b = fmax(b, rm[k][t]);
+            }
+            part[(long long)blockIdx.y * ldp + i] = a;
+            if (part_max) part_max[(long long)blockIdx.y * ldp + i] = b;
         }
-        part[(long long)blockIdx.y * ldp + i] = a;
-        if (part_max) part_max[(long long)blockIdx.y * ldp + i] = b;
     }
 }
 
@@ -128,27 +171,39 @@ __device__ __forceinline__ double squash_tails(double z) {  // g(), :483-487
 
 // X~ = (x - mean)/std  [+ g()];  missing entries take the column mean first (:404, :415, :423).
 // mode: 0 = 'standard', 1 = 'outliers', 2 = 'none' (cast only).  Output fp64, ld = ldo, columns >= n zeroed.
-template <typename T>
+template <typename T, int V>
 __global__ void standardize_kernel(const T* __restrict__ x, long long N, int n, long long ldx, int has_marker,
                                    double marker, int marker_is_nan, int mode, const double* __restrict__ impute,
                                    const double* __restrict__ mean, const double* __restrict__ sd,
                                    double* __restrict__ out, long long ldo) {
-    const int i = blockIdx.y * blockDim.x + threadIdx.x;  // rows on grid.x (up to 2^31-1), column blocks on grid.y
+    const int i0 = (blockIdx.y * blockDim.x + threadIdx.x) * V;  // rows on grid.x (up to 2^31-1), column blocks on grid.y
     const long long r = blockIdx.x;
-    if (i >= ldo || r >= N) return;
-    double o = 0.0;
-    if (i < n) {
-        const T v = x[r * ldx + i];
-        double d = (double)v;
-        if (is_missing(v, has_marker, marker, marker_is_nan)) d = impute[i];
-        if (mode == 2) {
-            o = d;
-        } else {
-            o = (d - mean[i]) / sd[i];
-            if (mode == 1) o = squash_tails(o);
+    if (i0 >= ldo || r >= N) return;
+    double v[V], o[V];
+    if (i0 < n) {
+        load_row_vec<T, V>(x + r * ldx + i0, v);
+    }
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+        const int i = i0 + j;
+        o[j] = 0.0;
+        if (i < n) {
+            double d = v[j];
+            if (is_missing_d(d, has_marker, marker, marker_is_nan)) d = impute[i];
+            if (mode == 2) {
+                o[j] = d;
+            } else {
+                o[j] = (d - mean[i]) / sd[i];
+                if (mode == 1) o[j] = squash_tails(o[j]);
+            }
         }
     }
-    out[r * ldo + i] = o;
+    if constexpr (V == 1) {
+        out[r * ldo + i0] = o[0];
+    } else {  // ldo is a multiple of 16 doubles and i0 of 4: 16-byte stores
+        *reinterpret_cast<double2*>(out + r * ldo + i0) = make_double2(o[0], o[1]);
+        *reinterpret_cast<double2*>(out + r * ldo + i0 + 2) = make_double2(o[2], o[3]);
+    }
 }
 
 }  // namespace lcx
