@@ -337,7 +337,8 @@ def run_ours(args, shape):
                                                         k1.value / max(1, pairs.value), k2.value / max(1, pairs.value), fp64_equiv))
         rl_source = ("2 x bf16_tflops_sustained of MEASURED_PEAKS.json%s (kind::i8 runs at twice the bf16 rate on B200; no int8 "
                      "entry is measured; sustained because the kernel is timed inside a long power-capped step; the burst "
-                     "figure would be 2 x %s); cuBLAS DGEMM in this run: %.1f TFLOP/s"
+                     "figure would be 2 x %s; the int8 pipe alone, fed from shared memory with random operands, measured 3706 "
+                     "TOP/s sustained / 4262 burst on this pool: profiles/r01_i8_peak_probe.txt); cuBLAS DGEMM in this run: %.1f TFLOP/s"
                      % ("" if "bf16_tflops_sustained" in peaks else " [fallback 1400]", peaks.get("bf16_tflops"), dgemm_peak))
     else:
         pair_ops = pair_flops
@@ -456,6 +457,9 @@ def run_ours(args, shape):
                                  "accumulators x 64 columns) fixes the 128 x 64 tile and with it the bytes per MAC "
                                  "(profiles/r01_oz_gemm_ncu_full_config3.csv, DESIGN.md 4)") if digits == 6 else None,
                      "operand_delivery": delivered,
+                     # the kind::i8 pipe alone, operands resident in shared memory, random int8 data (tools/experiments/
+                     # i8_peak_probe.cu, profiles/r01_i8_peak_probe.txt): 4262 TOP/s burst, 3706 sustained under the power cap
+                     "frac_of_measured_i8_pipe_sustained": (achieved / 3705.6) if digits else None,
                      "peak_source": rl_source},
         "clocks": clocks.summary(),
         "e2e": e2e,
