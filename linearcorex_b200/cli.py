@@ -98,8 +98,8 @@ def build_parser():
     group.add_option("-l", "--layers", dest="layers", type="string", default="2,1")
     group.add_option("-w", "--max_iter", action="store", dest="max_iter", type="int", default=10000)
     group.add_option("-a", "--additive", action="store_false", dest="additive", default=True)
-    group.add_option("-p", "--precision", action="store", dest="precision", type="string", default="fp64_split",
-                     help="fp64 (DMMA), fp64_split (int8 digit products on tcgen05, same 1e-9 parity; fp64_split5 / fp64_split7 = "
+    group.add_option("-p", "--precision", action="store", dest="precision", type="string", default="auto",
+                     help="auto (fp64_split, or fp64 for tiny problems), fp64 (DMMA), fp64_split (int8 digit products on tcgen05, same 1e-9 parity; fp64_split5 / fp64_split7 = "
                           "5 / 7 digits) or fast")
     parser.add_option_group(group)
     group = OptionGroup(parser, "Computational Options")

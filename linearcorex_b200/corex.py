@@ -26,6 +26,9 @@ behaviour):
                       default; for ill-conditioned fits (pure-noise data, extreme outliers) that amplify the 48-bit
                       mode's perturbation past 1e-9.
                       'fast': 3 digits (24 bits, fp32-equivalent products; opt-in, 1e-4 tolerance).
+                      'auto' (default): 'fp64_split', except for problems so small (N n m < 3e7: the README demo, big5,
+                      adni) that an iteration is launch-bound -- there 'fp64' (DMMA) has fewer launches and is
+                      10-50 % quicker (tools/small_configs.py).  Both are FP64-faithful; `precision_used` tells which ran.
   exact_trials        False (default): backtracking trials are evaluated through the linearity of
                       `_sig` (rho(W + eta U) = rho(W) + eta _sig(U)) -- one pass pair over X per
                       iteration instead of one per trial.  True: every trial
@@ -182,12 +185,22 @@ class _DeviceSession(object):
         return a[0] if squeeze else a
 
 
+AUTO_SPLIT_MIN_WORK = 3e7  # N n m above which the split-integer tcgen05 contractions beat the DMMA ones (see 'auto')
+
+
+def resolve_precision(precision, n_rows_total, n_vars, n_factors):
+    """'auto' -> 'fp64_split' or, for launch-bound small problems, 'fp64'; anything else passes through."""
+    if precision != 'auto':
+        return precision
+    return 'fp64_split' if float(n_rows_total) * float(n_vars) * float(n_factors) >= AUTO_SPLIT_MIN_WORK else 'fp64'
+
+
 class Corex(object):
     """Linear Total Correlation Explanation on B200 (see module docstring)."""
 
     def __init__(self, n_hidden=10, max_iter=10000, tol=1e-5, anneal=True, missing_values=None,
                  discourage_overlap=True, gaussianize='standard', gpu=True, verbose=False, seed=None,
-                 eliminate_synergy=None, precision='fp64_split', exact_trials=False, input_dtype='float64',
+                 eliminate_synergy=None, precision='auto', exact_trials=False, input_dtype='float64',
                  comm=None, device=None, stream_rows=None):
         self.m = n_hidden
         self.max_iter = max_iter
@@ -204,11 +217,12 @@ class Corex(object):
         if gaussianize not in ('standard', 'outliers', 'none'):
             raise ValueError("gaussianize must be 'standard', 'outliers' or 'none' "
                              "('empirical' is not supported: the reference itself cannot invert it, :425)")
-        if precision not in _lib.PRECISIONS:
-            raise ValueError("precision must be one of %s" % sorted(_lib.PRECISIONS))
+        if precision != 'auto' and precision not in _lib.PRECISIONS:
+            raise ValueError("precision must be 'auto' or one of %s" % sorted(_lib.PRECISIONS))
         if input_dtype not in ('float64', 'float32'):
             raise ValueError("input_dtype must be 'float64' or 'float32'")
         self.precision = precision
+        self.precision_used = None if precision == 'auto' else precision  # 'auto' is resolved when fit sees the shape
         self.exact_trials = bool(exact_trials)
         self.input_dtype = input_dtype
         self.stream_rows = stream_rows  # row-block size of the streamed preparation (None = decide from free memory)
@@ -260,9 +274,16 @@ class Corex(object):
     # ------------------------------------------------------------------------------------------
     # device helpers
     # ------------------------------------------------------------------------------------------
+    def _active_precision(self):
+        return self.precision_used or 'fp64_split'
+
     def _session(self):
+        want = _lib.PRECISIONS[self._active_precision()]
+        if self._sess is not None and self._sess.precision != want:  # 'auto' resolved differently for a new shape
+            self._sess.close()
+            self._sess = None
         if self._sess is None:
-            self._sess = _DeviceSession(_lib.PRECISIONS[self.precision], self._device)
+            self._sess = _DeviceSession(want, self._device)
         return self._sess
 
     def _reducer(self):
@@ -408,11 +429,13 @@ class Corex(object):
 
     def _prepare(self, x):
         """Preprocess, bind the device problem and initialise W (:108-122).  Returns the anneal schedule."""
-        sess = self._session()
-        lib = sess.lib
-        red = self._reducer()
         if self.m is None:
             raise ValueError("n_hidden=None (pick_n_hidden) is not supported: the reference helper is broken (:458-480)")
+        red = self._reducer()
+        if self.precision == 'auto':  # every rank sees the same total, so every rank takes the same path
+            self.precision_used = resolve_precision('auto', red.sum_scalar(int(np.shape(x)[0])), int(np.shape(x)[1]), self.m)
+        sess = self._session()
+        lib = sess.lib
         rows = self._stream_rows_for(x)
         if rows:
             self._prepare_streamed(x, rows, red)
@@ -447,14 +470,14 @@ class Corex(object):
     def _stream_rows_for(self, x):
         """Row-block size for streamed preparation, or 0 for the one-shot path.  Streaming applies to the split modes
         when the fp64 image of X~ would not fit beside its int8 digit planes (or when `stream_rows` forces it)."""
-        if self.precision == 'fp64' or self.gaussianize == 'none':
+        if self._active_precision() == 'fp64' or self.gaussianize == 'none':
             return 0
         if self.stream_rows:
             return int(self.stream_rows)
         torch = _torch()
         n_rows, n_vars = int(np.shape(x)[0]), int(np.shape(x)[1])
         free, _total = torch.cuda.mem_get_info(self._session().device)
-        digits = _lib.SPLIT_DIGITS.get(self.precision, 6)
+        digits = _lib.SPLIT_DIGITS.get(self._active_precision(), 6)
         need = n_rows * self._session().lib.lcx_ld(n_vars) * (8 + digits + 4)
         return 32768 if need > 0.8 * free else 0
 
@@ -801,7 +824,7 @@ class Corex(object):
             return y[:, :self.m]
         y_host = y[:, :self.m].cpu().numpy().copy()
         if details:
-            other = _DeviceSession(_lib.PRECISIONS[self.precision], self._device)
+            other = _DeviceSession(_lib.PRECISIONS[self._active_precision()], self._device)
             red = self._reducer()
             other.bind(xt, int(red.sum_scalar(ns)), nv, self.m, red)
             _lib.check(lib.lcx_set_w(other.h, w.ctypes.data_as(C.c_void_p), nv), "lcx_set_w")

@@ -100,3 +100,18 @@ def test_bench_data_is_row_shardable():
     # planted structure: variables i and i+4 share a parent
     c = np.corrcoef(full[:, 0], full[:, 4])[0, 1]
     assert 0.4 < c < 0.6
+
+
+def test_auto_precision_resolution():
+    """'auto' picks the split-integer tcgen05 path except for launch-bound small problems (N n m < 3e7), where the DMMA
+    path is quicker; explicit modes pass through."""
+    from linearcorex_b200.corex import resolve_precision, AUTO_SPLIT_MIN_WORK
+    assert resolve_precision("auto", 100, 50, 5) == "fp64"                 # README demo
+    assert resolve_precision("auto", 2000, 50, 5) == "fp64"                # big5
+    assert resolve_precision("auto", 566, 200, 30) == "fp64"               # adni
+    assert resolve_precision("auto", 4000, 2000, 20) == "fp64_split"
+    assert resolve_precision("auto", 100000, 10000, 100) == "fp64_split"   # config 3
+    assert resolve_precision("auto", 1000000, 20000, 100) == "fp64_split"  # target (int overflow safe)
+    assert AUTO_SPLIT_MIN_WORK == 3e7
+    for mode in ("fp64", "fp64_split", "fp64_split5", "fp64_split7", "fast"):
+        assert resolve_precision(mode, 10, 10, 1) == mode

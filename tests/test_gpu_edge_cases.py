@@ -187,3 +187,24 @@ def test_verbose_history_keys(overlap, capsys):
         assert np.all(np.isfinite(mdl.history["TCs"])) and np.any(mdl.history["TCs"])
     quiet = Corex(n_hidden=2, discourage_overlap=overlap, **BUDGET).fit(x)
     assert sorted(quiet.history) == ["TC"] and np.array_equal(quiet.ws, mdl.ws)
+
+
+def test_default_precision_is_auto():
+    """Default `precision='auto'`: DMMA for launch-bound small problems, the split-integer path otherwise; a refit of the
+    same object on a larger problem switches sessions."""
+    import corex_oracle as oc
+    from linearcorex_b200 import Corex
+    small = _data((200, 12))
+    mdl = Corex(n_hidden=3, **BUDGET)
+    assert mdl.precision == "auto" and mdl.precision_used is None
+    mdl.fit(small)
+    assert mdl.precision_used == "fp64" and mdl._sess.xt is not None
+    ref = oc.OracleCorex(work_dtype=np.float64, n_hidden=3, **BUDGET).fit(small)
+    _same_fit(mdl, ref, 1e-9)
+    big = oc.latent_factor_data(4000, 2000, 20, seed=1, snr=1.0, snr_spread=0.2)
+    mdl2 = Corex(n_hidden=20, **dict(BUDGET, max_iter=2)).fit(big)
+    assert mdl2.precision_used == "fp64_split" and mdl2._sess.xt is None
+    mdl.m = 20
+    mdl.ws = np.zeros((0, 0))
+    mdl.fit(big)  # same object, new shape: 'auto' resolves again and the session is rebuilt
+    assert mdl.precision_used == "fp64_split"
