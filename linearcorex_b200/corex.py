@@ -180,9 +180,12 @@ class _DeviceSession(object):
         flat = self.ws[off.value: off.value + rows.value * ld.value]
         return flat.view(rows.value, ld.value)[:, :cols.value]
 
-    def host(self, array_id, which=0, squeeze=False):
-        a = self.view(array_id, which).cpu().numpy().copy()
-        return a[0] if squeeze else a
+    def host(self, array_id, which=0, squeeze=False, transpose=False):
+        """Host copy of an exported array (`transpose=True`: turned around on the device first, so the host receives the
+        reference's n x m layout of `X_i Y_j` / `X_i Z_j` without a strided numpy copy)."""
+        v = self.view(array_id, which)
+        a = (v.t().contiguous() if transpose else v).cpu().numpy()  # .cpu() already owns fresh memory
+        return a[0].copy() if squeeze else a
 
 
 AUTO_SPLIT_MIN_WORK = 3e7  # N n m above which the split-integer tcgen05 contractions beat the DMMA ones (see 'auto')
@@ -709,8 +712,8 @@ class Corex(object):
             m["Qi-Si^2"] = sess.host(L.A_QISI2, squeeze=True)
             m["TC"] = tc
             m["MI"] = sess.host(L.A_MI)
-            m["X_i Y_j"] = np.ascontiguousarray(sess.host(L.A_XY).T)
-            m["X_i Z_j"] = np.ascontiguousarray(sess.host(L.A_XZ).T)
+            m["X_i Y_j"] = sess.host(L.A_XY, transpose=True)
+            m["X_i Z_j"] = sess.host(L.A_XZ, transpose=True)
             m["X_i^2 | Y"] = sess.host(L.A_X2Y, squeeze=True)
             m["I(Y_j ; X)"] = sess.host(L.A_IYX, squeeze=True)
             m["I(X_i ; Y)"] = sess.host(L.A_IXY, squeeze=True)
@@ -719,7 +722,7 @@ class Corex(object):
             m["TC_direct"] = sess.host(L.A_TCDIRECT, squeeze=True)
             m["additivity"] = float(sc[6])
         else:  # key set of _calculate_moments_syn (:336-373)
-            m["X_i Y_j"] = np.ascontiguousarray(sess.host(L.A_XY).T)
+            m["X_i Y_j"] = sess.host(L.A_XY, transpose=True)
             m["cy"] = sess.host(L.A_CY)
             m["Y_j^2"] = sess.host(L.A_YJ2, squeeze=True)
             m["ry"] = sess.host(L.A_RY)
@@ -730,7 +733,7 @@ class Corex(object):
             m["Qi"] = sess.host(L.A_QISI2, squeeze=True)
             m["Si"] = sess.host(L.A_SI, squeeze=True)
             m["MI"] = sess.host(L.A_MI)
-            m["X_i Z_j"] = np.ascontiguousarray(sess.host(L.A_XZ).T)
+            m["X_i Z_j"] = sess.host(L.A_XZ, transpose=True)
             m["X_i^2 | Y"] = sess.host(L.A_X2Y, squeeze=True)
             m["TCs"] = sess.host(L.A_TCS, squeeze=True)
             m["additivity"] = float(sc[6])
