@@ -58,6 +58,11 @@ enum {
     I_OZV,              //              scales: x(16) | a(ldm) | c(ldm) | y(ldm) | d(ldm)
     I_YSTAT,            //              per-slab column max / sum of squares of Y
     I_AMAX,             //              per-CTA partial max |X~|
+    I_MMA,              // m x m x n products on the int8 engine: row-scaled digit slices of the left operand  [S][m][ld8]
+    I_MMB,              //              row-scaled digit slices of the right operand (K-major, contraction over variables)
+    I_MMC,              //              column-scaled digit slices of the operand contracted over its rows (factors)
+    I_MMQ,              //              row-scaled digit slices of the m x m factor (ry or H)  [S][m][ldm8]
+    I_MMV,              //              scales: col partial max (32 x ld) | col scale (ld) | row scales a, b, q (3 x ldm)
     I_COUNT
 };
 
@@ -79,6 +84,11 @@ struct Layout {
     int ystat_slabs;
     int radix;                   // 128: 7-bit signed digits (|d| <= 64); 254: full int8 range (|d| <= 127)
     int oz_kmax;                 // longest contraction one int32 accumulator group may see: 2^31 / ((R/2)^2 S)
+    // the four m x m x n products of an iteration (ry, Qij, H, H W) on the same int8 engine (large m only)
+    int mm_i8;                   // 0 = DMMA (dgemm_mma.cuh)
+    long long ldm8;              // byte leading dimension of the digit slices of an m x m matrix
+    int mm_splits, mm_chunk;     // split-K over the variables of the m x m outputs
+    int mm_slabs, mm_slab_rows;  // row slabs of the per-column maximum
 };
 
 static int radix_for() {
@@ -94,6 +104,15 @@ static int digits_for(int precision) {
     if (precision == LCX_PRECISION_FP64_SPLIT5) return 5;   // 40 bits
     if (precision == LCX_PRECISION_FP64_SPLIT7) return 7;   // 56 bits: finer than binary64's own 53-bit significand
     return 6;                                               // 48 bits: truncation at the level of binary64 rounding
+}
+// LCX_MM_I8=1 / 0 forces the int8 engine for the m x m x n products on / off; otherwise it is used from m = 384 factors
+// (measured on a B200: m = 500, n = 50 000: direction 3.70 -> 3.19 ms, trial 2.25 -> 1.50 ms; m = 256, n = 8 000: 5 % slower --
+// the products grow with m^2 n, the extra digit slicing with m n).
+static int mm_i8_for(int S, int n, int m) {
+    if (S <= 0 || round_up(m, 64) > (1 << 14)) return 0;
+    const char* env = getenv("LCX_MM_I8");
+    if (env) return atoi(env) != 0;
+    return m >= 384 && n >= 2048;
 }
 constexpr int kYStatRows = 512;
 constexpr int kAmaxCtas = 592;
@@ -228,6 +247,35 @@ static Layout make_layout(long long Nl, int n, int m, int precision) {
         put1(I_AS, 1, as8, as8);
         put1(I_YS, 1, ys8, ys8);
         put1(I_AMAX, 1, kAmaxCtas, kAmaxCtas);
+        L.mm_i8 = mm_i8_for(L.S, n, m);
+        if (L.mm_i8) {
+            L.ldm8 = round_up(m, 128);
+            {   // m x m outputs, contraction over the variables: split to fill the SMs, never beyond the int32-exact length
+                const long long tiles_mm = (long long)cdiv(m, oz::kBM) * cdiv(m, oz::bn_max(L.S));
+                const int kblocks_mm = cdiv(n, oz::kBK);
+                const int smin_mm = cdiv(n, L.oz_kmax);
+                int bmm = smin_mm;
+                double cbest = 1e300;
+                for (int sp = smin_mm; sp <= max(smin_mm, min(64, kblocks_mm / 8)); ++sp) {
+                    const long long waves = (tiles_mm * sp + kSMs - 1) / kSMs;
+                    const double cost = (double)waves * (ceil((double)kblocks_mm / sp) + 16.0) + 1.5 * sp;
+                    if (cost < cbest - 1e-9) { cbest = cost; bmm = sp; }
+                }
+                L.mm_chunk = (int)round_up(cdiv(n, bmm), oz::kBK);
+                L.mm_splits = cdiv(n, L.mm_chunk);
+            }
+            L.mm_slabs = (int)min(32LL, (long long)cdiv(m, 8));
+            L.mm_slab_rows = cdiv(m, L.mm_slabs);
+            const long long need = (long long)L.mm_splits * mn * L.ldm;
+            if (need > L.slot[I_PART][0].cols) put1(I_PART, 1, need, need);
+            const long long pl8 = ((long long)L.S * mn * L.ld8 + 7) / 8;
+            const long long q8 = ((long long)L.S * mn * L.ldm8 + 7) / 8;
+            put1(I_MMA, 1, pl8, pl8);
+            put1(I_MMB, 1, pl8, pl8);
+            put1(I_MMC, 1, pl8, pl8);
+            put1(I_MMQ, 1, q8, q8);
+            put1(I_MMV, 1, 33 * L.ld + 3 * L.ldm, 33 * L.ld + 3 * L.ldm);
+        }
     }
     L.total = cur;
     return L;
@@ -260,6 +308,17 @@ struct lcx_session {
     // split-integer modes: TMA descriptors over the digit slices
     CUtensorMap map_x_k1, map_a_k1, map_a_k1_tail, map_x_k2, map_y_k2, map_y_k2_tail;
     int oz_bn_tail;   // width of the last factor tile of the first contraction (multiple of 16)
+    // m x m x n products on the int8 engine (L.mm_i8)
+    CUtensorMap map_mm_a, map_mm_b, map_mm_b_tail, map_mn_c, map_mn_q, map_mn_q_tail;
+    int8_t* mma() const { return (int8_t*)(ws + L.slot[I_MMA][0].off); }
+    int8_t* mmb() const { return (int8_t*)(ws + L.slot[I_MMB][0].off); }
+    int8_t* mmc() const { return (int8_t*)(ws + L.slot[I_MMC][0].off); }
+    int8_t* mmq() const { return (int8_t*)(ws + L.slot[I_MMQ][0].off); }
+    double* mm_colpart() const { return ws + L.slot[I_MMV][0].off; }
+    double* mm_colscale() const { return ws + L.slot[I_MMV][0].off + 32 * L.ld; }
+    double* mm_scale_a() const { return ws + L.slot[I_MMV][0].off + 33 * L.ld; }
+    double* mm_scale_b() const { return ws + L.slot[I_MMV][0].off + 33 * L.ld + L.ldm; }
+    double* mm_scale_q() const { return ws + L.slot[I_MMV][0].off + 33 * L.ld + 2 * L.ldm; }
     int8_t* xs() const { return (int8_t*)(ws + L.slot[I_XS][0].off); }
     int8_t* as() const { return (int8_t*)(ws + L.slot[I_AS][0].off); }
     int8_t* ys() const { return (int8_t*)(ws + L.slot[I_YS][0].off); }
@@ -454,6 +513,19 @@ static int oz_prepare(lcx_session* s, bool streamed) {
     LCX_TRY(oz::make_slice_map(&s->map_y_k2, s->ys(), s->Nl, s->m, L.S, L.ldk8, (long long)s->m * L.ldk8, oz::kBK, bnm, false));
     LCX_TRY(oz::make_slice_map(&s->map_y_k2_tail, s->ys(), s->Nl, s->m, L.S, L.ldk8, (long long)s->m * L.ldk8, oz::kBK,
                                s->oz_bn_tail, false));
+    if (L.mm_i8) {
+        LCX_REQUIRE(L.mm_chunk <= L.oz_kmax && round_up(s->m, oz::kBK) <= L.oz_kmax, "contraction chunk exceeds the int32-exact length");
+        const long long st_n = (long long)s->m * L.ld8, st_q = (long long)s->m * L.ldm8;
+        // ry = W rho^T, H = T rinv^T: both operands K-major over the variables (M side 128-row boxes, N side bn-row boxes)
+        LCX_TRY(oz::make_slice_map(&s->map_mm_a, s->mma(), s->n, s->m, L.S, L.ld8, st_n, oz::kBK, oz::kBM, false));
+        LCX_TRY(oz::make_slice_map(&s->map_mm_b, s->mmb(), s->n, s->m, L.S, L.ld8, st_n, oz::kBK, bnm, false));
+        LCX_TRY(oz::make_slice_map(&s->map_mm_b_tail, s->mmb(), s->n, s->m, L.S, L.ld8, st_n, oz::kBK, s->oz_bn_tail, false));
+        // Qij = ry rinv, grad += H W: M side = variables of the m x n operand (MN-major, contraction over its m rows),
+        // N side = the m x m factor, K-major
+        LCX_TRY(oz::make_slice_map(&s->map_mn_c, s->mmc(), s->n, s->m, L.S, L.ld8, st_n, oz::kBM, oz::kBK, true));
+        LCX_TRY(oz::make_slice_map(&s->map_mn_q, s->mmq(), s->m, s->m, L.S, L.ldm8, st_q, oz::kBK, bnm, false));
+        LCX_TRY(oz::make_slice_map(&s->map_mn_q_tail, s->mmq(), s->m, s->m, L.S, L.ldm8, st_q, oz::kBK, s->oz_bn_tail, false));
+    }
     return 0;
 }
 
@@ -541,6 +613,112 @@ static int oz_pair(lcx_session* s, const double* A, double* svec, cudaEvent_t* e
         case 7: return oz_pair_t<7>(s, A, svec, ev, first_only, want_tail);
     }
     return fail(LCX_ERR_STATE, "oz_pair", "bad digit count");
+}
+
+// ---- the m x m x n products of an iteration on the int8 engine (L.mm_i8; same kernel, same digit scheme) ----------
+// out (m x m) = left right^T over the variables, both m x n: each operand gets one exponent per factor row; split-K
+// partials are combined in fixed order and np.fill_diagonal is applied there (raw diagonal -> diag_out).
+template <int S>
+static int oz_square_t(lcx_session* s, const double* left, const double* right, double* out, double diag_value,
+                       double* diag_out) {
+    const Layout& L = s->L;
+    const int m = s->m, n = s->n;
+    const dim3 gs(m, cdiv(L.ld8, 4 * 128));
+    const long long st_n = (long long)m * L.ld8;
+    oz::row_scale_kernel<<<m, 256, 0, s->stream>>>(left, L.ld, n, s->mm_scale_a());
+    LAUNCHED(s);
+    oz::slice_rows_kernel<S><<<gs, 128, 0, s->stream>>>(left, L.ld, m, n, s->mm_scale_a(), nullptr, s->mma(), L.ld8, st_n,
+                                                       (double)L.radix);
+    LAUNCHED(s);
+    oz::row_scale_kernel<<<m, 256, 0, s->stream>>>(right, L.ld, n, s->mm_scale_b());
+    LAUNCHED(s);
+    oz::slice_rows_kernel<S><<<gs, 128, 0, s->stream>>>(right, L.ld, m, n, s->mm_scale_b(), nullptr, s->mmb(), L.ld8, st_n,
+                                                       (double)L.radix);
+    LAUNCHED(s);
+    oz::GemmParams p;
+    memset(&p, 0, sizeof(p));
+    const long long out_count = (long long)m * L.ldm;
+    p.C = s->ptr(I_PART);
+    p.ldc = L.ldm; p.c_split_stride = out_count;
+    p.row_scale = s->mm_scale_a();
+    p.col_scale = s->mm_scale_b();
+    p.inv_radix = 1.0 / (double)L.radix;
+    p.rows = m; p.cols = m; p.k_total = n; p.k_chunk = L.mm_chunk;
+    p.bn_tail = s->oz_bn_tail;
+    LCX_TRY((oz::launch_oz_gemm<S, true>(s->map_mm_a, s->map_mm_b, s->map_mm_b_tail, p,
+                                         dim3(cdiv(m, oz::bn_max(S)), cdiv(m, oz::kBM), L.mm_splits), s->stream, oz_cluster())));
+    LAUNCHED(s);
+    LCX_TRY(launch_reduce_splits(s->ptr(I_PART), L.mm_splits, out_count, out, m, m, L.ldm, s->stream,
+                                 diag_out ? diag_out : s->ptr(I_F), diag_value));
+    LAUNCHED(s);
+    LCX_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// out (m x n, factor-major) = c_add + Q V with Q m x m and V m x n: the contraction runs over V's rows, so V gets one
+// exponent per COLUMN (variable) and Q one per row; tiles of 128 variables x 64 factors like the second X contraction.
+// unit_diag: Q has an exact unit diagonal (ry after np.fill_diagonal, :263).  Its digits would be spent on that 1 while the
+// off-diagonal correlations are 1e-2 and below, so the product runs on Q - I and the caller passes c_add = V.
+template <int S>
+static int oz_mn_t(lcx_session* s, const double* Q, const double* V, double* out, const double* c_add, bool unit_diag) {
+    const Layout& L = s->L;
+    const int m = s->m, n = s->n;
+    oz::col_absmax_partial_kernel<<<dim3(cdiv(n, 512), L.mm_slabs), 256, 0, s->stream>>>(V, L.ld, m, n, L.mm_slab_rows,
+                                                                                       s->mm_colpart(), L.ld);
+    LAUNCHED(s);
+    oz::col_scale_finish_kernel<<<cdiv(n, 256), 256, 0, s->stream>>>(s->mm_colpart(), L.mm_slabs, L.ld, n, s->mm_colscale());
+    LAUNCHED(s);
+    oz::slice_colscaled_kernel<S><<<dim3(m, cdiv(L.ld8, 4 * 128)), 128, 0, s->stream>>>(V, L.ld, m, n, s->mm_colscale(), s->mmc(),
+                                                                                      L.ld8, (long long)m * L.ld8, (double)L.radix);
+    LAUNCHED(s);
+    oz::row_scale_kernel<<<m, 256, 0, s->stream>>>(Q, L.ldm, m, s->mm_scale_q(), unit_diag ? 1 : 0);
+    LAUNCHED(s);
+    const dim3 gq(m, cdiv(L.ldm8, 4 * 128));
+    if (unit_diag)
+        oz::slice_rows_kernel<S, true><<<gq, 128, 0, s->stream>>>(Q, L.ldm, m, m, s->mm_scale_q(), nullptr, s->mmq(), L.ldm8,
+                                                                 (long long)m * L.ldm8, (double)L.radix);
+    else
+        oz::slice_rows_kernel<S><<<gq, 128, 0, s->stream>>>(Q, L.ldm, m, m, s->mm_scale_q(), nullptr, s->mmq(), L.ldm8,
+                                                           (long long)m * L.ldm8, (double)L.radix);
+    LAUNCHED(s);
+    oz::GemmParams p;
+    memset(&p, 0, sizeof(p));
+    p.C = out;
+    p.ldc = L.ld; p.c_split_stride = 0;
+    p.row_scale = s->mm_colscale();
+    p.col_scale = s->mm_scale_q();
+    p.inv_radix = 1.0 / (double)L.radix;
+    p.rows = n; p.cols = m; p.k_total = m; p.k_chunk = (int)round_up(m, oz::kBK);
+    p.bn_tail = s->oz_bn_tail;
+    p.trans_out = 1;
+    p.c_add = c_add;
+    LCX_TRY((oz::launch_oz_gemm<S, false, true>(s->map_mn_c, s->map_mn_q, s->map_mn_q_tail, p,
+                                          dim3(cdiv(m, oz::bn_max(S)), cdiv(n, oz::kBM), 1), s->stream, oz_cluster())));
+    LAUNCHED(s);
+    LCX_CUDA(cudaGetLastError());
+    return 0;
+}
+
+static int oz_square(lcx_session* s, const double* left, const double* right, double* out, double diag_value, double* diag_out) {
+    switch (s->L.S) {
+        case 3: return oz_square_t<3>(s, left, right, out, diag_value, diag_out);
+        case 4: return oz_square_t<4>(s, left, right, out, diag_value, diag_out);
+        case 5: return oz_square_t<5>(s, left, right, out, diag_value, diag_out);
+        case 6: return oz_square_t<6>(s, left, right, out, diag_value, diag_out);
+        case 7: return oz_square_t<7>(s, left, right, out, diag_value, diag_out);
+    }
+    return fail(LCX_ERR_STATE, "oz_square", "bad digit count");
+}
+
+static int oz_mn(lcx_session* s, const double* Q, const double* V, double* out, const double* c_add, bool unit_diag) {
+    switch (s->L.S) {
+        case 3: return oz_mn_t<3>(s, Q, V, out, c_add, unit_diag);
+        case 4: return oz_mn_t<4>(s, Q, V, out, c_add, unit_diag);
+        case 5: return oz_mn_t<5>(s, Q, V, out, c_add, unit_diag);
+        case 6: return oz_mn_t<6>(s, Q, V, out, c_add, unit_diag);
+        case 7: return oz_mn_t<7>(s, Q, V, out, c_add, unit_diag);
+    }
+    return fail(LCX_ERR_STATE, "oz_mn", "bad digit count");
 }
 
 extern "C" int lcx_bind(lcx_session* s, const double* xt, long long n_rows_local, long long n_rows_total, int n_vars,
@@ -957,6 +1135,10 @@ static int moments_tail(lcx_session* s, int set, double c1, double e2, int uj_mo
     double* rinv = s->ptr(LCX_A_RHOINVRHO, set);
     double* ry = s->ptr(LCX_A_RY, set);
     double* Qij = s->ptr(LCX_A_QIJ, set);
+    if (L.mm_i8) {  // both products as exact int8 digit-plane products on tcgen05
+        LCX_TRY(oz_square(s, W, rho, ry, 1.0, s->ptr(I_UJDIAG)));
+        LCX_TRY(oz_mn(s, ry, rinv, Qij, rinv, true));  // Qij = rinv + (ry - I) rinv
+    } else {
     {   // ry = W rho^T  (:261), diag -> 1 (:263); the diagonal before the fill is uj by linearity
         GemmArgs a;
         memset(&a, 0, sizeof(a));
@@ -972,6 +1154,7 @@ static int moments_tail(lcx_session* s, int set, double c1, double e2, int uj_mo
         a.M = m; a.N = n; a.K = m;
         a.lda = L.ldm; a.ldb = L.ld; a.ldc = L.ld;
         LCX_TRY(run_gemm(s, kLayoutKN, L.plan_mn, a, nullptr, 0));
+    }
     }
     moments_stage2_kernel<<<L.nstrips, dim3(kStripCols, kStripRows), 0, s->stream>>>(
         rho, rinv, Qij, s->ptr(LCX_A_SI, set), s->ptr(LCX_A_QISI2, set), s->ptr(I_SPART), m, n, L.ld);
@@ -1138,6 +1321,10 @@ static int enqueue_direction(lcx_session* s, double eps) {
                                                                 s->ptr(LCX_A_SI), s->ptr(LCX_A_QISI2), s->ptr(LCX_A_UJ), T, G,
                                                                 m, n, L.ld);
     LAUNCHED(s);
+    if (L.mm_i8) {
+        LCX_TRY(oz_square(s, T, rinv, H, 0.0, nullptr));  // H = T rinv^T, diag -> 0 (:294-295)
+        LCX_TRY(oz_mn(s, H, W, G, G, false));             // grad = G0 + H W (:300)
+    } else {
     {   // H = T rinv^T, diag -> 0 (:294-295)
         GemmArgs a;
         memset(&a, 0, sizeof(a));
@@ -1153,6 +1340,7 @@ static int enqueue_direction(lcx_session* s, double eps) {
         a.M = m; a.N = n; a.K = m;
         a.lda = L.ldm; a.ldb = L.ld; a.ldc = L.ld;
         LCX_TRY(run_gemm(s, kLayoutKN, L.plan_mn, a, nullptr, 0));
+    }
     }
     LCX_TRY(xpair(s, G, false));  // X~^T (X~ grad^T): the one pass over X of this iteration (:301)
     row_dot_kernel<<<m, 256, 0, s->stream>>>(rho, G, s->ptr(I_BJ), n, L.ld);  // Bj (:302)

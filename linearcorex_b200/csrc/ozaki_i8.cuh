@@ -161,6 +161,8 @@ struct GemmParams {
     int bn_tail;                 // width (multiple of 16, <= bn_max(S)) of the LAST N tile, loaded through mapBt;
                                  // 0 or bn_max = full width.  m = 100 factors, S = 6 -> tiles of 64 + 48 instead of 64 + 64
     int trans_out;               // 1: store C[col][row] (the second contraction writes (X~^T Y)^T factor-major)
+    const double* c_add;         // optional (with trans_out, no split): C = c_add + product, c_add laid out like C (may be C
+                                 // itself: grad = G0 + H W, linearcorex.py:300; Qij = rinv + (ry - I) rinv, :266)
 };
 
 // The N-side (factor) operand is always K-major: B tile = [64 rows][64 B of K] (SW64), tensor map (K, rows, slice),
@@ -199,7 +201,9 @@ __device__ __forceinline__ void issue_kblock(uint32_t sa, uint32_t sb, uint32_t 
 // multicasts them into every CTA of the cluster, which divides the L2 -> SM traffic of that operand by CL (the kernel
 // ran at the L2 throughput cap without it: 18 GB per launch at config 3).  A stage is released to the producers only
 // when every CTA of the cluster has finished reading it (multicast tcgen05.commit on all empty barriers).
-template <int S, bool KMAJOR, int CL>
+// CADD: the epilogue adds p.c_add (transposed stores only).  Its values are fetched one 16-column chunk ahead -- the first
+// chunk while the MMAs are still running -- so the global-load latency is not paid once per column by a single resident CTA.
+template <int S, bool KMAJOR, int CL, bool CADD = false>
 __global__ void __launch_bounds__(kThreads, 1)
 oz_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                const __grid_constant__ CUtensorMap mapBt, const GemmParams p) {
@@ -314,6 +318,15 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         const int quarter = warp & 3;              // TMEM lane quarter this warp may read
         const int row_in_tile = quarter * 32 + lane;
         const int row = m_tile * kBM + row_in_tile;
+        double cadd[16];
+        auto fetch_cadd = [&](int c0) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const int col = n_tile * kBN + c0 + j;
+                cadd[j] = (row < p.rows && col < p.cols) ? p.c_add[(long long)col * p.ldc + row] : 0.0;
+            }
+        };
+        if (CADD) fetch_cadd(0);
         mbar_wait(&tmem_full_bar, 0);
         tc_fence_after();
         double* C = p.C + (long long)blockIdx.z * p.c_split_stride;
@@ -322,6 +335,12 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 #pragma unroll 1
         for (int c0 = 0; c0 < bn; c0 += 16) {
             double acc[16];
+            double cur[16];
+            if (CADD) {  // this chunk's addends are in registers; request the next chunk's before touching TMEM
+#pragma unroll
+                for (int j = 0; j < 16; ++j) cur[j] = cadd[j];
+                if (c0 + 16 < bn) fetch_cadd(c0 + 16);
+            }
             if (num_kb > 0) {
                 uint32_t r[16];
                 tmem_ld16(lane_addr + (uint32_t)((S - 1) * bn + c0), r);
@@ -351,6 +370,10 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                         if (col + 1 < p.cols) v1 *= p.col_scale[col + 1];
                     }
                     if (p.trans_out) {  // a warp's 32 rows are 32 consecutive doubles of one output row: coalesced
+                        if (CADD) {
+                            v0 += cur[j];
+                            v1 += cur[j + 1];
+                        }
                         if (col < p.cols) C[(long long)col * p.ldc + row] = v0;
                         if (col + 1 < p.cols) C[(long long)(col + 1) * p.ldc + row] = v1;
                     } else if (col + 1 < p.cols) {
@@ -398,7 +421,8 @@ __device__ __forceinline__ double pow2_above(double amax) {
 
 // Slices of a row-major fp64 matrix [rows][ld_in] into out[s][rows][ld_out] (int8), one scale per row
 // (row_scale != nullptr: value 2^E_row) or a single scale.  Columns in [cols, ld_out) are zero-filled.
-template <int S>
+// ZERO_DIAG: the diagonal entry of each row is taken as 0 (the unit diagonal of ry is added back exactly by the consumer).
+template <int S, bool ZERO_DIAG = false>
 __global__ void slice_rows_kernel(const double* __restrict__ in, long long ld_in, int rows, int cols,
                                   const double* __restrict__ row_scale, const double* __restrict__ one_scale,
                                   int8_t* __restrict__ out, long long ld_out, long long slice_stride, double radix) {
@@ -410,7 +434,7 @@ __global__ void slice_rows_kernel(const double* __restrict__ in, long long ld_in
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         const int c = c4 + j;
-        const double x = (c < cols) ? in[r * ld_in + c] : 0.0;
+        const double x = (c < cols && !(ZERO_DIAG && c == r)) ? in[r * ld_in + c] : 0.0;
         split_digits<S>(x, inv, radix, d[j]);
     }
 #pragma unroll
@@ -459,13 +483,97 @@ __global__ void __launch_bounds__(256) slice_cols_t_kernel(const double* __restr
 }
 
 // max |a[r][c]| over a row (one CTA of 256 threads per row) -> scale[r] = 2^E;  used for A (W or grad).
-__global__ void row_scale_kernel(const double* __restrict__ a, long long ld, int cols, double* __restrict__ scale) {
+// skip_diag: leave a[r][r] out of the maximum (square matrices sliced with ZERO_DIAG).
+__global__ void row_scale_kernel(const double* __restrict__ a, long long ld, int cols, double* __restrict__ scale,
+                                 int skip_diag = 0) {
     __shared__ double scratch[8];
     const double* ra = a + (long long)blockIdx.x * ld;
     double mx = 0.0;
-    for (int i = threadIdx.x; i < cols; i += 256) mx = lcx::amax_acc(mx, ra[i]);
+    if (skip_diag || ((uintptr_t)ra & 15) != 0) {
+        for (int i = threadIdx.x; i < cols; i += 256)
+            if (!(skip_diag && i == (int)blockIdx.x)) mx = lcx::amax_acc(mx, ra[i]);
+    } else {  // 16-byte loads, eight values in flight per thread (a row of W is 400 KB at n = 50 000)
+        const double2* ra2 = reinterpret_cast<const double2*>(ra);
+        const int pairs = cols >> 1;
+        double m1 = 0.0, m2 = 0.0, m3 = 0.0;
+        int i = threadIdx.x;
+        for (; i + 768 < pairs; i += 1024) {
+            const double2 v0 = ra2[i], v1 = ra2[i + 256], v2 = ra2[i + 512], v3 = ra2[i + 768];
+            mx = lcx::amax_acc(lcx::amax_acc(mx, v0.x), v0.y);
+            m1 = lcx::amax_acc(lcx::amax_acc(m1, v1.x), v1.y);
+            m2 = lcx::amax_acc(lcx::amax_acc(m2, v2.x), v2.y);
+            m3 = lcx::amax_acc(lcx::amax_acc(m3, v3.x), v3.y);
+        }
+        for (; i < pairs; i += 256) {
+            const double2 v = ra2[i];
+            mx = lcx::amax_acc(lcx::amax_acc(mx, v.x), v.y);
+        }
+        if ((cols & 1) && threadIdx.x == 0) mx = lcx::amax_acc(mx, ra[cols - 1]);
+        mx = fmax(fmax(mx, m1), fmax(m2, m3));
+    }
     mx = block_max_256(mx, scratch);
     if (threadIdx.x == 0) scale[blockIdx.x] = pow2_above(mx);
+}
+
+// ---- per-COLUMN scales (the m x m x n products on the int8 engine: an operand contracted over its rows needs an
+// exponent that is constant along the contraction, i.e. one per column) ----
+// part[slab][c] = max |a[r][c]| over the rows of one slab (columns across threads: coalesced; four loads in flight)
+__global__ void __launch_bounds__(256) col_absmax_partial_kernel(const double* __restrict__ a, long long ld, int rows, int cols,
+                                                                 int rows_per_slab, double* __restrict__ part, long long ldp) {
+    // two columns per thread (16-byte loads; ld is a multiple of 16 so the pair never leaves the row), four rows in flight
+    const int c = (blockIdx.x * 256 + threadIdx.x) * 2;
+    if (c >= cols) return;
+    const int r0 = blockIdx.y * rows_per_slab;
+    const int r1 = min(rows, r0 + rows_per_slab);
+    double x0 = 0.0, x1 = 0.0, x2 = 0.0, x3 = 0.0, y0 = 0.0, y1 = 0.0, y2 = 0.0, y3 = 0.0;
+    int r = r0;
+    for (; r + 3 < r1; r += 4) {
+        const double2 v0 = *reinterpret_cast<const double2*>(a + (long long)r * ld + c);
+        const double2 v1 = *reinterpret_cast<const double2*>(a + (long long)(r + 1) * ld + c);
+        const double2 v2 = *reinterpret_cast<const double2*>(a + (long long)(r + 2) * ld + c);
+        const double2 v3 = *reinterpret_cast<const double2*>(a + (long long)(r + 3) * ld + c);
+        x0 = lcx::amax_acc(x0, v0.x); y0 = lcx::amax_acc(y0, v0.y);
+        x1 = lcx::amax_acc(x1, v1.x); y1 = lcx::amax_acc(y1, v1.y);
+        x2 = lcx::amax_acc(x2, v2.x); y2 = lcx::amax_acc(y2, v2.y);
+        x3 = lcx::amax_acc(x3, v3.x); y3 = lcx::amax_acc(y3, v3.y);
+    }
+    for (; r < r1; ++r) {
+        const double2 v = *reinterpret_cast<const double2*>(a + (long long)r * ld + c);
+        x0 = lcx::amax_acc(x0, v.x); y0 = lcx::amax_acc(y0, v.y);
+    }
+    part[(long long)blockIdx.y * ldp + c] = fmax(fmax(x0, x1), fmax(x2, x3));
+    if (c + 1 < cols) part[(long long)blockIdx.y * ldp + c + 1] = fmax(fmax(y0, y1), fmax(y2, y3));
+}
+// scale[c] = 2^E above the column maximum
+__global__ void col_scale_finish_kernel(const double* __restrict__ part, int slabs, long long ldp, int cols,
+                                        double* __restrict__ scale) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= cols) return;
+    double mx = 0.0;
+    for (int s = 0; s < slabs; ++s) mx = fmax(mx, part[(long long)s * ldp + c]);
+    scale[c] = pow2_above(mx);
+}
+// slice_rows_kernel with one scale per COLUMN: out[s][r][c] = digit s of in[r][c] / col_scale[c]
+template <int S>
+__global__ void slice_colscaled_kernel(const double* __restrict__ in, long long ld_in, int rows, int cols,
+                                       const double* __restrict__ col_scale, int8_t* __restrict__ out, long long ld_out,
+                                       long long slice_stride, double radix) {
+    const long long r = blockIdx.x;
+    const int c4 = (blockIdx.y * blockDim.x + threadIdx.x) * 4;
+    if (r >= rows || c4 >= ld_out) return;
+    int8_t d[4][S];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int c = c4 + j;
+        const double x = (c < cols) ? in[r * ld_in + c] : 0.0;
+        const double inv = (c < cols) ? 1.0 / col_scale[c] : 1.0;
+        split_digits<S>(x, inv, radix, d[j]);
+    }
+#pragma unroll
+    for (int k = 0; k < S; ++k) {
+        char4 v = make_char4(d[0][k], d[1][k], d[2][k], d[3][k]);
+        *reinterpret_cast<char4*>(out + (long long)k * slice_stride + r * ld_out + c4) = v;
+    }
 }
 
 // Column statistics of Y (N x ldy): per-slab partial max|Y| and sum Y^2 -> part[slab][2][ldp]
@@ -581,12 +689,12 @@ inline int make_slice_map(CUtensorMap* map, const void* base, long long inner, l
     return 0;
 }
 
-template <int S, bool KMAJOR, int CL>
+template <int S, bool KMAJOR, int CL, bool CADD = false>
 inline int launch_oz_gemm_cl(const CUtensorMap& mapA, const CUtensorMap& mapB, const CUtensorMap& mapBt, GemmParams p, dim3 grid,
                              cudaStream_t st) {
     constexpr int SMEM = stages_for(S) * S * (kBM * kBK + bn_max(S) * kBK) + 1024;
     static bool configured = false;
-    auto kern = oz_gemm_kernel<S, KMAJOR, CL>;
+    auto kern = oz_gemm_kernel<S, KMAJOR, CL, CADD>;
     if (!configured) {
         LCX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
         configured = true;
@@ -613,25 +721,26 @@ inline int launch_oz_gemm_cl(const CUtensorMap& mapA, const CUtensorMap& mapB, c
 // cluster = how many N tiles share the M-side operand through TMA multicast (1, 2 or 4; default 2).  A padded cluster
 // slot would occupy an SM for the whole K loop and take a full copy of the X~ tile for nothing, so an odd tile count
 // under pairs runs as pairs plus one final cluster of three (m = 192: 3 tiles in 5.9 ms instead of 7.0 ms).
-template <int S, bool KMAJOR>
+template <int S, bool KMAJOR, bool CADD = false>
 inline int launch_oz_gemm(const CUtensorMap& mapA, const CUtensorMap& mapB, const CUtensorMap& mapBt, GemmParams p,
                           dim3 grid, cudaStream_t st, int cluster) {
     const int n_tiles = (int)grid.x;
     p.n_tiles = n_tiles;
     p.n_tile0 = 0;
-    if (cluster >= 4 && n_tiles >= 4) return launch_oz_gemm_cl<S, KMAJOR, 4>(mapA, mapB, mapBt, p, grid, st);
+    if (CADD) cluster = cluster > 2 ? 2 : cluster;  // (the c_add variant is built for clusters of 1, 2 and 3 only)
+    if (!CADD && cluster >= 4 && n_tiles >= 4) return launch_oz_gemm_cl<S, KMAJOR, 4, false>(mapA, mapB, mapBt, p, grid, st);
     if (cluster >= 2 && n_tiles >= 2) {
-        if (n_tiles % 2 == 0) return launch_oz_gemm_cl<S, KMAJOR, 2>(mapA, mapB, mapBt, p, grid, st);
+        if (n_tiles % 2 == 0) return launch_oz_gemm_cl<S, KMAJOR, 2, CADD>(mapA, mapB, mapBt, p, grid, st);
         if (n_tiles > 3) {
             grid.x = (unsigned)(n_tiles - 3);
-            const int rc = launch_oz_gemm_cl<S, KMAJOR, 2>(mapA, mapB, mapBt, p, grid, st);
+            const int rc = launch_oz_gemm_cl<S, KMAJOR, 2, CADD>(mapA, mapB, mapBt, p, grid, st);
             if (rc != 0) return rc;
         }
         p.n_tile0 = n_tiles - 3;
         grid.x = 3;
-        return launch_oz_gemm_cl<S, KMAJOR, 3>(mapA, mapB, mapBt, p, grid, st);
+        return launch_oz_gemm_cl<S, KMAJOR, 3, CADD>(mapA, mapB, mapBt, p, grid, st);
     }
-    return launch_oz_gemm_cl<S, KMAJOR, 1>(mapA, mapB, mapBt, p, grid, st);
+    return launch_oz_gemm_cl<S, KMAJOR, 1, CADD>(mapA, mapB, mapBt, p, grid, st);
 }
 
 }  // namespace oz
