@@ -45,6 +45,32 @@ def test_layout_arithmetic_without_gpu():
     assert lib.lcx_project_scratch_doubles(100000, 100) >= 782 * 104
 
 
+def test_layout_of_the_int8_product_route(monkeypatch):
+    """The m x m x n products move to the int8 engine from m = 384 factors (split modes only): the workspace then also holds
+    three m x n digit-plane operands, the planes of an m x m matrix and the per-column scale scratch."""
+    from linearcorex_b200 import _lib
+    lib = _lib.load()
+    monkeypatch.delenv("LCX_MM_I8", raising=False)
+    N, n, m = 1000, 50000, 500
+    auto = lib.lcx_workspace_doubles(N, n, m, 2)
+    monkeypatch.setenv("LCX_MM_I8", "0")
+    off = lib.lcx_workspace_doubles(N, n, m, 2)
+    monkeypatch.setenv("LCX_MM_I8", "1")
+    on = lib.lcx_workspace_doubles(N, n, m, 2)
+    assert auto == on > off
+    ld8 = (n + 127) // 128 * 128
+    assert on - off >= 3 * 6 * m * ld8 // 8 + 33 * n       # three operand plane sets + column scale scratch
+    assert on - off < 4 * 6 * m * ld8 // 8 + 64 * n + 10 * m * m
+    small_on = lib.lcx_workspace_doubles(100000, 10000, 100, 2)
+    monkeypatch.delenv("LCX_MM_I8")
+    assert lib.lcx_workspace_doubles(100000, 10000, 100, 2) < small_on   # m = 100 stays on DMMA unless forced
+    assert lib.lcx_workspace_doubles(N, 1000, m, 2) == (monkeypatch.setenv("LCX_MM_I8", "0") or
+                                                         lib.lcx_workspace_doubles(N, 1000, m, 2))  # n < 2048: DMMA
+    monkeypatch.setenv("LCX_MM_I8", "1")
+    assert lib.lcx_workspace_doubles(N, n, m, 0) == (monkeypatch.setenv("LCX_MM_I8", "0") or
+                                                      lib.lcx_workspace_doubles(N, n, m, 0))      # DMMA mode ignores it
+
+
 def test_no_cpu_fallback():
     import torch
     if torch.cuda.is_available():

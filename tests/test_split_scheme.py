@@ -78,3 +78,47 @@ def test_radix_254_beats_radix_128_at_equal_cost():
     e254 = np.abs(split_product(x, a, 6, 254)[0] - ref).max()
     e128 = np.abs(split_product(x, a, 6, 128)[0] - ref).max()
     assert e254 * 30 < e128
+
+
+def mn_product(q, v, S, R, unit_diag):
+    """out = Q V (Q m x m, V m x n) the way oz_mn_t in lcx_api.cu runs it: the contraction goes over V's ROWS, so V gets one
+    power-of-two scale per COLUMN and Q one per row; with `unit_diag` the product runs on Q - I and V is added back exactly."""
+    m = q.shape[0]
+    qq = q - np.eye(m) if unit_diag else q
+    sq = np.array([pow2_above(np.abs(r).max()) for r in qq])
+    sv = np.array([pow2_above(np.abs(c).max()) for c in v.T])
+    dq = split_digits(qq, sq[:, None], S, R)
+    dv = split_digits(v, sv[None, :], S, R)
+    groups = [np.zeros((m, v.shape[1]), dtype=np.int64) for _ in range(S)]
+    for k in range(S):
+        for l in range(S - k):
+            groups[k + l] += dq[l] @ dv[k]
+    acc = groups[S - 1].astype(np.float64)
+    for g in range(S - 2, -1, -1):
+        acc = acc / R + groups[g]
+    out = acc / (R * R) * sq[:, None] * sv[None, :]
+    return out + v if unit_diag else out
+
+
+def test_column_scaled_product_and_unit_diagonal():
+    """Qij = ry rinv (linearcorex.py:266) with ry = I + small correlations and rinv spanning orders of magnitude over the
+    variables (rho -> 1 blows rinv up): per-column scales keep every variable at 48 bits, and taking the exact unit
+    diagonal out of ry makes the digits resolve the 1e-2 off-diagonal entries instead of the 1."""
+    rng = np.random.RandomState(3)
+    m, n = 40, 900
+    ry = rng.randn(m, m) * 1e-2
+    ry = (ry + ry.T) / 2
+    np.fill_diagonal(ry, 1.0)
+    rinv = rng.randn(m, n) * 10.0 ** rng.uniform(-3, 2, size=(1, n))     # per-variable magnitude spread
+    ref = ry @ rinv
+    scale = np.abs(ref).max(axis=0)                                      # error measured per variable (column)
+    with_diag = np.abs(mn_product(ry, rinv, 6, 254, False) - ref).max(axis=0) / scale
+    no_diag = np.abs(mn_product(ry, rinv, 6, 254, True) - ref).max(axis=0) / scale
+    assert with_diag.max() < 1e-12
+    assert no_diag.max() < 5e-15
+    assert no_diag.max() * 20 < with_diag.max()
+    # one global scale for V instead of one per column would lose the small-magnitude variables altogether
+    sv = pow2_above(np.abs(rinv).max())
+    coarse = np.rint(rinv / sv * 254.0 ** 6) / 254.0 ** 6 * sv
+    glob = np.abs(ry @ coarse - ref).max(axis=0) / scale
+    assert glob.max() > 1e3 * no_diag.max()
