@@ -1,0 +1,353 @@
+// Host-side state of liblcx_b200.so: workspace layout (every array of a bound problem lives in ONE caller-provided
+// workspace), launch plans, the session handle.  Included by lcx_api.cu only.
+#pragma once
+#include "../../include/lcx_b200.h"
+
+#include <float.h>
+#include <math.h>
+
+#include "common.cuh"
+#include "corex_kernels.cuh"
+#include "dgemm_mma.cuh"
+#include "fused_allreduce.cuh"
+#include "ozaki_i8.cuh"
+#include "preprocess_kernels.cuh"
+
+namespace lcx {
+thread_local char g_err[512] = "";
+constexpr int kSMs = 148;  // B200; plans (and therefore workspace sizes) are fixed for this part
+constexpr int kMaxSplitsX = 32;
+constexpr int kMaxSplitsSmall = 148;
+
+__global__ void axpy_kernel(const double* __restrict__ W, const double* __restrict__ U, double eta, double* __restrict__ W2,
+                            int m, int n, long long ld) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y;
+    if (i < n && j < m) W2[(long long)j * ld + i] = W[(long long)j * ld + i] + eta * U[(long long)j * ld + i];
+}
+
+// out = c1 * D + e2 * u     (_sig, linearcorex.py:212)
+__global__ void sig_finish_kernel(const double* __restrict__ D, const double* __restrict__ u, double c1, double e2,
+                                  double* __restrict__ out, int m, int n, long long ld) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y;
+    if (i < n && j < m) out[(long long)j * ld + i] = c1 * D[(long long)j * ld + i] + e2 * u[(long long)j * ld + i];
+}
+}  // namespace lcx
+
+using namespace lcx;
+
+// internal (non-exported) workspace slots appended after the public enum
+enum {
+    I_T = LCX_A_COUNT,  // m x ld   rinv/(1+Qi-Si^2), also z of get_covariance and R of _update_syn
+    I_PART,             // split-K partials
+    I_COLSQ,            // K1 per-CTA column-sum-of-squares partials
+    I_SPART,            // scalar partials
+    I_W2,               // m   sum_i W^2
+    I_BJ,               // m
+    I_F,                // m   row scale factors
+    I_UJDIAG,           // m   diag(W rho^T)
+    I_ROWMI,            // m
+    I_SQRTY,            // m
+    I_RYINV,            // m x ldm
+    I_AUG,              // m x 2m
+    I_STATUS,           // 2 doubles (int status of the inverse)
+    I_XS,               // split modes: int8 digit slices of X~   [S][N_local][ld8]
+    I_AS,               //              int8 digit slices of A    [S][m][ld8]
+    I_YS,               //              int8 digit slices of Y, transposed  [S][m][ldk8]
+    I_OZV,              //              scales: x(16) | a(ldm) | c(ldm) | y(ldm) | d(ldm)
+    I_YSTAT,            //              per-slab column max / sum of squares of Y
+    I_AMAX,             //              per-CTA partial max |X~|
+    I_MMA,              // m x m x n products on the int8 engine: row-scaled digit slices of the left operand  [S][m][ld8]
+    I_MMB,              //              row-scaled digit slices of the right operand (K-major, contraction over variables)
+    I_MMC,              //              column-scaled digit slices of the operand contracted over its rows (factors)
+    I_MMQ,              //              row-scaled digit slices of the m x m factor (ry or H)  [S][m][ldm8]
+    I_MMV,              //              scales: col partial max (32 x ld) | col scale (ld) | row scales a, b, q (3 x ldm)
+    I_COUNT
+};
+
+struct Slot {
+    long long off, rows, cols, ld;
+};
+
+struct Layout {
+    Slot slot[I_COUNT][2];
+    long long total;
+    long long ld, ldm, ldy;
+    GemmPlan plan_k1, plan_k2, plan_mm, plan_mn;  // K1, K2, (m x m over n), (m x n over m)
+    int nstrips;
+    // split-integer modes (ozaki_i8.cuh)
+    int S;                       // digits per operand, 0 = DMMA mode
+    long long ld8, ldk8;         // byte leading dimensions of the X~/A slices and of the transposed Y slices (samples)
+    int oz_splits, oz_chunk;     // split-K of the second contraction (over samples)
+    int oz1_splits, oz1_chunk;   // split-K of the first contraction (over variables), only when row tiles are scarce
+    int ystat_slabs;
+    int radix;                   // 128: 7-bit signed digits (|d| <= 64); 254: full int8 range (|d| <= 127)
+    int oz_kmax;                 // longest contraction one int32 accumulator group may see: 2^31 / ((R/2)^2 S)
+    // the four m x m x n products of an iteration (ry, Qij, H, H W) on the same int8 engine (large m only)
+    int mm_i8;                   // 0 = DMMA (dgemm_mma.cuh)
+    long long ldm8;              // byte leading dimension of the digit slices of an m x m matrix
+    int mm_splits, mm_chunk;     // split-K over the variables of the m x m outputs
+    int mm_slabs, mm_slab_rows;  // row slabs of the per-column maximum
+};
+
+static int radix_for() {
+    const char* env = getenv("LCX_SPLIT_RADIX");
+    return (env && atoi(env) == 128) ? 128 : 254;  // 254: digits use the full int8 range (measured 100x tighter parity)
+}
+
+static int digits_for(int precision) {
+    if (precision == LCX_PRECISION_FP64) return 0;
+    const char* env = getenv("LCX_SPLIT_DIGITS");
+    if (env && atoi(env) >= 3 && atoi(env) <= 7) return atoi(env);
+    if (precision == LCX_PRECISION_FAST) return 3;          // 24 bits: fp32-equivalent products
+    if (precision == LCX_PRECISION_FP64_SPLIT5) return 5;   // 40 bits
+    if (precision == LCX_PRECISION_FP64_SPLIT7) return 7;   // 56 bits: finer than binary64's own 53-bit significand
+    return 6;                                               // 48 bits: truncation at the level of binary64 rounding
+}
+// LCX_MM_I8=1 / 0 forces the int8 engine for the m x m x n products on / off; otherwise it is used from m = 384 factors
+// (measured on a B200: m = 500, n = 50 000: direction 3.70 -> 3.19 ms, trial 2.25 -> 1.50 ms; m = 256, n = 8 000: 5 % slower --
+// the products grow with m^2 n, the extra digit slicing with m n).
+static int mm_i8_for(int S, int n, int m) {
+    if (S <= 0 || round_up(m, 64) > (1 << 14)) return 0;
+    const char* env = getenv("LCX_MM_I8");
+    if (env) return atoi(env) != 0;
+    return m >= 384 && n >= 2048;
+}
+constexpr int kYStatRows = 512;
+constexpr int kAmaxCtas = 592;
+
+static long long align16(long long v) { return round_up(v, 16); }
+
+static Layout make_layout(long long Nl, int n, int m, int precision) {
+    Layout L;
+    memset(&L, 0, sizeof(L));
+    L.S = digits_for(precision);
+    L.radix = radix_for();
+    if (L.S > 0) {
+        const long long half = L.radix / 2;
+        L.oz_kmax = (int)(((1LL << 31) / (half * half * L.S)) / 64 * 64);
+        if (L.oz_kmax > 65536) L.oz_kmax = 65536;
+    }
+    L.ld = round_up(n, 16);
+    L.ldm = round_up(m, 16);
+    L.ldy = round_up(m, 8);
+    // few samples (N << 128 * 148 rows): split the first contraction over the variables as well
+    const bool k1_split = (long long)cdiv(Nl, 128) * cdiv(m, 128) < kSMs / 2;
+    L.plan_k1 = plan_gemm((int)Nl, m, n, kSMs, k1_split ? 16 : 1, k1_split);
+    L.plan_k2 = plan_gemm(n, m, (int)Nl, kSMs, kMaxSplitsX, true);
+    L.plan_mm = plan_gemm(m, m, n, kSMs, kMaxSplitsSmall, true);
+    L.plan_mn = plan_gemm(m, n, m, kSMs, 1, false);
+    L.nstrips = cdiv(n, kStripCols);
+    long long cur = 0;
+    auto put = [&](int id, int set, long long rows, long long cols, long long ld) {
+        L.slot[id][set] = Slot{cur, rows, cols, ld};
+        cur = align16(cur + rows * ld);
+    };
+    const long long mn = m;
+    for (int set = 0; set < 2; ++set) {
+        put(LCX_A_W, set, mn, n, L.ld);
+        put(LCX_A_RHO, set, mn, n, L.ld);
+        put(LCX_A_INVRHO, set, mn, n, L.ld);
+        put(LCX_A_RHOINVRHO, set, mn, n, L.ld);
+        put(LCX_A_QIJ, set, mn, n, L.ld);
+        put(LCX_A_SI, set, 1, n, L.ld);
+        put(LCX_A_QISI2, set, 1, n, L.ld);
+        put(LCX_A_RY, set, mn, m, L.ldm);
+        put(LCX_A_UJ, set, 1, m, L.ldm);
+    }
+    auto put1 = [&](int id, long long rows, long long cols, long long ld) {
+        put(id, 0, rows, cols, ld);
+        L.slot[id][1] = L.slot[id][0];
+    };
+    put1(LCX_A_GRAD, mn, n, L.ld);
+    put1(LCX_A_UPDATE, mn, n, L.ld);
+    put1(LCX_A_RDIR, mn, n, L.ld);
+    put1(LCX_A_D, mn + cdiv(m, L.ld), n, L.ld);  // D (m x ld) immediately followed by s (m values)
+    put1(LCX_A_MI, mn, n, L.ld);
+    put1(LCX_A_XZ, mn, n, L.ld);
+    put1(LCX_A_XY, mn, n, L.ld);
+    put1(LCX_A_X2Y, 1, n, L.ld);
+    put1(LCX_A_IXY, 1, n, L.ld);
+    put1(LCX_A_YJ2, 1, m, L.ldm);
+    put1(LCX_A_IYX, 1, m, L.ldm);
+    put1(LCX_A_TCS, 1, m, L.ldm);
+    put1(LCX_A_TCDIRECT, 1, m, L.ldm);
+    put1(LCX_A_CY, mn, m, L.ldm);
+    put1(LCX_A_Y, Nl, m, L.ldy);
+    put1(LCX_A_SCALARS, 1, 16, 16);
+    put1(I_T, mn, n, L.ld);
+    long long part = 0;
+    if (L.plan_k2.splits > 1) part = max(part, (long long)L.plan_k2.splits * mn * L.ld);
+    if (L.plan_mm.splits > 1) part = max(part, (long long)L.plan_mm.splits * mn * L.ldm);
+    if (L.plan_k1.splits > 1) part = max(part, (long long)L.plan_k1.splits * Nl * L.ldy);
+    put1(I_PART, 1, max(part, 16LL), max(part, 16LL));
+    put1(I_COLSQ, L.plan_k1.grid.x, m, L.ldy);
+    const long long spart = max(3LL * L.nstrips, (long long)m * cdiv(n, 256));
+    put1(I_SPART, 1, spart, spart);
+    put1(I_W2, 1, m, L.ldm);
+    put1(I_BJ, 1, m, L.ldm);
+    put1(I_F, 1, m, L.ldm);
+    put1(I_UJDIAG, 1, m, L.ldm);
+    put1(I_ROWMI, 1, m, L.ldm);
+    put1(I_SQRTY, 1, m, L.ldm);
+    put1(I_RYINV, mn, m, L.ldm);
+    put1(I_AUG, mn, 2 * mn, 2 * mn);
+    put1(I_STATUS, 1, 2, 2);
+    L.ystat_slabs = cdiv(Nl, kYStatRows);
+    put1(I_OZV, 1, 16 + 4 * L.ldm, 16 + 4 * L.ldm);
+    put1(I_YSTAT, (long long)L.ystat_slabs * 2, m, L.ldm);
+    if (L.S > 0) {
+        L.ld8 = round_up(n, 128);
+        L.ldk8 = round_up(Nl, 128);
+        // second contraction: 128 x 64 tiles over (variables x factors), split over samples to fill whole waves;
+        // at most oz_kmax samples per split keeps every int32 accumulator exact
+        const long long tiles = (long long)cdiv(n, oz::kBM) * cdiv(m, oz::bn_max(L.S));
+        const int kblocks = cdiv(Nl, oz::kBK);
+        // time model in units of one 64-deep K block: waves x (K blocks per CTA + fixed prologue/TMEM-drain/store cost
+        // of ~16 blocks) + the partial-buffer round trip; measured at 12.5k and 100k rows per GPU
+        int best = 1;
+        double best_cost = 1e300;
+        const int smin = cdiv(Nl, L.oz_kmax), smax = (int)min(64LL, (long long)max(1, kblocks / 8));
+        for (int sp = smin; sp <= max(smin, smax); ++sp) {
+            const long long ctas = tiles * sp;
+            const long long waves = (ctas + kSMs - 1) / kSMs;
+            const double kb = ceil((double)kblocks / sp);
+            const double cost = (double)waves * (kb + 16.0) + (sp > 1 ? 1.5 * sp : 0.0);
+            if (cost < best_cost - 1e-9) { best_cost = cost; best = sp; }
+        }
+        if (const char* env = getenv("LCX_OZ_SPLITS")) {  // experiment override; never below the int32-exact minimum
+            const int v = atoi(env);
+            if (v >= smin && v <= kblocks) best = v;
+        }
+        L.oz_chunk = (int)round_up(cdiv(Nl, best), oz::kBK);
+        L.oz_splits = cdiv(Nl, L.oz_chunk);
+        {   // first contraction: same cost model over its (row tile x factor tile) grid
+            const long long tiles1 = (long long)cdiv(Nl, oz::kBM) * cdiv(m, oz::bn_max(L.S));
+            const int kblocks1 = cdiv(n, oz::kBK);
+            int b1 = cdiv(n, L.oz_kmax);
+            double c1best = 1e300;
+            const int s1min = cdiv(n, L.oz_kmax);  // int32 exactness of every accumulator group
+            for (int sp = s1min; sp <= max(s1min, min(8, kblocks1 / 16)); ++sp) {
+                const long long waves = (tiles1 * sp + kSMs - 1) / kSMs;
+                const double cost = (double)waves * (ceil((double)kblocks1 / sp) + 16.0) + (sp > 1 ? 4.0 * sp : 0.0);
+                if (cost < c1best - 1e-9) { c1best = cost; b1 = sp; }
+            }
+            L.oz1_chunk = (int)round_up(cdiv(n, b1), oz::kBK);
+            L.oz1_splits = cdiv(n, L.oz1_chunk);
+        }
+        const long long part = max((long long)L.oz_splits * mn * L.ld, L.oz1_splits > 1 ? (long long)L.oz1_splits * Nl * L.ldy : 0LL);
+        if (part > L.slot[I_PART][0].cols) {  // grow the split-K partial buffer (it is the last big slot before these)
+            put1(I_PART, 1, part, part);
+        }
+        const long long xs8 = ((long long)L.S * Nl * L.ld8 + 7) / 8;   // int8 planes counted in doubles (64-bit sizes:
+        const long long as8 = ((long long)L.S * mn * L.ld8 + 7) / 8;   // the target shape has 1.5e10 doubles of planes)
+        const long long ys8 = ((long long)L.S * mn * L.ldk8 + 7) / 8;
+        put1(I_XS, 1, xs8, xs8);
+        put1(I_AS, 1, as8, as8);
+        put1(I_YS, 1, ys8, ys8);
+        put1(I_AMAX, 1, kAmaxCtas, kAmaxCtas);
+        L.mm_i8 = mm_i8_for(L.S, n, m);
+        if (L.mm_i8) {
+            L.ldm8 = round_up(m, 128);
+            {   // m x m outputs, contraction over the variables: split to fill the SMs, never beyond the int32-exact length
+                const long long tiles_mm = (long long)cdiv(m, oz::kBM) * cdiv(m, oz::bn_max(L.S));
+                const int kblocks_mm = cdiv(n, oz::kBK);
+                const int smin_mm = cdiv(n, L.oz_kmax);
+                int bmm = smin_mm;
+                double cbest = 1e300;
+                for (int sp = smin_mm; sp <= max(smin_mm, min(64, kblocks_mm / 8)); ++sp) {
+                    const long long waves = (tiles_mm * sp + kSMs - 1) / kSMs;
+                    const double cost = (double)waves * (ceil((double)kblocks_mm / sp) + 16.0) + 1.5 * sp;
+                    if (cost < cbest - 1e-9) { cbest = cost; bmm = sp; }
+                }
+                L.mm_chunk = (int)round_up(cdiv(n, bmm), oz::kBK);
+                L.mm_splits = cdiv(n, L.mm_chunk);
+            }
+            L.mm_slabs = (int)min(32LL, (long long)cdiv(m, 8));
+            L.mm_slab_rows = cdiv(m, L.mm_slabs);
+            const long long need = (long long)L.mm_splits * mn * L.ldm;
+            if (need > L.slot[I_PART][0].cols) put1(I_PART, 1, need, need);
+            const long long pl8 = ((long long)L.S * mn * L.ld8 + 7) / 8;
+            const long long q8 = ((long long)L.S * mn * L.ldm8 + 7) / 8;
+            put1(I_MMA, 1, pl8, pl8);
+            put1(I_MMB, 1, pl8, pl8);
+            put1(I_MMC, 1, pl8, pl8);
+            put1(I_MMQ, 1, q8, q8);
+            put1(I_MMV, 1, 33 * L.ld + 3 * L.ldm, 33 * L.ld + 3 * L.ldm);
+        }
+    }
+    L.total = cur;
+    return L;
+}
+
+struct lcx_session {
+    int device, precision;
+    cudaStream_t stream;
+    lcx_allreduce_fn hook;
+    void* hook_user;
+    long long launches;
+    double* mailbox;  // pinned host, 16 doubles
+    bool bound;
+    const double* xt;
+    long long Nl, Nt, ldx;
+    int n, m;
+    double* ws;
+    Layout L;
+    int cur;  // which physical set is "set 0" (current)
+    // optional device-side timing of the two X contractions (bench.py roofline); events are
+    // recorded on the session stream around each launch and resolved at lcx_profile_read
+    bool prof_on;
+    cudaEvent_t* prof_ev;      // 4 per pair: [0] before K1, [1] after K1, [3] before K2, [2] after K2 (+ split reduction)
+    int prof_pending, prof_cap;
+    double prof_k1_ms, prof_k2_ms;
+    long long prof_pairs;
+    // sample sharding over NVLink peers (fused_allreduce.cuh); peers.world <= 1 means off
+    far::Peers peers;
+    unsigned long long ar_calls;
+    // split-integer modes: TMA descriptors over the digit slices
+    CUtensorMap map_x_k1, map_a_k1, map_a_k1_tail, map_x_k2, map_y_k2, map_y_k2_tail;
+    int oz_bn_tail;   // width of the last factor tile of the first contraction (multiple of 16)
+    // m x m x n products on the int8 engine (L.mm_i8)
+    CUtensorMap map_mm_a, map_mm_b, map_mm_b_tail, map_mn_c, map_mn_q, map_mn_q_tail;
+    int8_t* mma() const { return (int8_t*)(ws + L.slot[I_MMA][0].off); }
+    int8_t* mmb() const { return (int8_t*)(ws + L.slot[I_MMB][0].off); }
+    int8_t* mmc() const { return (int8_t*)(ws + L.slot[I_MMC][0].off); }
+    int8_t* mmq() const { return (int8_t*)(ws + L.slot[I_MMQ][0].off); }
+    double* mm_colpart() const { return ws + L.slot[I_MMV][0].off; }
+    double* mm_colscale() const { return ws + L.slot[I_MMV][0].off + 32 * L.ld; }
+    double* mm_scale_a() const { return ws + L.slot[I_MMV][0].off + 33 * L.ld; }
+    double* mm_scale_b() const { return ws + L.slot[I_MMV][0].off + 33 * L.ld + L.ldm; }
+    double* mm_scale_q() const { return ws + L.slot[I_MMV][0].off + 33 * L.ld + 2 * L.ldm; }
+    int8_t* xs() const { return (int8_t*)(ws + L.slot[I_XS][0].off); }
+    int8_t* as() const { return (int8_t*)(ws + L.slot[I_AS][0].off); }
+    int8_t* ys() const { return (int8_t*)(ws + L.slot[I_YS][0].off); }
+    double* oz_xscale() const { return ws + L.slot[I_OZV][0].off; }
+    double* oz_ascale() const { return ws + L.slot[I_OZV][0].off + 16; }
+    double* oz_cscale() const { return ws + L.slot[I_OZV][0].off + 16 + L.ldm; }
+    double* oz_yscale() const { return ws + L.slot[I_OZV][0].off + 16 + 2 * L.ldm; }
+    double* oz_dscale() const { return ws + L.slot[I_OZV][0].off + 16 + 3 * L.ldm; }
+
+    double* ptr(int id, int set = 0) const {
+        const int phys = (id <= LCX_A_UJ) ? (set ^ cur) : 0;
+        return ws + L.slot[id][phys].off;
+    }
+    long long off(int id, int set = 0) const {
+        const int phys = (id <= LCX_A_UJ) ? (set ^ cur) : 0;
+        return L.slot[id][phys].off;
+    }
+};
+
+#define S_REQUIRE_BOUND(s)                                                        \
+    do {                                                                          \
+        if (!(s)) return fail(LCX_ERR_ARG, "session", "null session");            \
+        if (!(s)->bound) return fail(LCX_ERR_STATE, "session", "no bound problem"); \
+        LCX_CUDA(cudaSetDevice((s)->device));                                     \
+    } while (0)
+
+#define LAUNCHED(s) ((s)->launches++)
+
+static int combine_and_allreduce(lcx_session* s, const double* part, int splits, long long stride, int rows, int cols,
+                                 long long ld, double* dst_body, double* tail, int ntail);
+
+static dim3 grid_mn(int m, int n) { return dim3(cdiv(n, 256), m); }

@@ -43,7 +43,7 @@ def split_product(x, a, S, R):
 @pytest.mark.parametrize("S,R,bound", [(7, 254, 127), (6, 254, 127), (5, 254, 127), (3, 254, 127), (6, 128, 64)])
 def test_digit_ranges_and_int32_exactness(S, R, bound):
     rng = np.random.RandomState(S * 1000 + R)
-    kmax = ((1 << 31) // ((R // 2) ** 2 * S)) // 64 * 64          # oz_kmax in lcx_api.cu
+    kmax = ((1 << 31) // ((R // 2) ** 2 * S)) // 64 * 64          # oz_kmax in csrc/host_session.cuh
     k = min(kmax, 4096)
     x = rng.randn(64, k) * 3.0
     x[3, 7] = 11.5
@@ -81,7 +81,7 @@ def test_radix_254_beats_radix_128_at_equal_cost():
 
 
 def mn_product(q, v, S, R, unit_diag):
-    """out = Q V (Q m x m, V m x n) the way oz_mn_t in lcx_api.cu runs it: the contraction goes over V's ROWS, so V gets one
+    """out = Q V (Q m x m, V m x n) the way oz_mn_t in csrc/host_oz.cuh runs it: the contraction goes over V's ROWS, so V gets one
     power-of-two scale per COLUMN and Q one per row; with `unit_diag` the product runs on Q - I and V is added back exactly."""
     m = q.shape[0]
     qq = q - np.eye(m) if unit_diag else q
