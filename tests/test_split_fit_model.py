@@ -1,0 +1,129 @@
+"""CPU model of the int8 route of the four m x m x n products (csrc/host_oz.cuh: oz_square_t, oz_mn_t) inside FULL fits:
+the oracle's `ry = W rho^T`, `Qij = ry rinv`, `H = T rinv^T` and `grad += H W` (linearcorex.py:261, :266, :294, :300) are
+replaced by the numpy restatement of the digit-plane scheme (6 radix-254 digits, one exponent per factor row, one per
+variable for the operand contracted over its rows, unit diagonal of ry taken out) and the fits must still land on the
+reference's golden vectors at 1e-9 with the same iteration counts -- the per-iteration truncation noise of the scheme
+(~1e-14) must not move the trajectory.  The CUDA kernels are held to the same goldens in tests/test_gpu_mm_i8.py."""
+import numpy as np
+import pytest
+
+import corex_oracle as oc
+from conftest import load_golden
+from test_split_scheme import pow2_above, split_digits
+
+S, R = 6, 254
+
+
+def _planes(a, scale):
+    return [p.astype(np.float64) for p in split_digits(a, scale, S, R)]  # |sums| < 2^31: exact in binary64, BLAS-fast
+
+
+def _recombine(groups):
+    acc = groups[S - 1]
+    for g in range(S - 2, -1, -1):
+        acc = acc / R + groups[g]
+    return acc / (R * R)
+
+
+def square_product(left, right):
+    """left right^T over the variables, one power-of-two scale per row of each operand (oz_square_t)."""
+    sl = np.array([pow2_above(np.abs(r).max()) for r in left])
+    sr = np.array([pow2_above(np.abs(r).max()) for r in right])
+    dl, dr = _planes(left, sl[:, None]), _planes(right, sr[:, None])
+    groups = [np.zeros((left.shape[0], right.shape[0])) for _ in range(S)]
+    for k in range(S):
+        for l in range(S - k):
+            groups[k + l] += dl[k] @ dr[l].T
+    return _recombine(groups) * sl[:, None] * sr[None, :]
+
+
+def mn_product(q, v, unit_diag):
+    """Q V with V scaled per COLUMN and Q per row; `unit_diag`: the product runs on Q - I, V is added back (oz_mn_t)."""
+    qq = q - np.eye(q.shape[0]) if unit_diag else q
+    sq = np.array([pow2_above(np.abs(r).max()) for r in qq])
+    sv = np.array([pow2_above(np.abs(c).max()) for c in v.T])
+    dq, dv = _planes(qq, sq[:, None]), _planes(v, sv[None, :])
+    groups = [np.zeros((q.shape[0], v.shape[1])) for _ in range(S)]
+    for k in range(S):
+        for l in range(S - k):
+            groups[k + l] += dq[l] @ dv[k]
+    out = _recombine(groups) * sq[:, None] * sv[None, :]
+    return out + v if unit_diag else out
+
+
+def model_moments_ns(xt, w, eps, quick=False, yscale=1.):
+    """oracle.moments_ns with the two products through the digit-plane model (quick part only differs)."""
+    n_samples = xt.shape[0]
+    y, s = oc.project_sumsq(xt, w)
+    m = {}
+    m["uj"] = (1 - eps ** 2) * s / n_samples + eps ** 2 * np.sum(w ** 2, axis=1)
+    if quick and np.max(m["uj"]) >= 1.:
+        return None
+    d = xt.T.dot(y)
+    rho = (1 - eps ** 2) * d.T / n_samples + eps ** 2 * w
+    ry = square_product(w, rho)
+    m["Y_j^2"] = yscale ** 2 / (1. - m["uj"])
+    np.fill_diagonal(ry, 1)
+    inv = 1. / (1. - rho ** 2)
+    rinv = rho * inv
+    qij = mn_product(ry, rinv, True)
+    si = np.sum(rho * rinv, axis=0)
+    qs = np.einsum('ki,ki->i', rinv, qij - si * rho)
+    m["rho"], m["ry"], m["invrho"], m["rhoinvrho"] = rho, ry, inv, rinv
+    m["Qij"], m["Si"], m["Qi-Si^2"] = qij, si, qs
+    m["TC"] = np.sum(np.log(1 + si)) - 0.5 * np.sum(np.log(1 + qs)) + 0.5 * np.sum(np.log(1 - m["uj"]))
+    if not quick:
+        full = _ORIG_MOMENTS(xt, w, eps, quick=False, yscale=yscale)
+        for key, val in full.items():
+            m.setdefault(key, val)
+    return m
+
+
+def model_direction_ns(xt, w, m, eps):
+    rj = 1. - m["uj"][:, np.newaxis]
+    h = square_product(m["rhoinvrho"] / (1 + m["Qi-Si^2"]), m["rhoinvrho"])
+    np.fill_diagonal(h, 0)
+    grad = w / rj
+    grad -= 2 * m["invrho"] * m["rhoinvrho"] / (1 + m["Si"])
+    grad += m["invrho"] ** 2 * ((1 + m["rho"] ** 2) * m["Qij"] - 2 * m["rho"] * m["Si"]) / (1 + m["Qi-Si^2"])
+    grad = mn_product(h, w, False) + grad
+    sig_grad = oc.sigma_times(xt, grad, eps)
+    bj = np.sum(m["rho"] * grad, axis=1, keepdims=True)
+    update = - rj * (grad - 2. * w / (2 - rj) * bj)
+    tangent = np.einsum('ji,ji', sig_grad, update)
+    return grad, sig_grad, update, tangent
+
+
+_ORIG_MOMENTS = oc.moments_ns
+
+
+def _rel(a, b):
+    return np.abs(np.asarray(a) - np.asarray(b)).max() / np.abs(np.asarray(b)).max()
+
+
+def test_products_of_the_model_match_numpy():
+    rng = np.random.RandomState(1)
+    w, rho = rng.randn(12, 700) * 0.01, rng.randn(12, 700) * 0.3
+    assert _rel(square_product(w, rho), w @ rho.T) < 1e-12
+    h = rng.randn(12, 12)
+    assert _rel(mn_product(h, w, False), h @ w) < 1e-12
+
+
+@pytest.mark.parametrize("name", ["readme_demo_f64", "big5_l0_f64", "big5_l1_f64", "syn_400x300x10_f64", "syn_60x400x8_f64",
+                                  "syn_400x300x10_noanneal_f64", "outliers_missing_f64", "outliers_f64",
+                                  "standard_missing_f64", "adni_l1_f64", "adni_l2_f64",
+                                  "adni_l0_f64",             # 2 414 iterations, the worst-conditioned fixture: measured 1e-11
+                                  "syn_4000x2000x20_f64"])   # measured 2e-14
+def test_full_fit_with_modelled_products(monkeypatch, name):
+    z, kw, x = load_golden(name)
+    mdl = oc.OracleCorex(work_dtype=np.float64, **kw)
+    if name.startswith("readme_demo"):
+        x = np.random.random((100, 50))  # README.md:49-51: drawn after the constructor seeded the RNG
+    monkeypatch.setattr(oc, "moments_ns", model_moments_ns)
+    monkeypatch.setattr(oc, "direction_ns", model_direction_ns)
+    mdl.fit(x)
+    assert len(mdl.history["TC"]) == len(z["history_TC"])
+    assert _rel(mdl.history["TC"], z["history_TC"]) < 1e-9
+    assert _rel(mdl.ws, z["ws"]) < 1e-9
+    assert _rel(mdl.tcs, z["m_TCs"]) < 1e-9
+    np.testing.assert_array_equal(mdl.clusters(), z["clusters"])
