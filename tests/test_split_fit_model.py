@@ -127,3 +127,26 @@ def test_full_fit_with_modelled_products(monkeypatch, name):
     assert _rel(mdl.ws, z["ws"]) < 1e-9
     assert _rel(mdl.tcs, z["m_TCs"]) < 1e-9
     np.testing.assert_array_equal(mdl.clusters(), z["clusters"])
+
+
+# ---- the two X contractions themselves through the model (tools/split_model_scan.py holds the model) -------------------
+@pytest.mark.parametrize("digits,tol", [(6, 1e-9), (5, 1e-9)])
+@pytest.mark.parametrize("name", ["big5_l0_f64", "syn_400x300x10_f64", "standard_missing_f64"])
+def test_full_fit_with_modelled_x_contractions(monkeypatch, name, digits, tol):
+    """Y = X~ A^T and X~^T Y as digit-plane products (one exponent for all of X~, one per factor row / column), every
+    trial from X: the fit lands on the golden at 1e-9 with 6 digits (measured 7e-14 .. 2e-13) and with 5 (2e-11 .. 4e-11)."""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location(
+        "split_model_scan", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "split_model_scan.py"))
+    scan = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(scan)
+    for attr in ("project_sumsq", "sigma_times", "moments_ns"):  # install() rebinds these; monkeypatch restores them
+        monkeypatch.setattr(oc, attr, getattr(oc, attr))
+    scan.install(scan.XModel(digits, digits, digits))
+    z, kw, x = load_golden(name)
+    mdl = oc.OracleCorex(work_dtype=np.float64, **kw).fit(x)
+    assert len(mdl.history["TC"]) == len(z["history_TC"])
+    assert _rel(mdl.ws, z["ws"]) < tol
+    assert _rel(mdl.history["TC"], z["history_TC"]) < tol
+    np.testing.assert_array_equal(mdl.clusters(), z["clusters"])
