@@ -1,4 +1,5 @@
-// Round-2 starter experiment (written in round 1 without GPU time left: compiles for sm_100a, NOT yet run).
+// Operand-delivery probe for oz_gemm_kernel.  First seven cases measured at the very end of round 1
+// (profiles/r01_dsmem_feed_probe.txt); the HBM-resident and multicast cases below were added afterwards and are NOT yet run.
 //
 // Question.  oz_gemm_kernel is bound by operand delivery into the SMs: every SM of a CTA pair receives the whole X~ tile
 // (48 KB per 64-deep K block; TMA multicast halves the L2 reads, not the bytes delivered to each SM) plus its 24 KB of
@@ -13,6 +14,15 @@
 // overwritten once its receiver has waited on it.  Reported: bytes per clock per SM for L2 only, peer only, and both.
 //   additive  (both ~ L2-only + peer-only)  -> build the forwarding variant of oz_gemm_kernel;
 //   not additive (both ~ L2-only)            -> delivery into an SM is one port whatever the source; drop the idea.
+//
+// Round-1 result (B200, L2-resident source, one issuing thread per CTA): L2 only 72 KB / 48 KB / 24 KB per iteration = 1396 / 1137 /
+// 852 cycles (52.8 / 43.2 / 28.8 B/clk per SM; ~570 cycles of per-iteration issue + wait overhead in the single thread, ~90 B/clk
+// marginal); peer only 24 KB = 1957 cycles (12.6 B/clk); L2 48 KB + peer 24 KB = 2941 cycles -- WORSE than 72 KB from L2 alone.
+// So (1) DSMEM bulk copies are slow (<= 12.6 B/clk per SM) and slow the L2 stream down as well: forwarding is dead;
+// (2) L2-resident data reaches every SM at >= 52.8 B/clk, i.e. the real kernel's 1 644 cycles per 72 KB K block (44.8 B/clk)
+// is NOT the fabric's L2 -> SM ceiling.  What the real kernel does differently: its X~ planes come from HBM (6 GB per launch, L2 hit
+// rate 40-50 %) and are multicast to the CTA pair.  `feed_probe_mc` and the HBM-resident cases reproduce exactly that traffic
+// without any math; if they also run at ~1 650 cycles the bound is this data path, otherwise it is inside the SM.
 //
 // build + run (one B200):
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o /tmp/dsmem_feed_probe tools/experiments/dsmem_feed_probe.cu && /tmp/dsmem_feed_probe
@@ -141,6 +151,91 @@ feed_probe(const uint8_t* __restrict__ src, long long region_bytes, int l2_bytes
     asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void bar_arrive_local(uint64_t* b) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s32(b)) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s_mc(uint32_t dst, const void* src, uint32_t bytes, uint64_t* bar, uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(dst),
+        "l"(src), "r"(bytes), "r"(s32(bar)), "h"(mask)
+        : "memory");
+}
+
+// The real kernel's traffic without its math: per iteration 48 KB shared by the pair (six 8 KB pieces, piece p fetched by cluster
+// rank p % 2 and multicast into both CTAs) + 24 KB of the CTA's own; a stage is refilled once BOTH CTAs have waited on it.
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1)
+feed_probe_mc(const uint8_t* __restrict__ src, long long region_bytes, int iters, unsigned long long* __restrict__ cycles) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    __shared__ __align__(8) uint64_t full[kStages], empty[kStages];
+    uint32_t rank;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+    const uint32_t peer = rank ^ 1u;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; ++s) {
+            bar_init(&full[s], 1);
+            bar_init(&empty[s], 2);  // this CTA and its peer have both consumed the stage
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+    if (threadIdx.x == 0) {
+        const uint8_t* shared_src = src + (long long)(blockIdx.x & ~1u) * region_bytes;  // the pair's common operand
+        const uint8_t* own_src = src + (long long)(blockIdx.x | 1u) * region_bytes + (long long)rank * (region_bytes / 2);
+        long long off_sh = 0, off_own = 0;
+        const unsigned long long t0 = clock64();
+        for (int i = 0; i < iters + kStages - 1; ++i) {
+            if (i < iters) {
+                const int s = i % kStages;
+                const uint32_t ph = (uint32_t)(i / kStages) & 1u;
+                uint8_t* st = smem + s * (kMaxL2 + kMaxPeer);
+                bar_wait(&empty[s], ph ^ 1u);
+                bar_expect(&full[s], (uint32_t)(kMaxL2 + kMaxPeer));
+                for (int p = 0; p < kMaxL2 / kPiece; ++p)
+                    if ((uint32_t)(p & 1) == rank) bulk_g2s_mc(s32(st) + p * kPiece, shared_src + off_sh + (long long)p * kPiece, kPiece, &full[s], 3);
+                off_sh += kMaxL2;
+                if (off_sh + kMaxL2 > region_bytes) off_sh = 0;
+                for (int p = 0; p < kMaxPeer / kPiece; ++p)
+                    bulk_g2s(s32(st) + kMaxL2 + p * kPiece, own_src + off_own + (long long)p * kPiece, kPiece, &full[s]);
+                off_own += kMaxPeer;
+                if (off_own + kMaxPeer > region_bytes / 2) off_own = 0;
+            }
+            const int j = i - (kStages - 1);
+            if (j >= 0) {
+                const int s = j % kStages;
+                bar_wait(&full[s], (uint32_t)(j / kStages) & 1u);
+                bar_arrive_local(&empty[s]);
+                bar_arrive_remote(peer_addr(s32(&empty[s]), peer));
+            }
+        }
+        cycles[blockIdx.x] = clock64() - t0;
+    }
+    __syncthreads();
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+static double run_mc(const uint8_t* src, long long region, int iters, unsigned long long* d_cyc, int ctas, float* ms_out) {
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    for (int rep = 0; rep < 2; ++rep) {
+        CK(cudaEventRecord(e0));
+        feed_probe_mc<<<ctas, 128, kSmem>>>(src, region, iters, d_cyc);
+        CK(cudaEventRecord(e1));
+        CK(cudaDeviceSynchronize());
+    }
+    CK(cudaEventElapsedTime(ms_out, e0, e1));
+    unsigned long long* h = (unsigned long long*)malloc(sizeof(unsigned long long) * ctas);
+    CK(cudaMemcpy(h, d_cyc, sizeof(unsigned long long) * ctas, cudaMemcpyDeviceToHost));
+    double worst = 0;
+    for (int i = 0; i < ctas; ++i) worst = h[i] > worst ? (double)h[i] : worst;
+    free(h);
+    return worst;
+}
+
 static double run(const uint8_t* src, long long region, int l2_bytes, int peer_bytes, int iters, unsigned long long* d_cyc,
                   int ctas, float* ms_out) {
     cudaEvent_t e0, e1;
@@ -187,6 +282,22 @@ int main() {
         const double per = cyc / iters;
         printf("%-52s %12.0f %12.1f %12.1f %10.3f\n", c.name, per, c.l2 / per, c.peer / per, ms);
     }
-    printf("(a 64-deep K block of oz_gemm_kernel<6> needs 1344 tensor cycles at full rate; today it takes ~1750)\n");
+    // ---- not yet run: the real kernel's traffic pattern (multicast pair) and an HBM-resident source ----
+    CK(cudaFuncSetAttribute(feed_probe_mc, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+    const long long big_region = 40LL << 20;  // per CTA; 148 regions = 5.9 GB: every load misses the 126 MB L2
+    uint8_t* big;
+    CK(cudaMalloc(&big, big_region * ctas));
+    CK(cudaMemset(big, 1, big_region * ctas));
+    const int it_big = 500;  // 500 x 72 KB = 36 MB per CTA: one pass over its region, no reuse
+    {
+        float ms = 0.f;
+        double per = run_mc(src, region, iters, d_cyc, ctas, &ms) / iters;
+        printf("%-52s %12.0f %12.1f %12s %10.3f\n", "pair multicast 48 KB + own 24 KB, L2-resident", per, 73728 / per, "-", ms);
+        per = run(big, big_region, kMaxL2 + kMaxPeer, 0, it_big, d_cyc, ctas, &ms) / it_big;
+        printf("%-52s %12.0f %12.1f %12s %10.3f\n", "72 KB per iteration, HBM-resident source", per, 73728 / per, "-", ms);
+        per = run_mc(big, big_region, it_big, d_cyc, ctas, &ms) / it_big;
+        printf("%-52s %12.0f %12.1f %12s %10.3f\n", "pair multicast 48 KB + own 24 KB, HBM-resident", per, 73728 / per, "-", ms);
+    }
+    printf("(a 64-deep K block of oz_gemm_kernel<6> needs 1344 tensor cycles at full rate; the kernel takes 1644 at config 3)\n");
     return 0;
 }
