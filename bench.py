@@ -20,8 +20,11 @@ iterations over the 7 anneal stages instead).  `roofline` is for the dominant ke
 contractions over X, 93 % of a step: `oz_gemm_kernel`, exact int8 digit-plane products on tcgen05 in the default
 FP64-faithful mode `fp64_split`; `dgemm_mma_kernel`, DMMA, with --precision fp64), timed live by CUDA events on the
 launching stream.
-`cpu_baseline` / `--impl reference` time oracle/corex_oracle.py (the numpy restatement of the reference;
-/root/reference does not exist on the GPU box) on a bounded row subsample with all host threads.
+`target` (default workload only) = the same resident measurement at BASELINE.json's north-star shape, 1M x 20k x 100, rows
+sharded over the N ranks, so the driver's scaling record carries that curve too.
+`cpu_baseline` / `--impl reference` time one fit iteration of the reference algorithm in float64 on all host cores at the
+FULL config-3 size (8 GB of X~): the unmodified reference when $LCX_REFERENCE_ROOT (default /root/reference) exists, else
+oracle/corex_oracle.py, its numpy restatement (the GPU box has no /root/reference).  Both legs share one code path.
 """
 import argparse
 import ctypes as C
@@ -152,40 +155,103 @@ class ClockSampler(object):
 
 
 # ----------------------------------------------------------------------------------------------------
-# reference algorithm on the host cores (oracle port; the only place bench.py executes oracle/)
+# reference algorithm on the host cores (the only place bench.py executes oracle/)
 # ----------------------------------------------------------------------------------------------------
-def time_reference_cpu(n_total, n_vars, n_factors, steps, warmup, flop_budget):
-    """Time `step_ns` of oracle/corex_oracle.py in float64 on a row subsample; scale linearly in N.
+REFERENCE_ROOT = os.environ.get("LCX_REFERENCE_ROOT", "/root/reference")
 
-    Per-iteration cost is linear in N apart from the O(m n) / O(m^2 n) terms (<1 % here), SURVEY.md 8(d)."""
+
+def host_standardized(n_total, n_vars, n_factors, rows, threads):
+    """float64 X~ of the first `rows` synthetic rows: (x - mean) / std per column, built block-wise in threads (the timed
+    quantity is the fit iteration; this only has to be quick)."""
+    from concurrent.futures import ThreadPoolExecutor
+    x32 = make_rows(n_total, n_vars, n_factors, 0, rows, threads=threads)
+    blocks = [(lo, min(rows, lo + 2048)) for lo in range(0, rows, 2048)]
+    with ThreadPoolExecutor(max_workers=threads) as ex:
+        mu = sum(ex.map(lambda b: x32[b[0]:b[1]].sum(axis=0, dtype=np.float64), blocks)) / rows
+        sq = sum(ex.map(lambda b: ((x32[b[0]:b[1]] - mu) ** 2).sum(axis=0), blocks))
+        sd = np.sqrt(sq / rows).clip(1e-10)
+        xt = np.empty((rows, n_vars), dtype=np.float64)
+
+        def fill(b):
+            xt[b[0]:b[1]] = (x32[b[0]:b[1]] - mu) / sd
+        list(ex.map(fill, blocks))
+    return xt
+
+
+def _reference_stepper(n_factors):
+    """(kind, init, step) over the UNMODIFIED reference when LCX_REFERENCE_ROOT exists (its float64 path: the module-global
+    numpy shim of oracle/gen_golden.py), else over the oracle port (the GPU box has no /root/reference)."""
+    if os.path.isdir(os.path.join(REFERENCE_ROOT, "linearcorex")):
+        try:
+            sys.path.insert(0, REFERENCE_ROOT)
+            import linearcorex.linearcorex as ref
+
+            class _F64(object):
+                float32 = np.float64
+
+                def __getattr__(self, name):
+                    return getattr(np, name)
+            ref.np = _F64()
+            mdl = ref.Corex(n_hidden=n_factors, seed=0, tol=1e-12)
+
+            def init(xt, w, eps):
+                mdl.n_samples, mdl.nv = xt.shape
+                mdl.eps, mdl.ws = eps, w
+                mdl.moments = mdl._calculate_moments(xt, w, quick=True)
+
+            def step(xt):
+                mdl.ws, mdl.moments = mdl._update_ns(xt)
+                return None
+            return "reference", init, step, "unmodified %s/linearcorex/linearcorex.py _update_ns (:290-334), float64 path" % REFERENCE_ROOT
+        except Exception:
+            pass
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import corex_oracle as oc
+    state = {}
+
+    def init(xt, w, eps):
+        state.update(w=w, eps=eps, m=oc.moments_ns(xt, w, eps))
+
+    def step(xt):
+        rec = {}
+        state["w"], state["m"] = oc.step_ns(xt, state["w"], state["m"], state["eps"], 1e-12, trace=rec)
+        return rec.get("trials")
+    return "port", init, step, "oracle/corex_oracle.py step_ns (numpy float64 restatement of linearcorex.py:290-334)"
+
+
+def time_reference_cpu(n_total, n_vars, n_factors, steps, warmup):
+    """Time one fit iteration (`_update_ns`) of the reference algorithm in float64 on the host cores, at the FULL row count
+    whenever X~ fits in host memory (config 3: 8 GB), else on the largest row sub-sample that does (cost is linear in N)."""
     try:  # torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU arm must use every host core
         from threadpoolctl import threadpool_limits
         threadpool_limits(limits=os.cpu_count() or 1)
     except Exception:
         pass
-    per_row = 11.0 * n_vars * n_factors  # ~ (4 + 4t) N n m flops per iteration at t ~ 1.7 trials
-    rows = int(min(n_total, max(512, flop_budget / (per_row * (steps + warmup)))))
-    x = make_rows(n_total, n_vars, n_factors, 0, rows).astype(np.float64)
+    threads = min(32, os.cpu_count() or 1)
+    try:
+        import psutil
+        avail = psutil.virtual_memory().available
+    except Exception:
+        avail = 64 << 30
+    per_row = n_vars * (8 + 4) * 1.6  # float64 X~ + the float32 source + numpy temporaries of a step
+    rows = int(min(n_total, max(512, 0.6 * avail / per_row)))
     t0 = time.perf_counter()
-    xt, theta, _ = oc.standardize(x, 'standard', None)
+    xt = host_standardized(n_total, n_vars, n_factors, rows, threads)
     t_pre = time.perf_counter() - t0
-    del x
+    kind, init, step, what = _reference_stepper(n_factors)
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import corex_oracle as oc
     np.random.seed(0)
     eps = 0.6
     w = np.random.randn(n_factors, n_vars)
     w /= (10. * oc.norm_y(xt, w, 0.0))[:, np.newaxis]
-    m = oc.moments_ns(xt, w, eps)
+    init(xt, w, eps)
     trials = []
     for _ in range(warmup):
-        rec = {}
-        w, m = oc.step_ns(xt, w, m, eps, 1e-12, trace=rec)
+        step(xt)
     t0 = time.perf_counter()
     for _ in range(steps):
-        rec = {}
-        w, m = oc.step_ns(xt, w, m, eps, 1e-12, trace=rec)
-        trials.append(rec.get("trials", 0))
+        trials.append(step(xt))
     dt = time.perf_counter() - t0
     try:
         from threadpoolctl import threadpool_info
@@ -194,12 +260,13 @@ def time_reference_cpu(n_total, n_vars, n_factors, steps, warmup, flop_budget):
         cores = os.cpu_count() or 1
     it_s_sample = steps / dt
     scale = rows / float(n_total)
-    return {"value": it_s_sample * scale, "unit": UNIT, "cores": int(cores), "kind": "port",
-            "sample": "oracle/corex_oracle.py step_ns (numpy float64 restatement of linearcorex.py:290-334), "
-                      "%d of %d rows x %d vars x %d factors, %d iterations after %d warm-up, %.2f trials/iteration; "
-                      "%.4g it/s on the sample scaled x%.4g (cost linear in N); preprocess of the sample %.2f s"
-                      % (rows, n_total, n_vars, n_factors, steps, warmup, float(np.mean(trials)) if trials else 0.0,
-                         it_s_sample, scale, t_pre),
+    tr = [t for t in trials if t is not None]
+    return {"value": it_s_sample * scale, "unit": UNIT, "cores": int(cores), "kind": kind,
+            "sample": "%s, %d of %d rows x %d vars x %d factors%s, %d iterations after %d warm-up%s; %.4g it/s measured%s; "
+                      "building X~ on the host %.1f s (untimed)"
+                      % (what, rows, n_total, n_vars, n_factors, " (FULL size)" if rows == n_total else "", steps, warmup,
+                         ", %.2f trials/iteration" % float(np.mean(tr)) if tr else "", it_s_sample,
+                         "" if rows == n_total else " on the sample, scaled x%.4g (cost linear in N)" % scale, t_pre),
             "ms_per_step_sample": 1e3 * dt / steps, "rows": rows}
 
 
@@ -208,7 +275,7 @@ def run_reference(args, shape):
     if rank != 0:
         return
     n_total, n_vars, n_factors = shape
-    base = time_reference_cpu(n_total, n_vars, n_factors, args.steps, args.warmup, flop_budget=6e12)
+    base = time_reference_cpu(n_total, n_vars, n_factors, args.steps, args.warmup)
     line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / base["value"], "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -221,13 +288,14 @@ def run_reference(args, shape):
 
 
 def workload_name(args, shape):
-    if args.impl == "reference":
-        return "%s: synthetic latent-factor data N=%d x n=%d, m=%d, FP64 mode" % (args.workload, shape[0], shape[1], shape[2])
-    return "%s: synthetic latent-factor data N=%d x n=%d, m=%d, %s mode" % (
-        args.workload, shape[0], shape[1], shape[2],
-        {"fp64": "FP64 (DMMA)", "fp64_split": "FP64 (6 int8 radix-254 digit planes on tcgen05)",
-         "fp64_split5": "FP64 (5 int8 radix-254 digit planes on tcgen05)",
-         "fp64_split7": "FP64 (7 int8 radix-254 digit planes on tcgen05)", "fast": "fast (3 int8 digit planes)"}[args.precision])
+    """The same string in both arms (the driver compares it); the arithmetic of each arm is in config.mode / dtype."""
+    return "%s: synthetic latent-factor data N=%d x n=%d, m=%d, FP64 mode" % (args.workload, shape[0], shape[1], shape[2])
+
+
+MODE_NAMES = {"fp64": "FP64 (DMMA)", "fp64_split": "FP64 (6 int8 radix-254 digit planes on tcgen05)",
+              "fp64_split5": "FP64 (5 int8 radix-254 digit planes on tcgen05)",
+              "fp64_split7": "FP64 (7 int8 radix-254 digit planes on tcgen05)", "fast": "fast (3 int8 digit planes)"}
+DIGITS = {"fp64": 0, "fp64_split": 6, "fp64_split5": 5, "fp64_split7": 7, "fast": 3}
 
 
 # ----------------------------------------------------------------------------------------------------
@@ -247,6 +315,181 @@ def measure_dgemm_peak(torch):
         if i > 0:
             best = min(best, e0.elapsed_time(e1))
     return 2.0 * n ** 3 / best / 1e9
+
+
+def measure_int8_peak(torch, seconds=1.0):
+    """int8 tensor throughput measured in this run: cuBLASLt IGEMM 8192^3 (torch._int_mm, int8 x int8 -> int32, random
+    operands), best single launch (burst) and back to back for `seconds` (sustained, under the power cap)."""
+    try:
+        n = 8192
+        a = torch.randint(-127, 128, (n, n), dtype=torch.int8, device="cuda")
+        b = torch.randint(-127, 128, (n, n), dtype=torch.int8, device="cuda").t()  # column-major B: the TN form
+        for _ in range(3):
+            torch._int_mm(a, b)
+        torch.cuda.synchronize()
+        best = 1e30
+        for _ in range(5):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            torch._int_mm(a, b)
+            e1.record()
+            torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        reps = max(8, int(seconds * 1e3 / best))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            torch._int_mm(a, b)
+        e1.record()
+        torch.cuda.synchronize()
+        ops = 2.0 * n ** 3
+        return {"burst_tops": ops / best / 1e9, "sustained_tops": ops * reps / e0.elapsed_time(e1) / 1e9,
+                "how": "torch._int_mm (cuBLASLt IGEMM) 8192^3, random int8; best of 5 / %d launches back to back" % reps}
+    except Exception as exc:  # noqa: BLE001
+        return {"burst_tops": None, "sustained_tops": None, "how": "torch._int_mm unavailable: %r" % (exc,)}
+
+
+def ncu_evidence(precision):
+    """Per-launch numbers of the dominant kernel from the newest committed `ncu --set full` summary of this workload
+    (profiles/rNN_oz_gemm_ncu_full_config3.csv / rNN_dgemm_ncu_full_config3.csv), identified by file name and hash."""
+    import glob
+    import hashlib
+    pat = "r*_oz_gemm_ncu_full_config3.csv" if precision != "fp64" else "r*_dgemm_ncu_full_config3.csv"
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", pat)))
+    if not files:
+        return None
+    path = files[-1]
+    raw = open(path, "rb").read()
+    rows = {}
+    import csv
+    for rec in csv.reader(raw.decode().splitlines()):
+        if len(rec) >= 3:
+            rows[rec[0]] = rec[1:]
+    scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0, "Tbyte": 1e12}
+
+    def vals(name):
+        if name not in rows:
+            return None
+        unit = rows[name][0]
+        try:
+            return [float(v) * scale.get(unit, 1.0) for v in rows[name][1:]]
+        except ValueError:
+            return None
+    rd, wr = vals("dram__bytes_read.sum"), vals("dram__bytes_write.sum")
+    if not rd or not wr:
+        return None
+    out = {"file": os.path.relpath(path, ROOT), "sha256_16": hashlib.sha256(raw).hexdigest()[:16],
+           "kernels": rows.get("metric", ["", ""])[1:],
+           "dram_bytes_per_launch": [a + b for a, b in zip(rd, wr)]}
+    for key, name in (("delivered_bytes_per_launch", "l1tex__m_xbar2l1tex_read_bytes.sum"),
+                      ("tensor_pipe_active_pct", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"),
+                      ("duration_ms_under_ncu", "gpu__time_duration.sum")):
+        v = vals(name)
+        if v:
+            out[key] = v
+    return out
+
+
+def resident_run(torch, dist, shape, args, steps, warmup, world, rank, local, device_source, x_host, lo, hi):
+    """Exactly `steps` fit iterations with X~ resident in HBM, timed by CUDA events, max over ranks."""
+    from linearcorex_b200 import Corex, _lib
+    n_total, n_vars, n_factors = shape
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    x_dev = DeviceRows(n_total, n_vars, n_factors, lo, hi) if device_source else torch.from_numpy(x_host).cuda()
+    mdl = Corex(n_hidden=n_factors, seed=0, tol=1e-12, max_iter=10 ** 9, precision=args.precision,
+                gaussianize=args.gaussianize, comm=True if world > 1 else None,
+                stream_rows=32768 if device_source else None)
+    schedule = mdl._prepare(x_dev)
+    prep = dict(mdl.timings)
+    del x_dev
+    mdl._begin_stage(schedule[0], rescale=False)
+    sess = mdl._sess
+    for _ in range(warmup):
+        mdl._iterate()
+    sess.lib.lcx_profile_enable(sess.h, 1)
+    k1, k2, kx, pairs = C.c_double(), C.c_double(), C.c_double(), C.c_longlong()
+    sess.lib.lcx_profile_read_phases(sess.h, C.byref(k1), C.byref(k2), C.byref(kx), C.byref(pairs), 1)
+    launches0 = sess.launches()
+    n_trace0 = len(mdl.trace)
+    barrier()
+    with ClockSampler(local) as clocks:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            mdl._iterate()
+        e1.record()
+        barrier()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = t.item()
+    sess.lib.lcx_profile_read_phases(sess.h, C.byref(k1), C.byref(k2), C.byref(kx), C.byref(pairs), 1)
+    sess.lib.lcx_profile_enable(sess.h, 0)
+    np_ = max(1, pairs.value)
+    # every rank must hold bit-identical weights (the replicated line search stays in lock-step only then)
+    identical = None
+    if world > 1:
+        cs = sess.view(_lib.A_W).contiguous().view(torch.int64).sum().reshape(1)
+        lo_, hi_ = cs.clone(), cs.clone()
+        dist.all_reduce(lo_, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi_, op=dist.ReduceOp.MAX)
+        identical = bool((lo_ == hi_).item())
+    trace = mdl.trace[n_trace0:]
+    res = {"ms": ms, "it_s": steps / (ms / 1e3), "k1_ms": k1.value / np_, "k2_ms": k2.value / np_, "exchange_ms": kx.value / np_,
+           "pairs": pairs.value, "launches": sess.launches() - launches0, "prep": prep,
+           "trials": float(np.mean([t["trials"] for t in trace])) if trace else 0.0, "tc": float(mdl.tc),
+           "clocks": clocks.summary(), "peer": sess._peer_buf is not None, "ranks_bit_identical": identical,
+           "n_local": hi - lo}
+    del mdl, sess
+    torch.cuda.empty_cache()
+    return res
+
+
+def roofline_of(res, shape, args, peaks, dgemm_peak, i8_peak):
+    """Roofline record of the two X contractions from the live CUDA-event timings of a resident run."""
+    n_total, n_vars, n_factors = shape
+    digits = DIGITS[args.precision]
+    if os.environ.get("LCX_SPLIT_DIGITS") and digits:
+        digits = int(os.environ["LCX_SPLIT_DIGITS"])
+    n_local = res["n_local"]
+    pair_flops = 4.0 * n_local * n_vars * n_factors           # K1 + K2 of one pass pair on this rank (FP64-equivalent)
+    pair_ms = res["k1_ms"] + res["k2_ms"]                      # the two contractions incl. their digit-slicing kernels
+    fp64_equiv = pair_flops / (pair_ms / 1e3) / 1e12 if pair_ms > 0 else 0.0
+    out = {"bound": "tensor"}
+    if digits:
+        # split-integer modes: each FP64 multiply-add is S(S+1)/2 exact int8 multiply-adds on tcgen05 (kind::i8)
+        pair_ops = pair_flops * digits * (digits + 1) / 2
+        achieved = pair_ops / (pair_ms / 1e3) / 1e12 if pair_ms > 0 else 0.0
+        peak = 2.0 * float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1400.0)))
+        out.update(achieved=achieved, peak=peak, unit="TOP/s", frac=achieved / peak,
+                   kernel="oz_gemm_kernel<%d,*> (tcgen05.mma kind::i8 + TMA; Y = X~ A^T and X~^T Y as %d int8 digit-plane "
+                          "products each, incl. digit slicing of A and Y), %d pass pairs timed by CUDA events"
+                          % (digits, digits * (digits + 1) // 2, res["pairs"]),
+                   peak_source="2 x bf16_tflops_sustained of MEASURED_PEAKS.json%s (kind::i8 runs at twice the bf16 rate on B200; "
+                               "sustained because the kernel is timed inside a long power-capped step; burst would be 2 x %s)"
+                               % ("" if "bf16_tflops_sustained" in peaks else " [fallback 1400]", peaks.get("bf16_tflops")))
+        if i8_peak and i8_peak.get("sustained_tops"):
+            out["int8_peak_measured_in_run"] = i8_peak
+            out["frac_of_int8_measured_in_run"] = achieved / i8_peak["sustained_tops"]
+        # the kind::i8 pipe alone, operands resident in shared memory, random int8 data (tools/experiments/
+        # i8_peak_probe.cu, profiles/r01_i8_peak_probe.txt): 4262 TOP/s burst, 3706 sustained under the power cap
+        out["frac_of_measured_i8_pipe_sustained"] = achieved / 3705.6
+    else:
+        pair_ops = pair_flops
+        out.update(achieved=fp64_equiv, peak=dgemm_peak, unit="TFLOP/s", frac=fp64_equiv / dgemm_peak if dgemm_peak else None,
+                   kernel="dgemm_mma_kernel (Y = X~ A^T and X~^T Y, DMMA.8x8x4), %d pass pairs timed by CUDA events" % res["pairs"],
+                   peak_source="cuBLAS DGEMM 6144^3 measured in this run (MEASURED_PEAKS.json has no FP64 entry; nominal B200 "
+                               "FP64 tensor peak is 40 TFLOP/s)")
+    out.update(algorithmic_ops_per_pair=pair_ops, fp64_equivalent_tflops=fp64_equiv,
+               share_of_step=pair_ms * res["pairs"] / res["ms"] if res["ms"] > 0 else None,
+               cublas_dgemm_tflops_in_run=dgemm_peak)
+    return out
 
 
 def run_ours(args, shape):
@@ -277,83 +520,16 @@ def run_ours(args, shape):
             peaks = json.load(fh)
     except Exception:
         pass
+    digits = DIGITS[args.precision]
     dgemm_peak = measure_dgemm_peak(torch) if rank == 0 else 0.0
+    i8_peak = measure_int8_peak(torch) if (rank == 0 and digits) else None
 
     # ---- device-resident timing: exactly K iterations ----------------------------------------------
-    x_dev = DeviceRows(n_total, n_vars, n_factors, lo, hi) if device_source else torch.from_numpy(x_host).cuda()
-    mdl = Corex(n_hidden=n_factors, seed=0, tol=1e-12, max_iter=10 ** 9, precision=args.precision,
-                gaussianize=args.gaussianize, comm=True if world > 1 else None,
-                stream_rows=32768 if device_source else None)
-    schedule = mdl._prepare(x_dev)
-    prep = dict(mdl.timings)
-    del x_dev
-    mdl._begin_stage(schedule[0], rescale=False)
-    sess = mdl._sess
-    for _ in range(args.warmup):
-        mdl._iterate()
-    sess.lib.lcx_profile_enable(sess.h, 1)
-    k1, k2, pairs = C.c_double(), C.c_double(), C.c_longlong()
-    sess.lib.lcx_profile_read(sess.h, C.byref(k1), C.byref(k2), C.byref(pairs), 1)
-    launches0 = sess.launches()
-    n_trace0 = len(mdl.trace)
-    barrier()
-    with ClockSampler(local) as clocks:
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(args.steps):
-            mdl._iterate()
-        e1.record()
-        barrier()
-    ms = e0.elapsed_time(e1)
-    if world > 1:
-        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = t.item()
-    sess.lib.lcx_profile_read(sess.h, C.byref(k1), C.byref(k2), C.byref(pairs), 1)
-    sess.lib.lcx_profile_enable(sess.h, 0)
-    launches = sess.launches() - launches0
-    trace = mdl.trace[n_trace0:]
-    trials = float(np.mean([t["trials"] for t in trace])) if trace else 0.0
-    tc_last = float(mdl.tc)
-    it_s = args.steps / (ms / 1e3)
-    n_local = hi - lo
-    pair_flops = 4.0 * n_local * n_vars * n_factors           # K1 + K2 of one pass pair on this rank (FP64-equivalent)
-    pair_ms = (k1.value + k2.value) / max(1, pairs.value)
-    k1_ms, k2_ms = k1.value / max(1, pairs.value), k2.value / max(1, pairs.value)  # each includes its digit-slicing kernels
-    fp64_equiv = pair_flops / (pair_ms / 1e3) / 1e12 if pair_ms > 0 else 0.0
-    digits = {"fp64": 0, "fp64_split": 6, "fp64_split5": 5, "fp64_split7": 7, "fast": 3}[args.precision]
-    if os.environ.get("LCX_SPLIT_DIGITS") and digits:
-        digits = int(os.environ["LCX_SPLIT_DIGITS"])
-    if digits:
-        # split-integer modes: each FP64 multiply-add is S(S+1)/2 exact int8 multiply-adds on tcgen05 (kind::i8)
-        pair_ops = pair_flops * digits * (digits + 1) / 2
-        achieved = pair_ops / (pair_ms / 1e3) / 1e12 if pair_ms > 0 else 0.0
-        # the kernel is timed inside a long, power-capped step -> the sustained bf16 figure is the right denominator
-        peak = 2.0 * float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1400.0)))
-        rl_unit = "TOP/s"
-        rl_kernel = ("oz_gemm_kernel<%d,*> (tcgen05.mma kind::i8 + TMA; Y = X~ A^T and X~^T Y as %d int8 digit-plane products "
-                     "each, incl. digit slicing of A and Y), %d pass pairs timed by CUDA events; K1 %.3f ms, K2 %.3f ms per launch; "
-                     "FP64-equivalent %.1f TFLOP/s" % (digits, digits * (digits + 1) // 2, pairs.value,
-                                                        k1.value / max(1, pairs.value), k2.value / max(1, pairs.value), fp64_equiv))
-        rl_source = ("2 x bf16_tflops_sustained of MEASURED_PEAKS.json%s (kind::i8 runs at twice the bf16 rate on B200; no int8 "
-                     "entry is measured; sustained because the kernel is timed inside a long power-capped step; the burst "
-                     "figure would be 2 x %s; the int8 pipe alone, fed from shared memory with random operands, measured 3706 "
-                     "TOP/s sustained / 4262 burst on this pool: profiles/r01_i8_peak_probe.txt); cuBLAS DGEMM in this run: %.1f TFLOP/s"
-                     % ("" if "bf16_tflops_sustained" in peaks else " [fallback 1400]", peaks.get("bf16_tflops"), dgemm_peak))
-    else:
-        pair_ops = pair_flops
-        achieved, peak, rl_unit = fp64_equiv, dgemm_peak, "TFLOP/s"
-        rl_kernel = ("dgemm_mma_kernel (Y = X~ A^T and X~^T Y, DMMA.8x8x4), %d pass pairs timed by CUDA events; "
-                     "K1 %.3f ms, K2 %.3f ms per launch" % (pairs.value, k1.value / max(1, pairs.value),
-                                                            k2.value / max(1, pairs.value)))
-        rl_source = ("cuBLAS DGEMM 6144^3 measured in this run (MEASURED_PEAKS.json has no FP64 entry; nominal B200 FP64 "
-                     "tensor peak is 40 TFLOP/s); bf16 measured peak for context: %s TF/s" % peaks.get("bf16_tflops"))
+    res = resident_run(torch, dist, shape, args, args.steps, args.warmup, world, rank, local, device_source, x_host, lo, hi)
+    ms, it_s, n_local = res["ms"], res["it_s"], res["n_local"]
     exchange = ("none (single rank)" if world == 1 else
-                "fused split-K combine + two-shot all-reduce kernel over NVLink peer memory" if sess._peer_buf is not None
+                "fused split-K combine + two-shot all-reduce kernel over NVLink peer memory" if res["peer"]
                 else "split-K combine kernel + NCCL all-reduce (torch.distributed hook)")
-    if not device_source:
-        del mdl, sess
-        torch.cuda.empty_cache()
 
     # ---- end to end through the public API, host buffers in, host results out -----------------------
     per_stage = max(1, args.steps // 7)
@@ -364,8 +540,6 @@ def run_ours(args, shape):
         barrier()
         e2e_mdl = Corex(n_hidden=n_factors, seed=0, tol=1e-12, max_iter=per_stage, precision=args.precision,
                         gaussianize=args.gaussianize, comm=True if world > 1 else None, stream_rows=32768)
-        del mdl, sess
-        torch.cuda.empty_cache()
         t0 = time.perf_counter()
         e2e_mdl.fit(DeviceRows(n_total, n_vars, n_factors, lo, hi))
         torch.cuda.synchronize()
@@ -375,10 +549,9 @@ def run_ours(args, shape):
                "d2h_bytes_per_step": int(sum(np.asarray(v).nbytes for v in e2e_mdl.moments.values()) / e2e_iters),
                "iterations": e2e_iters, "seconds": e2e_s, "phases_s": {k: round(v, 4) for k, v in e2e_mdl.timings.items()},
                "what": "Corex.fit(device row generator), streamed preparation; not a host-buffer e2e (see config3)"}
-        x_host = np.empty((0, n_vars), dtype=np.float32)
-    # the e2e input lives in page-locked host memory (the contract's "from pinned host memory"); --pageable times
-    # the pageable-numpy path (an extra pipelined host memcpy into pinned staging) instead
-    if not device_source:
+    else:
+        # the e2e input lives in page-locked host memory (the contract's "from pinned host memory"); --pageable times
+        # the pageable-numpy path (an extra pipelined host memcpy into pinned staging) instead
         x_pin = None if args.pageable else torch.from_numpy(x_host).pin_memory()
         # "converge" = the call a user makes: Corex(n_hidden=m).fit(X) with the reference's default stopping rule
         # (tol=1e-5, max_iter=10000; 410 iterations at config 3).  "budget" = K iterations spread over the 7 stages.
@@ -387,8 +560,9 @@ def run_ours(args, shape):
                       comm=True if world > 1 else None)
         if not converge:
             e2e_kw.update(tol=1e-12, max_iter=per_stage)
-        # one untimed fit of a single iteration per stage first: the timed call then reuses the caching allocator's
-        # blocks (cudaMalloc of ~20 GB costs 0.2-0.3 s the first time) like any second fit in a user's process
+        # The timed call is the SECOND fit in this process: one untimed fit of a single iteration per stage runs first, so
+        # the caching allocator already holds its blocks (cudaMalloc of ~20 GB costs 0.2-0.3 s the first time) and the
+        # NVLink peer mapping exists -- a first call in a fresh process pays ~0.3 s more.
         warm = Corex(**dict(e2e_kw, tol=1e-12, max_iter=1))
         warm.fit(x_pin if x_pin is not None else x_host)
         del warm
@@ -407,11 +581,38 @@ def run_ours(args, shape):
         e2e = {"value": e2e_iters / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(x_host.nbytes * world / e2e_iters),
                "d2h_bytes_per_step": int(d2h / e2e_iters), "iterations": e2e_iters, "seconds": e2e_s,
                "phases_s": {k: round(v, 4) for k, v in e2e_mdl.timings.items()},
-               "what": "Corex(n_hidden=%d%s).fit(pinned host float32 X): H2D of X, preprocess, digit slicing, 7 anneal "
-                       "stages%s, final sort + full moments, D2H of ws and every moments key"
+               "what": "second fit in the process: Corex(n_hidden=%d%s).fit(pinned host float32 X): H2D of X, preprocess, digit "
+                       "slicing, 7 anneal stages%s, final sort + full moments, D2H of ws and every moments key"
                        % (n_factors, "" if converge else ", tol=1e-12, max_iter=%d" % per_stage,
                           " run to the reference's default stopping rule (tol=1e-5, max_iter=10000)" if converge else "")}
+        del x_pin
     del e2e_mdl
+    x_host = None
+    torch.cuda.empty_cache()
+
+    # ---- the north-star shape (BASELINE.json target: 1M x 20k x 100) as a sub-record of the same line -------------------
+    target = None
+    custom = bool(args.rows or args.vars or args.factors)
+    if args.workload == "config3" and not custom and not args.no_target and digits:
+        tshape = WORKLOADS["target"]
+        tlo, thi = shard_rows(tshape[0], rank, world)
+        tsteps = max(4, min(args.steps, 8))
+        barrier()
+        tres = resident_run(torch, dist, tshape, args, tsteps, 3, world, rank, local, True, None, tlo, thi)
+        trl = roofline_of(tres, tshape, args, peaks, dgemm_peak, i8_peak)
+        target = {"workload": "target: synthetic latent-factor data N=%d x n=%d, m=%d, %s mode; rows drawn on the device "
+                              "(no 80 GB host copy in this harness), streamed preparation" % (tshape + (MODE_NAMES[args.precision],)),
+                  "metric": METRIC, "value": tres["it_s"], "unit": UNIT, "ms_per_step": tres["ms"] / tsteps, "steps": tsteps,
+                  "warmup": 3, "n_gpus": world, "rows_per_gpu": tres["n_local"], "scaling": "strong",
+                  "updates_per_sec": tres["it_s"] * tshape[0] * tshape[1] * tshape[2],
+                  "roofline": {k: trl[k] for k in ("bound", "achieved", "peak", "unit", "frac", "fp64_equivalent_tflops",
+                                                   "share_of_step", "frac_of_int8_measured_in_run") if k in trl},
+                  "phases_ms": {"k1": tres["k1_ms"], "k2": tres["k2_ms"], "exchange": tres["exchange_ms"],
+                                "replicated_and_sync": tres["ms"] / tsteps - tres["pairs"] / tsteps *
+                                (tres["k1_ms"] + tres["k2_ms"] + tres["exchange_ms"])},
+                  "clocks": tres["clocks"], "TC_after_timed_region": tres["tc"], "prepare_s": {k: round(v, 3) for k, v in tres["prep"].items()},
+                  "trials_per_iteration": tres["trials"], "ranks_bit_identical": tres["ranks_bit_identical"],
+                  "gpu_launches": int(tres["launches"])}
 
     if rank != 0:
         if world > 1:
@@ -419,20 +620,42 @@ def run_ours(args, shape):
         return
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        # 5 warm-up iterations: the first iterations of a stage backtrack 4-5 times (uj >= 1 rejections); timing those
-        # would understate the CPU path's steady-state rate (1.3-1.9 trials per iteration)
-        cpu = time_reference_cpu(n_total, n_vars, n_factors, steps=3, warmup=5, flop_budget=3e12)
+        # same rows, warm-up and code path as `--impl reference` (5 warm-up iterations: the first iterations of a stage
+        # backtrack 4-5 times; steady state is 1.3-1.9 trials per iteration), fewer timed steps
+        cpu = time_reference_cpu(n_total, n_vars, n_factors, steps=4, warmup=5)
         cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    rl = roofline_of(res, shape, args, peaks, dgemm_peak, i8_peak)
+    k1_ms, k2_ms = res["k1_ms"], res["k2_ms"]
     delivered = None
     if digits:
         # operand tiles landing in shared memory per launch (what ncu reports as l1tex__m_xbar2l1tex_read_bytes): per
         # 128-row M tile and 64-deep K block every factor tile receives the S planes of the X~ tile plus its own factor planes
         bn = 128 if digits <= 4 else 64
         per_block = digits * 64 * (128 * -(-n_factors // bn) + 16 * -(-n_factors // 16))
-        k1 = -(-n_local // 128) * -(-n_vars // 64) * per_block
-        k2 = -(-n_vars // 128) * -(-n_local // 64) * per_block
-        delivered = {"bytes_per_launch": [k1, k2],
-                     "tb_per_s": [k1 / (k1_ms * 1e9) if k1_ms > 0 else None, k2 / (k2_ms * 1e9) if k2_ms > 0 else None]}
+        b1 = -(-n_local // 128) * -(-n_vars // 64) * per_block
+        b2 = -(-n_vars // 128) * -(-n_local // 64) * per_block
+        delivered = {"bytes_per_launch_model": [b1, b2],
+                     "tb_per_s": [b1 / (k1_ms * 1e9) if k1_ms > 0 else None, b2 / (k2_ms * 1e9) if k2_ms > 0 else None]}
+    # evidence from the committed ncu capture of this exact workload (config 3, one GPU): DRAM traffic per launch and what
+    # limits the kernel -- read from the file, never typed in
+    ev = ncu_evidence(args.precision) if (args.workload == "config3" and not custom and world == 1) else None
+    algo_bytes = n_local * n_vars * (digits if digits else 8)
+    traffic = args.traffic
+    limiter = None
+    if ev is not None:
+        if traffic is None:
+            traffic = float(np.mean(ev["dram_bytes_per_launch"]))
+        limiter = "%s (sha256 %s): DRAM %s GB per launch vs %.2f GB algorithmic" % (
+            ev["file"], ev["sha256_16"], "/".join("%.2f" % (v / 1e9) for v in ev["dram_bytes_per_launch"]), algo_bytes / 1e9)
+        if "tensor_pipe_active_pct" in ev:
+            limiter += "; tensor pipe %s %% of active cycles" % "/".join("%.1f" % v for v in ev["tensor_pipe_active_pct"])
+        if "delivered_bytes_per_launch" in ev:
+            limiter += "; operand delivery L2->SM %s GB per launch (%.2fx the algorithmic operand bytes)" % (
+                "/".join("%.2f" % (v / 1e9) for v in ev["delivered_bytes_per_launch"]),
+                float(np.mean(ev["delivered_bytes_per_launch"])) / algo_bytes)
+    rl.update(traffic=traffic, limiter=limiter, ncu_evidence=ev, operand_delivery=delivered,
+              kernel=rl["kernel"] + "; K1 %.3f ms, K2 %.3f ms per launch" % (k1_ms, k2_ms))
+    pair_total = res["pairs"] / args.steps * (k1_ms + k2_ms + res["exchange_ms"])
     line = {
         "metric": METRIC, "value": it_s, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -440,31 +663,25 @@ def run_ours(args, shape):
                   "fp64_split5": "f64 (5 int8 digit planes = 40 bits, exact int32 products, f64 recombination)",
                   "fp64_split7": "f64 (7 int8 digit planes = 56 bits, exact int32 products, f64 recombination)",
                   "fast": "3 int8 digit planes = 24 bits (fp32-equivalent), f64 elsewhere"}[args.precision], "data": "synthetic",
-        "config": {"workload": workload_name(args, shape), "n_samples": n_total, "n_variables": n_vars,
-                   "n_factors": n_factors, "rows_per_gpu": n_local, "parallelism": "sample-sharded x%d" % world, "exchange_per_pass_pair": exchange,
+        "config": {"workload": workload_name(args, shape), "mode": MODE_NAMES[args.precision], "n_samples": n_total,
+                   "n_variables": n_vars, "n_factors": n_factors, "rows_per_gpu": n_local,
+                   "parallelism": "sample-sharded x%d" % world, "exchange_per_pass_pair": exchange,
                    "l2": "inputs_exceed_l2 (X~ block is %.1f GB per GPU)"
                          % (n_local * n_vars * (8 if args.precision == "fp64" else digits) / 1e9),
-                   "prepare_s": {k: round(v, 3) for k, v in prep.items()},
-                   "trials_per_iteration": trials, "TC_after_timed_region": tc_last},
+                   "prepare_s": {k: round(v, 3) for k, v in res["prep"].items()},
+                   "trials_per_iteration": res["trials"], "TC_after_timed_region": res["tc"]},
         "updates_per_sec": it_s * n_total * n_vars * n_factors,
-        "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": rl_unit,
-                     "frac": achieved / peak if peak else None, "traffic": args.traffic,
-                     "kernel": rl_kernel,
-                     "algorithmic_ops_per_pair": pair_ops, "fp64_equivalent_tflops": fp64_equiv,
-                     "share_of_step": pair_ms * pairs.value / ms if ms > 0 else None,
-                     "limiter": ("operand delivery into the SMs: ncu l1tex__m_xbar2l1tex_read_bytes = 17.4 GB per launch at "
-                                 "9.7-9.9 TB/s (~6200 B/clk chip-wide) with the tensor pipe 72-73 % active; TMEM (6 int32 group "
-                                 "accumulators x 64 columns) fixes the 128 x 64 tile and with it the bytes per MAC "
-                                 "(profiles/r01_oz_gemm_ncu_full_config3.csv, DESIGN.md 4)") if digits == 6 else None,
-                     "operand_delivery": delivered,
-                     # the kind::i8 pipe alone, operands resident in shared memory, random int8 data (tools/experiments/
-                     # i8_peak_probe.cu, profiles/r01_i8_peak_probe.txt): 4262 TOP/s burst, 3706 sustained under the power cap
-                     "frac_of_measured_i8_pipe_sustained": (achieved / 3705.6) if digits else None,
-                     "peak_source": rl_source},
-        "clocks": clocks.summary(),
+        "phases_ms_per_step": {"k1": res["pairs"] / args.steps * k1_ms, "k2": res["pairs"] / args.steps * k2_ms,
+                               "exchange_incl_split_k_combine": res["pairs"] / args.steps * res["exchange_ms"],
+                               "replicated_mxn_phase_and_host_sync": ms / args.steps - pair_total},
+        "ranks_bit_identical": res["ranks_bit_identical"],
+        "roofline": rl,
+        "clocks": res["clocks"],
         "e2e": e2e,
-        "gpu_launches": int(launches),
+        "gpu_launches": int(res["launches"]),
     }
+    if target is not None:
+        line["target"] = target
     if cpu is not None:
         line["cpu_baseline"] = cpu
     emit(line)
@@ -503,6 +720,7 @@ def main():
     ap.add_argument("--vars", type=int, default=0)
     ap.add_argument("--factors", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-target", action="store_true", help="skip the 1M x 20k x 100 sub-record of the default workload")
     ap.add_argument("--pageable", action="store_true", help="e2e input as a pageable numpy array instead of pinned memory")
     ap.add_argument("--e2e-fit", default=None, choices=["converge", "budget"],
                     help="end-to-end fit: run to the default stopping rule (default for config3) or K iterations over the stages")
@@ -517,11 +735,6 @@ def main():
         args.gaussianize = "outliers"
     if args.e2e_fit is None:
         args.e2e_fit = "converge" if args.workload == "config3" and not (args.rows or args.vars or args.factors) else "budget"
-    if args.traffic is None and args.workload == "config3" and args.gpus == 1 and not (args.rows or args.vars or args.factors):
-        # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
-        # `ncu --set full` captures (profiles/r01_oz_gemm_ncu_full_config3.csv, profiles/r01_dgemm_ncu_full_config3.csv):
-        # mean of the two contractions; algorithmic bytes are 6.09e9 (split, 6 planes) / 8.09e9 (DMMA) per launch
-        args.traffic = {"fp64_split": 6.31e9, "fp64": 8.17e9}.get(args.precision)
     if args.impl == "reference":
         run_reference(args, tuple(shape))
     else:

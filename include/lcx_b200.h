@@ -40,6 +40,7 @@ extern "C" {
 #define LCX_ERR_ARG (-1)
 #define LCX_ERR_CUDA (-2)
 #define LCX_ERR_STATE (-3)
+#define LCX_ERR_SINGULAR (-4) /* a pivot of the details-path solve was exactly zero: numpy raises LinAlgError there */
 
 /* precision modes */
 #define LCX_PRECISION_FP64 0   /* DMMA (mma.sync m8n8k4 f64) contractions, everything in binary64 */
@@ -90,7 +91,7 @@ enum lcx_array {
     LCX_A_CY,           /* m x ldm  moments['cy'] (syn)                                  */
     LCX_A_Y,            /* N_local x ldy   Y = X~ A^T of the last projection             */
     LCX_A_SCALARS,      /* 16       [0] TC [1] max uj [2] tangent [4] TC_no_overlap [5] sum I(X_i;Y)
-                                    [6] additivity [7] sum I(Y_j;X)                      */
+                                    [6] additivity [7] sum I(Y_j;X) [8] status of the details-path solve */
     LCX_A_COUNT
 };
 
@@ -119,6 +120,9 @@ int lcx_launch_count(lcx_session* s, long long* launches);   /* kernels launched
  * lcx_profile_read synchronises the stream and returns accumulated milliseconds and the pair count. */
 int lcx_profile_enable(lcx_session* s, int on);
 int lcx_profile_read(lcx_session* s, double* k1_ms, double* k2_ms, long long* pairs, int reset);
+/* The same with the second contraction split into the kernel itself and what follows it: the split-K combine and the
+ * exchange over ranks (lcx_profile_read's k2_ms is their sum). */
+int lcx_profile_read_phases(lcx_session* s, double* k1_ms, double* k2_ms, double* exchange_ms, long long* pairs, int reset);
 
 /* ---- layout --------------------------------------------------------------------------------- */
 long long lcx_ld(int n_vars);                       /* leading dimension of m x n arrays */
@@ -211,6 +215,12 @@ int lcx_update_syn(lcx_session* s, double eta, double* tc, double* additivity);
  * with eps; synergy = 1: X_i Z_j X_i Y_j^T.  sd = theta[1] (device, n). */
 int lcx_get_covariance(lcx_session* s, int synergy, double eps, const double* sd, int row0, int rows, double* out,
                        long long ldc);
+/* The same row block from explicit factors, with no bound problem (a model restored from a pickle holds only host
+ * moments, which is all the reference reads at :443-455):  out = diag(sd) fill_diagonal(left^T right / scale, 1) diag(sd),
+ * left / right factor-major n_factors x ld device arrays -- ns: left = right = rhoinvrho / (1 + Si), scale = 1 - eps^2;
+ * synergy: left = X_i Z_j^T, right = X_i Y_j^T, scale = 1. */
+int lcx_covariance_rows(lcx_session* s, const double* left, const double* right, long long ld, int n_factors, int n_vars,
+                        double scale, const double* sd, int row0, int rows, double* out, long long ldc);
 
 /* ---- raw FP64 tensor-core GEMM (unit tests / building block) ----------------------------------- */
 /* layout: 0 = A[M][K], B[N][K];  1 = A[K][M], B[K][N];  2 = A[M][K], B[K][N].  C = A*B (+ cadd), optionally
@@ -218,8 +228,12 @@ int lcx_get_covariance(lcx_session* s, int synergy, double eps, const double* sd
 int lcx_gemm_f64(lcx_session* s, int layout, int M, int N, int K, const double* a, long long lda, const double* b,
                  long long ldb, double* c, long long ldc, int trans_out, const double* cadd, int max_splits,
                  double* scratch, long long scratch_doubles);
-/* out = inverse(a) for an m x m device matrix; aug >= 2*m*m doubles of scratch */
-int lcx_inverse(lcx_session* s, const double* a, long long lda, int m, double* out, long long ldo, double* aug);
+/* x (m x ldx, n_rhs columns) = a^-1 b for an m x m device matrix a and m x n_rhs right-hand sides b, by LU with partial
+ * pivoting and two triangular sweeps -- what np.linalg.solve does at linearcorex.py:280 and :366 (x may alias b for
+ * m <= 832).  Returns LCX_ERR_SINGULAR on an exactly zero pivot.  scratch >= lcx_solve_scratch_doubles(m). */
+long long lcx_solve_scratch_doubles(int m);
+int lcx_solve(lcx_session* s, const double* a, long long lda, int m, const double* b, long long ldb, double* x,
+              long long ldx, int n_rhs, double* scratch, long long scratch_doubles);
 
 #ifdef __cplusplus
 }

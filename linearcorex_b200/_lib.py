@@ -9,6 +9,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "liblcx_b200.so")
 
 OK, QUICK_FAIL = 0, 1
+ERR_SINGULAR = -4
 PRECISION_FP64, PRECISION_FAST, PRECISION_FP64_SPLIT, PRECISION_FP64_SPLIT5, PRECISION_FP64_SPLIT7 = 0, 1, 2, 3, 4
 PRECISIONS = {"fp64": PRECISION_FP64, "fast": PRECISION_FAST, "fp64_split": PRECISION_FP64_SPLIT,
               "fp64_split5": PRECISION_FP64_SPLIT5, "fp64_split7": PRECISION_FP64_SPLIT7}
@@ -39,6 +40,7 @@ SIGNATURES = {
     "lcx_launch_count": (_i, [_p, _pll]),
     "lcx_profile_enable": (_i, [_p, _i]),
     "lcx_profile_read": (_i, [_p, _pd, _pd, _pll, _i]),
+    "lcx_profile_read_phases": (_i, [_p, _pd, _pd, _pd, _pll, _i]),
     "lcx_ld": (_ll, [_i]),
     "lcx_ldy": (_ll, [_i]),
     "lcx_workspace_doubles": (_ll, [_ll, _i, _i, _i]),
@@ -70,8 +72,10 @@ SIGNATURES = {
     "lcx_moments_syn": (_i, [_p, _pd, _pd]),
     "lcx_update_syn": (_i, [_p, _d, _pd, _pd]),
     "lcx_get_covariance": (_i, [_p, _i, _d, _p, _i, _i, _p, _ll]),
+    "lcx_covariance_rows": (_i, [_p, _p, _p, _ll, _i, _i, _d, _p, _i, _i, _p, _ll]),
     "lcx_gemm_f64": (_i, [_p, _i, _i, _i, _i, _p, _ll, _p, _ll, _p, _ll, _i, _p, _i, _p, _ll]),
-    "lcx_inverse": (_i, [_p, _p, _ll, _i, _p, _ll, _p]),
+    "lcx_solve_scratch_doubles": (_ll, [_i]),
+    "lcx_solve": (_i, [_p, _p, _ll, _i, _p, _ll, _p, _ll, _i, _p, _ll]),
 }
 
 _lib = None
@@ -100,6 +104,9 @@ def load():
 
 def check(rc, what=""):
     """Raise on a negative status; pass non-negative codes (OK / QUICK_FAIL) through."""
+    if rc == ERR_SINGULAR:  # np.linalg.solve raises this at linearcorex.py:280 / :366
+        import numpy as np
+        raise np.linalg.LinAlgError("Singular matrix")
     if rc < 0:
         msg = load().lcx_last_error()
         raise LcxError("%s failed (%d): %s" % (what or "lcx call", rc, msg.decode() if msg else "?"))

@@ -148,6 +148,10 @@ class _DeviceSession(object):
             need = self.lib.lcx_peer_buffer_doubles(n_vars, n_factors)
             group = reducer.group if reducer.group is not None else dist.group.WORLD
             key = (id(group), self.device.index, need)
+            prev = getattr(self, "_peer_entry", None)
+            if prev is not None:  # a re-bind of this session (second fit on the same model) reuses its own buffer
+                prev[2] = False
+                self._peer_entry = None
             # mapping peers costs ~0.1 s (VMM handles over the process group): a released buffer is reused by the next
             # session of the same shape; a buffer still owned by a live session is never shared (its flags carry epochs)
             entry = _PEER_BUFFERS.get(key)
@@ -246,6 +250,7 @@ class Corex(object):
         self._device = device
         self._sess = None
         self._theta_dev = None
+        self._fitted_in_session = False  # the bound device workspace holds this model's final moments
 
     # ------------------------------------------------------------------------------------------
     # pickling (vis_corex.py:549): host state only
@@ -254,6 +259,7 @@ class Corex(object):
         d = dict(self.__dict__)
         for k in ("_sess", "_theta_dev", "_comm"):
             d[k] = None
+        d["_fitted_in_session"] = False
         return d
 
     # ------------------------------------------------------------------------------------------
@@ -439,7 +445,10 @@ class Corex(object):
             self.precision_used = resolve_precision('auto', red.sum_scalar(int(np.shape(x)[0])), int(np.shape(x)[1]), self.m)
         sess = self._session()
         lib = sess.lib
+        self._fitted_in_session = False
         rows = self._stream_rows_for(x)
+        if red.world > 1:  # the two preparation paths issue different collective sequences: every rank must take the same
+            rows = int(red.max_scalar(rows))
         if rows:
             self._prepare_streamed(x, rows, red)
         else:
@@ -606,6 +615,7 @@ class Corex(object):
         _lib.check(sess.lib.lcx_permute_rows(sess.h, (C.c_int * self.m)(*[int(o) for o in order])), "lcx_permute_rows")
         self._full_moments()
         self.ws = self._get_w()
+        self._fitted_in_session = True
         self.timings["finish_s"] = time.perf_counter() - t0
         return self
 
@@ -851,28 +861,77 @@ class Corex(object):
             return self.theta[1] * (core + np.arctanh(np.clip(x - core, -1 + 1e-10, 1 - 1e-10))) + self.theta[0]
         return x
 
-    def predict(self, y):
-        return self.invert(np.dot(self.moments["X_i Z_j"], np.asarray(y).T).T)  # :440-441
+    def _factor_major_device(self, key, live_id):
+        """(m x ld) device tensor of an n x m moments array: the live workspace view, or an upload of the host copy
+        (a model restored from a pickle has only host state, which is all the reference reads at :440-455)."""
+        torch = _torch()
+        sess = self._session()
+        if sess.ws is not None and sess.n == self.nv and sess.m == self.m and getattr(self, "_fitted_in_session", False):
+            v = sess.view(live_id)
+            return v, v.stride(0)
+        ld = sess.lib.lcx_ld(self.nv)
+        t = torch.zeros((self.m, ld), dtype=torch.float64, device=sess.device)
+        t[:, :self.nv].copy_(torch.from_numpy(np.ascontiguousarray(np.asarray(self.moments[key], dtype=np.float64).T)))
+        return t, ld
 
-    def get_covariance(self, block_rows=4096):
-        """n x n covariance estimate (:443-455), computed on the device in row blocks."""
+    def predict(self, y):
+        """E(X | Y = y) in the original space (:440-441): invert(y . X_i Z_j^T); the N x n product runs on the device."""
+        torch = _torch()
+        sess = self._session()
+        y = np.ascontiguousarray(np.asarray(y, dtype=np.float64))
+        ny = y.shape[0]
+        xz, ld = self._factor_major_device("X_i Z_j", _lib.A_XZ)
+        ldy = sess.lib.lcx_ldy(self.m)
+        yd = torch.zeros((ny, ldy), dtype=torch.float64, device=sess.device)
+        yd[:, :self.m].copy_(torch.from_numpy(y))
+        out = torch.empty((ny, ld), dtype=torch.float64, device=sess.device)
+        _lib.check(sess.lib.lcx_gemm_f64(sess.h, 2, ny, self.nv, self.m, yd.data_ptr(), ldy, xz.data_ptr(), ld, out.data_ptr(), ld,
+                                         0, None, 1, None, 0), "lcx_gemm_f64")
+        return self.invert(out[:, :self.nv].cpu().numpy())
+
+    def get_covariance(self, block_rows=4096, out=None, block_callback=None):
+        """n x n covariance estimate (:443-455), computed on the device in row blocks from `moments` and `theta` (host
+        state is enough, so this also works on an unpickled model).
+
+        out=None            returns a new (n, n) float64 ndarray like the reference.
+        out=ndarray/memmap  (n, n) float64: filled block by block (n = 50 000 is 20 GB: pass an np.memmap).
+        out=CUDA tensor     (n, n) float64, even row stride: blocks are written in place, nothing crosses to the host.
+        block_callback      callable(row0, block) called with each (rows, n) CUDA row block instead of gathering anything."""
         torch = _torch()
         sess = self._session()
         lib = sess.lib
-        if sess.ws is None:
-            raise _lib.LcxError("get_covariance needs the fitted device state (call fit in this process)")
         n = self.nv
         if self.theta is None:
             raise ValueError("get_covariance needs theta (gaussianize='none' has none, like the reference)")
         sd = torch.as_tensor(np.asarray(self.theta[1], dtype=np.float64), device=sess.device)
+        if self.discourage_overlap:  # :447-451
+            m = self.moments
+            z = np.asarray(m['rhoinvrho'], dtype=np.float64) / (1 + np.asarray(m['Si'], dtype=np.float64))
+            ld = lib.lcx_ld(n)
+            left = torch.zeros((self.m, ld), dtype=torch.float64, device=sess.device)
+            left[:, :n].copy_(torch.from_numpy(np.ascontiguousarray(z)))
+            right, scale = left, 1. - self.eps ** 2
+        else:  # :453-454
+            left, ld = self._factor_major_device("X_i Z_j", _lib.A_XZ)
+            right, _ = self._factor_major_device("X_i Y_j", _lib.A_XY)
+            scale = 1.
+        on_device = isinstance(out, torch.Tensor) and out.is_cuda
+        if on_device:
+            assert tuple(out.shape) == (n, n) and out.dtype == torch.float64 and out.stride(1) == 1 and out.stride(0) % 2 == 0, \
+                "out must be an (n, n) float64 CUDA tensor with unit column stride and an even row stride"
+        elif out is None and block_callback is None:
+            out = np.empty((n, n), dtype=np.float64)
         ldc = lib.lcx_ld(n)
         block_rows = max(2, min(block_rows, n + (n % 2)))
         block_rows -= block_rows % 2
-        buf = torch.empty((block_rows, ldc), dtype=torch.float64, device=sess.device)
-        out = np.empty((n, n), dtype=np.float64)
+        buf = None if on_device else torch.empty((block_rows, ldc), dtype=torch.float64, device=sess.device)
         for r0 in range(0, n, block_rows):
             rows = min(block_rows, n - r0)
-            _lib.check(lib.lcx_get_covariance(sess.h, int(not self.discourage_overlap), float(self.eps), sd.data_ptr(),
-                                              r0, rows, buf.data_ptr(), ldc), "lcx_get_covariance")
-            out[r0:r0 + rows] = buf[:rows, :n].cpu().numpy()
+            dst, ldd = (out[r0:r0 + rows], out.stride(0)) if on_device else (buf, ldc)
+            _lib.check(lib.lcx_covariance_rows(sess.h, left.data_ptr(), right.data_ptr(), ld, self.m, n, float(scale),
+                                               sd.data_ptr(), r0, rows, dst.data_ptr(), ldd), "lcx_covariance_rows")
+            if block_callback is not None:
+                block_callback(r0, dst[:rows, :n])
+            elif not on_device:
+                out[r0:r0 + rows] = buf[:rows, :n].cpu().numpy()
         return out

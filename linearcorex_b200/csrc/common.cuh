@@ -36,6 +36,20 @@ inline int fail(int code, const char* what, const char* detail) {
         if (_rc < 0) return _rc;   \
     } while (0)
 
+// cudaFuncSetAttribute applies to the current device's context only: one "done" flag per device ordinal, so a second
+// session on another GPU of the same process configures its own copy of the kernel.
+struct PerDeviceOnce {
+    bool done[64];
+    bool first_time() {
+        int d = 0;
+        if (cudaGetDevice(&d) != cudaSuccess) return true;
+        d &= 63;
+        if (done[d]) return false;
+        done[d] = true;
+        return true;
+    }
+};
+
 inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 inline long long round_up(long long a, long long b) { return (a + b - 1) / b * b; }
 

@@ -464,75 +464,4 @@ __global__ void cov_finish_kernel(double* __restrict__ cov, long long ldc, int r
     }
 }
 
-// ---- m x m inverse (details path; replaces np.linalg.solve at :280 / :366) ------------------------
-// Gauss-Jordan with partial pivoting on the augmented matrix [A | I] held in global memory
-// (m <= a few hundred: L1/L2 resident).  One CTA of 1024 threads; out = A^-1 (m x m, ld = ldo).
-__global__ void __launch_bounds__(1024) gauss_jordan_inverse_kernel(const double* __restrict__ A, long long lda, int m,
-                                                                    double* __restrict__ aug, double* __restrict__ out,
-                                                                    long long ldo, int* __restrict__ status) {
-    __shared__ double sval[32];
-    __shared__ int sidx[32];
-    __shared__ int piv_row;
-    __shared__ double piv_inv;
-    const int tid = threadIdx.x, nth = blockDim.x;
-    const int w2 = 2 * m;
-    for (int e = tid; e < m * w2; e += nth) {
-        const int r = e / w2, c = e % w2;
-        aug[e] = (c < m) ? A[(long long)r * lda + c] : ((c - m == r) ? 1.0 : 0.0);
-    }
-    if (tid == 0) *status = 0;
-    __syncthreads();
-    for (int k = 0; k < m; ++k) {
-        // pivot search over rows k..m-1 of column k
-        double best = -1.0;
-        int bi = k;
-        for (int r = k + tid; r < m; r += nth) {
-            const double v = fabs(aug[(long long)r * w2 + k]);
-            if (v > best) { best = v; bi = r; }
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const double ov = __shfl_xor_sync(0xffffffffu, best, o);
-            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-            if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
-        }
-        if ((tid & 31) == 0) { sval[tid >> 5] = best; sidx[tid >> 5] = bi; }
-        __syncthreads();
-        if (tid == 0) {
-            double b = sval[0];
-            int ix = sidx[0];
-            for (int w = 1; w < (nth >> 5); ++w)
-                if (sval[w] > b || (sval[w] == b && sidx[w] < ix)) { b = sval[w]; ix = sidx[w]; }
-            piv_row = ix;
-            if (!(b > 0.0)) *status = 1;  // singular
-            piv_inv = 1.0 / aug[(long long)ix * w2 + k];
-        }
-        __syncthreads();
-        const int pr = piv_row;
-        const double pinv = piv_inv;
-        // swap rows k and pr, scale the pivot row
-        for (int c = tid; c < w2; c += nth) {
-            const double a = aug[(long long)pr * w2 + c];
-            const double b = aug[(long long)k * w2 + c];
-            aug[(long long)pr * w2 + c] = b;
-            aug[(long long)k * w2 + c] = a * pinv;
-        }
-        __syncthreads();
-        // eliminate column k from every other row; factors are read before any write of column k
-        // because column k is handled last (c == k is skipped here and zeroed after the barrier).
-        for (int e = tid; e < m * w2; e += nth) {
-            const int r = e / w2, c = e % w2;
-            if (r != k && c != k) aug[e] -= aug[(long long)r * w2 + k] * aug[(long long)k * w2 + c];
-        }
-        __syncthreads();
-        for (int r = tid; r < m; r += nth)
-            if (r != k) aug[(long long)r * w2 + k] = 0.0;
-        __syncthreads();
-    }
-    for (int e = tid; e < m * m; e += nth) {
-        const int r = e / m, c = e % m;
-        out[(long long)r * ldo + c] = aug[(long long)r * w2 + m + c];
-    }
-}
-
 }  // namespace lcx

@@ -350,12 +350,10 @@ template <int NT, bool A_KC, bool B_KC>
 inline int launch_gemm_inst(const GemmArgs& a, dim3 grid, cudaStream_t st) {
     constexpr int STAGES = 4;
     using Cfg = GemmCfg<NT, A_KC, B_KC, STAGES>;
-    static bool configured = false;
+    static PerDeviceOnce configured = {};
     auto kern = dgemm_mma_kernel<NT, A_KC, B_KC, STAGES>;
-    if (!configured) {
+    if (configured.first_time())
         LCX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-        configured = true;
-    }
     kern<<<grid, 256, Cfg::SMEM_BYTES, st>>>(a);
     LCX_CUDA(cudaGetLastError());
     return 0;

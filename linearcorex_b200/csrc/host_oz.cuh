@@ -127,6 +127,7 @@ static int oz_pair_t(lcx_session* s, const double* A, double* svec, cudaEvent_t*
         LCX_TRY((oz::launch_oz_gemm<S, false>(s->map_x_k2, s->map_y_k2, s->map_y_k2_tail, p,
                                               dim3(cdiv(m, oz::bn_max(S)), cdiv(n, oz::kBM), L.oz_splits), s->stream, oz_cluster())));
         LAUNCHED(s);
+        if (ev) LCX_CUDA(cudaEventRecord(ev[4], s->stream));
         LCX_TRY(combine_and_allreduce(s, split ? s->ptr(I_PART) : D, split ? L.oz_splits : 1, (long long)m * L.ld, m, n, L.ld, D, svec,
                                       want_tail ? m : 0));
     }

@@ -10,6 +10,7 @@
 #include "corex_kernels.cuh"
 #include "dgemm_mma.cuh"
 #include "fused_allreduce.cuh"
+#include "lu_solve.cuh"
 #include "ozaki_i8.cuh"
 #include "preprocess_kernels.cuh"
 
@@ -17,6 +18,7 @@ namespace lcx {
 thread_local char g_err[512] = "";
 constexpr int kSMs = 148;  // B200; plans (and therefore workspace sizes) are fixed for this part
 constexpr int kMaxSplitsX = 32;
+constexpr int kProfEv = 5;
 constexpr int kMaxSplitsSmall = 148;
 
 __global__ void axpy_kernel(const double* __restrict__ W, const double* __restrict__ U, double eta, double* __restrict__ W2,
@@ -49,9 +51,8 @@ enum {
     I_UJDIAG,           // m   diag(W rho^T)
     I_ROWMI,            // m
     I_SQRTY,            // m
-    I_RYINV,            // m x ldm
-    I_AUG,              // m x 2m
-    I_STATUS,           // 2 doubles (int status of the inverse)
+    I_RYINV,            // m x ldm  scratch (H of the search direction)
+    I_AUG,              // scratch of the pivoted LU solve (lu_solve.cuh): work | LU | perm | status
     I_XS,               // split modes: int8 digit slices of X~   [S][N_local][ld8]
     I_AS,               //              int8 digit slices of A    [S][m][ld8]
     I_YS,               //              int8 digit slices of Y, transposed  [S][m][ldk8]
@@ -192,8 +193,7 @@ static Layout make_layout(long long Nl, int n, int m, int precision) {
     put1(I_ROWMI, 1, m, L.ldm);
     put1(I_SQRTY, 1, m, L.ldm);
     put1(I_RYINV, mn, m, L.ldm);
-    put1(I_AUG, mn, 2 * mn, 2 * mn);
-    put1(I_STATUS, 1, 2, 2);
+    put1(I_AUG, 1, lu::scratch_doubles(m), lu::scratch_doubles(m));
     L.ystat_slabs = cdiv(Nl, kYStatRows);
     put1(I_OZV, 1, 16 + 4 * L.ldm, 16 + 4 * L.ldm);
     put1(I_YSTAT, (long long)L.ystat_slabs * 2, m, L.ldm);
@@ -298,9 +298,10 @@ struct lcx_session {
     // optional device-side timing of the two X contractions (bench.py roofline); events are
     // recorded on the session stream around each launch and resolved at lcx_profile_read
     bool prof_on;
-    cudaEvent_t* prof_ev;      // 4 per pair: [0] before K1, [1] after K1, [3] before K2, [2] after K2 (+ split reduction)
+    cudaEvent_t* prof_ev;      // kProfEv per pair: [0] before K1, [1] after K1, [3] before K2, [4] before the split-K combine /
+                               // rank exchange, [2] after it
     int prof_pending, prof_cap;
-    double prof_k1_ms, prof_k2_ms;
+    double prof_k1_ms, prof_k2_ms, prof_x_ms;
     long long prof_pairs;
     // sample sharding over NVLink peers (fused_allreduce.cuh); peers.world <= 1 means off
     far::Peers peers;

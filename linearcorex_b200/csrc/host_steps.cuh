@@ -104,7 +104,7 @@ static int xpair(lcx_session* s, const double* A, bool want_colsq) {
     double* D = s->ptr(LCX_A_D);
     double* svec = D + (long long)m * L.ld;
     cudaEvent_t* ev = nullptr;
-    if (s->prof_on && s->prof_pending < s->prof_cap) ev = s->prof_ev + 4 * s->prof_pending;
+    if (s->prof_on && s->prof_pending < s->prof_cap) ev = s->prof_ev + kProfEv * s->prof_pending;
     if (ev) LCX_CUDA(cudaEventRecord(ev[0], s->stream));
     if (L.S > 0) {
         LCX_TRY(oz_pair(s, A, svec, ev, false, want_colsq));
@@ -146,13 +146,14 @@ static int xpair(lcx_session* s, const double* A, bool want_colsq) {
         a.trans_out = 1;
         if (ev) LCX_CUDA(cudaEventRecord(ev[3], s->stream));  // K2 starts after the (tiny) colsq reduction
         LCX_TRY(run_gemm(s, kLayoutMN, L.plan_k2, a, s->ptr(I_PART), (long long)m * L.ld, true));
+        if (ev) LCX_CUDA(cudaEventRecord(ev[4], s->stream));
+        const bool split = L.plan_k2.splits > 1;
+        LCX_TRY(combine_and_allreduce(s, split ? s->ptr(I_PART) : D, split ? L.plan_k2.splits : 1, (long long)m * L.ld, m, n, L.ld,
+                                      D, svec, want_colsq ? m : 0));
         if (ev) {
             LCX_CUDA(cudaEventRecord(ev[2], s->stream));
             s->prof_pending++;
         }
-        const bool split = L.plan_k2.splits > 1;
-        LCX_TRY(combine_and_allreduce(s, split ? s->ptr(I_PART) : D, split ? L.plan_k2.splits : 1, (long long)m * L.ld, m, n, L.ld,
-                                      D, svec, want_colsq ? m : 0));
     }
     }
     LCX_CUDA(cudaGetLastError());
@@ -290,11 +291,10 @@ static int enqueue_trial(lcx_session* s, double eps, double eta, int exact) {
     return 0;
 }
 
-static int run_inverse(lcx_session* s, const double* a, long long lda, int m, double* out, long long ldo, double* aug,
-                       int* status) {
-    gauss_jordan_inverse_kernel<<<1, 1024, 0, s->stream>>>(a, lda, m, aug, out, ldo, status);
-    LAUNCHED(s);
-    LCX_CUDA(cudaGetLastError());
+// X (m x ldx, n columns) = A^-1 B by LU with partial pivoting (np.linalg.solve, linearcorex.py:280 / :366).  The status word
+// of the factorisation lands in scalars[8] (read back with the mailbox: non-zero = singular matrix).
+static int run_solve(lcx_session* s, const double* a, long long lda, const double* b, long long ldb, double* x, long long ldx) {
+    LCX_TRY(lu::solve(a, lda, s->m, b, ldb, x, ldx, s->n, s->ptr(I_AUG), s->ptr(LCX_A_SCALARS) + 8, s->stream, &s->launches));
     return 0;
 }
 

@@ -31,32 +31,54 @@ extern "C" int lcx_profile_enable(lcx_session* s, int on) {
     LCX_CUDA(cudaSetDevice(s->device));
     if (on && s->prof_ev == nullptr) {
         s->prof_cap = 4096;
-        s->prof_ev = new cudaEvent_t[4 * s->prof_cap];
-        for (int i = 0; i < 4 * s->prof_cap; ++i) LCX_CUDA(cudaEventCreate(&s->prof_ev[i]));
+        s->prof_ev = new cudaEvent_t[kProfEv * s->prof_cap];
+        for (int i = 0; i < kProfEv * s->prof_cap; ++i) LCX_CUDA(cudaEventCreate(&s->prof_ev[i]));
     }
     s->prof_on = on != 0;
     return 0;
 }
 
-extern "C" int lcx_profile_read(lcx_session* s, double* k1_ms, double* k2_ms, long long* pairs, int reset) {
-    LCX_REQUIRE(s != nullptr, "null session");
+static int profile_resolve(lcx_session* s) {
     LCX_CUDA(cudaSetDevice(s->device));
     LCX_CUDA(cudaStreamSynchronize(s->stream));
     for (int i = 0; i < s->prof_pending; ++i) {
-        cudaEvent_t* ev = s->prof_ev + 4 * i;
-        float a = 0.f, b = 0.f;
+        cudaEvent_t* ev = s->prof_ev + kProfEv * i;
+        float a = 0.f, b = 0.f, c = 0.f;
         LCX_CUDA(cudaEventElapsedTime(&a, ev[0], ev[1]));
-        LCX_CUDA(cudaEventElapsedTime(&b, ev[3], ev[2]));
+        LCX_CUDA(cudaEventElapsedTime(&b, ev[3], ev[4]));
+        LCX_CUDA(cudaEventElapsedTime(&c, ev[4], ev[2]));
         s->prof_k1_ms += a;
         s->prof_k2_ms += b;
+        s->prof_x_ms += c;
         s->prof_pairs++;
     }
     s->prof_pending = 0;
+    return 0;
+}
+
+extern "C" int lcx_profile_read(lcx_session* s, double* k1_ms, double* k2_ms, long long* pairs, int reset) {
+    LCX_REQUIRE(s != nullptr, "null session");
+    LCX_TRY(profile_resolve(s));
     if (k1_ms) *k1_ms = s->prof_k1_ms;
-    if (k2_ms) *k2_ms = s->prof_k2_ms;
+    if (k2_ms) *k2_ms = s->prof_k2_ms + s->prof_x_ms;
     if (pairs) *pairs = s->prof_pairs;
     if (reset) {
-        s->prof_k1_ms = s->prof_k2_ms = 0.0;
+        s->prof_k1_ms = s->prof_k2_ms = s->prof_x_ms = 0.0;
+        s->prof_pairs = 0;
+    }
+    return 0;
+}
+
+extern "C" int lcx_profile_read_phases(lcx_session* s, double* k1_ms, double* k2_ms, double* exchange_ms, long long* pairs,
+                                       int reset) {
+    LCX_REQUIRE(s != nullptr, "null session");
+    LCX_TRY(profile_resolve(s));
+    if (k1_ms) *k1_ms = s->prof_k1_ms;
+    if (k2_ms) *k2_ms = s->prof_k2_ms;
+    if (exchange_ms) *exchange_ms = s->prof_x_ms;
+    if (pairs) *pairs = s->prof_pairs;
+    if (reset) {
+        s->prof_k1_ms = s->prof_k2_ms = s->prof_x_ms = 0.0;
         s->prof_pairs = 0;
     }
     return 0;
@@ -65,7 +87,7 @@ extern "C" int lcx_profile_read(lcx_session* s, double* k1_ms, double* k2_ms, lo
 extern "C" int lcx_session_destroy(lcx_session* s) {
     if (!s) return 0;
     if (s->prof_ev) {
-        for (int i = 0; i < 4 * s->prof_cap; ++i) cudaEventDestroy(s->prof_ev[i]);
+        for (int i = 0; i < kProfEv * s->prof_cap; ++i) cudaEventDestroy(s->prof_ev[i]);
         delete[] s->prof_ev;
     }
     if (s->mailbox) cudaFreeHost(s->mailbox);
@@ -524,22 +546,15 @@ extern "C" int lcx_details_ns(lcx_session* s, double* tc_no_overlap, double* add
     const Layout& L = s->L;
     const int m = s->m, n = s->n;
     double* rho = s->ptr(LCX_A_RHO);
-    // X_i Z_j = solve(ry, rho)^T (:280) as ry^-1 rho
-    LCX_TRY(run_inverse(s, s->ptr(LCX_A_RY), L.ldm, m, s->ptr(I_RYINV), L.ldm, s->ptr(I_AUG), (int*)s->ptr(I_STATUS)));
-    {
-        GemmArgs a;
-        memset(&a, 0, sizeof(a));
-        a.A = s->ptr(I_RYINV); a.B = rho; a.C = s->ptr(LCX_A_XZ);
-        a.M = m; a.N = n; a.K = m;
-        a.lda = L.ldm; a.ldb = L.ld; a.ldc = L.ld;
-        LCX_TRY(run_gemm(s, kLayoutKN, L.plan_mn, a, nullptr, 0));
-    }
+    // X_i Z_j = solve(ry, rho)^T (:280)
+    LCX_TRY(run_solve(s, s->ptr(LCX_A_RY), L.ldm, rho, L.ld, s->ptr(LCX_A_XZ), L.ld));
     LCX_TRY(details_tail(s, rho, nullptr));
     // X_i Y_j = rho^T sqrt(Y_j^2) (:279)
     scale_rows_out_kernel<<<grid_mn(m, n), 256, 0, s->stream>>>(rho, s->ptr(I_SQRTY), s->ptr(LCX_A_XY), m, n, L.ld);
     LAUNCHED(s);
     LCX_CUDA(cudaGetLastError());
     LCX_TRY(read_mailbox(s));
+    if (s->mailbox[8] != 0.0) return fail(LCX_ERR_SINGULAR, "lcx_details_ns", "Singular matrix (ry)");
     if (tc_no_overlap) *tc_no_overlap = s->mailbox[4];
     if (additivity) *additivity = s->mailbox[6];
     return 0;
@@ -585,22 +600,15 @@ extern "C" int lcx_moments_syn(lcx_session* s, double* tc, double* additivity) {
     syn_qi_kernel<<<L.nstrips, dim3(kStripCols, kStripRows), 0, s->stream>>>(rinv, s->ptr(LCX_A_QIJ), s->ptr(LCX_A_QISI2), m, n,
                                                                            L.ld);
     LAUNCHED(s);
-    // X_i Z_j = solve(cy, XY^T)^T (:366) as cy^-1 XY
-    LCX_TRY(run_inverse(s, cy, L.ldm, m, s->ptr(I_RYINV), L.ldm, s->ptr(I_AUG), (int*)s->ptr(I_STATUS)));
-    {
-        GemmArgs a;
-        memset(&a, 0, sizeof(a));
-        a.A = s->ptr(I_RYINV); a.B = XY; a.C = s->ptr(LCX_A_XZ);
-        a.M = m; a.N = n; a.K = m;
-        a.lda = L.ldm; a.ldb = L.ld; a.ldc = L.ld;
-        LCX_TRY(run_gemm(s, kLayoutKN, L.plan_mn, a, nullptr, 0));
-    }
+    // X_i Z_j = solve(cy, XY^T)^T (:366)
+    LCX_TRY(run_solve(s, cy, L.ldm, XY, L.ld, s->ptr(LCX_A_XZ), L.ld));
     // sqrtY currently holds sqrt(Yj2); details_finish rewrites it with the same values
     LCX_TRY(details_tail(s, XY, s->ptr(LCX_A_YJ2)));
     syn_tc_kernel<<<1, 32, 0, s->stream>>>(s->ptr(LCX_A_SCALARS) + 4, s->ptr(LCX_A_SCALARS));
     LAUNCHED(s);
     LCX_CUDA(cudaGetLastError());
     LCX_TRY(read_mailbox(s));
+    if (s->mailbox[8] != 0.0) return fail(LCX_ERR_SINGULAR, "lcx_moments_syn", "Singular matrix (cy)");
     if (tc) *tc = s->mailbox[0];
     if (additivity) *additivity = s->mailbox[6];
     return 0;
@@ -638,6 +646,24 @@ extern "C" int lcx_update_syn(lcx_session* s, double eta, double* tc, double* ad
     return lcx_moments_syn(s, tc, additivity);
 }
 
+// rows [row0, row0 + rows) of  diag(sd) fill_diagonal(left^T right / scale, 1) diag(sd)   (:447-451, :453-454); left / right are
+// factor-major m x ld device arrays.  Free-standing: needs no bound problem.
+static int covariance_rows(lcx_session* s, const double* left, const double* right, long long ld, int m, int n, double scale,
+                           const double* sd, int row0, int rows, double* out, long long ldc) {
+    GemmPlan pl = plan_gemm(rows, n, m, kSMs, 1, false);
+    GemmArgs a;
+    memset(&a, 0, sizeof(a));
+    a.A = left + row0; a.B = right; a.C = out;
+    a.M = rows; a.N = n; a.K = m;
+    a.lda = ld; a.ldb = ld; a.ldc = ldc;
+    LCX_TRY(launch_gemm(kLayoutMN, pl, a, s->stream));
+    LAUNCHED(s);
+    cov_finish_kernel<<<dim3(cdiv(n, 256), rows), 256, 0, s->stream>>>(out, ldc, row0, rows, n, scale, sd);
+    LAUNCHED(s);
+    LCX_CUDA(cudaGetLastError());
+    return 0;
+}
+
 extern "C" int lcx_get_covariance(lcx_session* s, int synergy, double eps, const double* sd, int row0, int rows, double* out,
                                   long long ldc) {
     S_REQUIRE_BOUND(s);
@@ -646,31 +672,24 @@ extern "C" int lcx_get_covariance(lcx_session* s, int synergy, double eps, const
     LCX_REQUIRE(sd && out, "null argument");
     LCX_REQUIRE(row0 >= 0 && rows > 0 && row0 + rows <= n && row0 % 2 == 0, "bad row block (row0 must be even)");
     LCX_REQUIRE(ldc >= n && ldc % 2 == 0, "ldc must be even and >= n");
-    const double* left;
-    const double* right;
     if (!synergy) {
         double* z = s->ptr(I_T);
         cov_z_kernel<<<grid_mn(m, n), 256, 0, s->stream>>>(s->ptr(LCX_A_RHOINVRHO), s->ptr(LCX_A_SI), z, m, n, L.ld);
         LAUNCHED(s);
-        left = z;
-        right = z;
-    } else {
-        left = s->ptr(LCX_A_XZ);
-        right = s->ptr(LCX_A_XY);
+        return covariance_rows(s, z, z, L.ld, m, n, 1.0 - eps * eps, sd, row0, rows, out, ldc);
     }
-    GemmPlan pl = plan_gemm(rows, n, m, kSMs, 1, false);
-    GemmArgs a;
-    memset(&a, 0, sizeof(a));
-    a.A = left + row0; a.B = right; a.C = out;
-    a.M = rows; a.N = n; a.K = m;
-    a.lda = L.ld; a.ldb = L.ld; a.ldc = ldc;
-    LCX_TRY(launch_gemm(kLayoutMN, pl, a, s->stream));
-    LAUNCHED(s);
-    cov_finish_kernel<<<dim3(cdiv(n, 256), rows), 256, 0, s->stream>>>(out, ldc, row0, rows, n,
-                                                                     synergy ? 1.0 : (1.0 - eps * eps), sd);
-    LAUNCHED(s);
-    LCX_CUDA(cudaGetLastError());
-    return 0;
+    return covariance_rows(s, s->ptr(LCX_A_XZ), s->ptr(LCX_A_XY), L.ld, m, n, 1.0, sd, row0, rows, out, ldc);
+}
+
+extern "C" int lcx_covariance_rows(lcx_session* s, const double* left, const double* right, long long ld, int n_factors,
+                                   int n_vars, double scale, const double* sd, int row0, int rows, double* out, long long ldc) {
+    LCX_REQUIRE(s && left && right && sd && out, "null argument");
+    LCX_REQUIRE(n_factors > 0 && n_vars > 0 && ld >= n_vars && ld % 2 == 0, "bad shape (ld must be even and >= n_vars)");
+    LCX_REQUIRE(row0 >= 0 && rows > 0 && row0 + rows <= n_vars && row0 % 2 == 0, "bad row block (row0 must be even)");
+    LCX_REQUIRE(ldc >= n_vars && ldc % 2 == 0, "ldc must be even and >= n_vars");
+    LCX_REQUIRE(((uintptr_t)left % 16 == 0) && ((uintptr_t)right % 16 == 0) && ((uintptr_t)out % 16 == 0), "misaligned device pointer");
+    LCX_CUDA(cudaSetDevice(s->device));
+    return covariance_rows(s, left, right, ld, n_factors, n_vars, scale, sd, row0, rows, out, ldc);
 }
 
 extern "C" int lcx_gemm_f64(lcx_session* s, int layout, int M, int N, int K, const double* a, long long lda, const double* b,
@@ -695,8 +714,19 @@ extern "C" int lcx_gemm_f64(lcx_session* s, int layout, int M, int N, int K, con
     return run_gemm(s, (GemmLayout)layout, pl, g, scratch, out_count);
 }
 
-extern "C" int lcx_inverse(lcx_session* s, const double* a, long long lda, int m, double* out, long long ldo, double* aug) {
-    LCX_REQUIRE(s && a && out && aug && m > 0, "bad argument");
+extern "C" long long lcx_solve_scratch_doubles(int m) { return m > 0 ? lu::scratch_doubles(m) : -1; }
+
+extern "C" int lcx_solve(lcx_session* s, const double* a, long long lda, int m, const double* b, long long ldb, double* x,
+                         long long ldx, int n_rhs, double* scratch, long long scratch_doubles) {
+    LCX_REQUIRE(s && a && b && x && scratch && m > 0 && n_rhs > 0, "bad argument");
+    LCX_REQUIRE(lda >= m && ldb >= n_rhs && ldx >= n_rhs, "bad leading dimension");
+    LCX_REQUIRE(scratch_doubles >= lu::scratch_doubles(m), "scratch too small (see lcx_solve_scratch_doubles)");
     LCX_CUDA(cudaSetDevice(s->device));
-    return run_inverse(s, a, lda, m, out, ldo, aug, (int*)(aug + 2LL * m * m));
+    lu::Scratch sc = lu::carve(scratch, m);
+    LCX_TRY(lu::solve(a, lda, m, b, ldb, x, ldx, n_rhs, scratch, nullptr, s->stream, &s->launches));
+    int status = 0;
+    LCX_CUDA(cudaMemcpyAsync(&status, sc.status, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+    LCX_CUDA(cudaStreamSynchronize(s->stream));
+    if (status != 0) return fail(LCX_ERR_SINGULAR, "lcx_solve", "Singular matrix");
+    return 0;
 }

@@ -342,17 +342,17 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 if (c0 + 16 < bn) fetch_cadd(c0 + 16);
             }
             if (num_kb > 0) {
-                uint32_t r[16];
-                tmem_ld16(lane_addr + (uint32_t)((S - 1) * bn + c0), r);
+                // all S group loads of this chunk in flight before the one wait (a wait per load serialised S TMEM round trips)
+                uint32_t r[S][16];
+#pragma unroll
+                for (int g = 0; g < S; ++g) tmem_ld16(lane_addr + (uint32_t)(g * bn + c0), r[g]);
                 tmem_ld_wait();
 #pragma unroll
-                for (int j = 0; j < 16; ++j) acc[j] = (double)(int)r[j];
+                for (int j = 0; j < 16; ++j) acc[j] = (double)(int)r[S - 1][j];
 #pragma unroll
                 for (int g = S - 2; g >= 0; --g) {
-                    tmem_ld16(lane_addr + (uint32_t)(g * bn + c0), r);
-                    tmem_ld_wait();
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) acc[j] = acc[j] * p.inv_radix + (double)(int)r[j];  // 1/R per group
+                    for (int j = 0; j < 16; ++j) acc[j] = acc[j] * p.inv_radix + (double)(int)r[g][j];  // 1/R per group
                 }
             } else {
 #pragma unroll
@@ -693,12 +693,9 @@ template <int S, bool KMAJOR, int CL, bool CADD = false>
 inline int launch_oz_gemm_cl(const CUtensorMap& mapA, const CUtensorMap& mapB, const CUtensorMap& mapBt, GemmParams p, dim3 grid,
                              cudaStream_t st) {
     constexpr int SMEM = stages_for(S) * S * (kBM * kBK + bn_max(S) * kBK) + 1024;
-    static bool configured = false;
+    static PerDeviceOnce configured = {};
     auto kern = oz_gemm_kernel<S, KMAJOR, CL, CADD>;
-    if (!configured) {
-        LCX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-        configured = true;
-    }
+    if (configured.first_time()) LCX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     // grid.x = N tiles of THIS launch (starting at p.n_tile0); p.n_tiles = all N tiles of the product
     grid.x = (unsigned)round_up(grid.x, CL);  // padded tiles load zeros (TMA OOB fill) and store nothing
     cudaLaunchConfig_t cfg;

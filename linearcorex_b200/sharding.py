@@ -37,6 +37,17 @@ class Reducer(object):
             dist.all_reduce(tensor, op=dist.ReduceOp.SUM, group=self.group)
         return tensor
 
+    def max_scalar(self, value):
+        """Maximum of a host scalar over the ranks (used to make per-rank decisions collective)."""
+        if self.world == 1:
+            return value
+        import torch
+        import torch.distributed as dist
+        dev = torch.device("cuda", torch.cuda.current_device()) if self.backend == "nccl" else torch.device("cpu")
+        t = torch.tensor([float(value)], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+        return t.item()
+
     def sum_scalar(self, value):
         if self.world == 1:
             return value

@@ -70,21 +70,45 @@ def test_dgemm_matches_numpy(dev, layout, M, N, K, variant):
     assert torch.isnan(cd[:, out_shape[1]:]).all()  # padding untouched
 
 
-@pytest.mark.parametrize("m", [1, 2, 5, 30, 100, 257])
-def test_inverse_matches_numpy(dev, m):
+@pytest.mark.parametrize("m,n", [(1, 7), (2, 33), (5, 64), (30, 100), (100, 257), (160, 40), (161, 300), (257, 1000),
+                                 (500, 96), (840, 70)])
+def test_solve_matches_numpy(dev, m, n):
+    """lcx_solve = np.linalg.solve (linearcorex.py:280, :366): LU with partial pivoting + triangular sweeps.  Covers the
+    single-CTA shared-memory factorisation (m <= 160), the cooperative one, and the in-place-in-output sweep (m > 832)."""
     sess, L, torch = dev
     rng = np.random.RandomState(m)
     Wm = rng.randn(m, 3 * m + 5)
     A = Wm @ Wm.T / (3 * m + 5) + 0.05 * rng.randn(m, m) / max(1, m)  # well conditioned, not symmetric
     np.fill_diagonal(A, 1.0)
-    ad = _dev_mat(torch, A)
-    od = torch.zeros((m, m + (m % 2) + 2), dtype=torch.float64, device="cuda")
-    aug = torch.empty(2 * m * m + 16, dtype=torch.float64, device="cuda")
-    L.check(sess.lib.lcx_inverse(sess.h, ad.data_ptr(), ad.stride(0), m, od.data_ptr(), od.stride(0), aug.data_ptr()))
-    torch.cuda.synchronize()
-    got = od[:, :m].cpu().numpy()
-    want = np.linalg.inv(A)
-    np.testing.assert_allclose(got, want, rtol=1e-9, atol=1e-11 * np.abs(want).max())
+    A[[0, m - 1]] = A[[m - 1, 0]]  # force row exchanges
+    B = rng.randn(m, n)
+    ad, bd = _dev_mat(torch, A), _dev_mat(torch, B)
+    xd = torch.full((m, n + (n % 2) + 2), float("nan"), dtype=torch.float64, device="cuda")
+    nscr = sess.lib.lcx_solve_scratch_doubles(m)
+    scr = torch.empty(nscr, dtype=torch.float64, device="cuda")
+    L.check(sess.lib.lcx_solve(sess.h, ad.data_ptr(), ad.stride(0), m, bd.data_ptr(), bd.stride(0), xd.data_ptr(),
+                               xd.stride(0), n, scr.data_ptr(), nscr))
+    got = xd[:, :n].cpu().numpy()
+    want = np.linalg.solve(A, B)
+    np.testing.assert_allclose(got, want, rtol=1e-10, atol=1e-12 * np.abs(want).max())
+    assert torch.isnan(xd[:, n:]).all()  # padding untouched
+    if m <= 832:  # in place
+        L.check(sess.lib.lcx_solve(sess.h, ad.data_ptr(), ad.stride(0), m, bd.data_ptr(), bd.stride(0), bd.data_ptr(),
+                                   bd.stride(0), n, scr.data_ptr(), nscr))
+        np.testing.assert_allclose(bd[:, :n].cpu().numpy(), want, rtol=1e-10, atol=1e-12 * np.abs(want).max())
+
+
+def test_solve_singular_raises(dev):
+    sess, L, torch = dev
+    A = np.ones((6, 6))
+    B = np.ones((6, 3))
+    ad, bd = _dev_mat(torch, A), _dev_mat(torch, B)
+    xd = torch.zeros((6, 4), dtype=torch.float64, device="cuda")
+    nscr = sess.lib.lcx_solve_scratch_doubles(6)
+    scr = torch.empty(nscr, dtype=torch.float64, device="cuda")
+    with pytest.raises(np.linalg.LinAlgError):
+        L.check(sess.lib.lcx_solve(sess.h, ad.data_ptr(), ad.stride(0), 6, bd.data_ptr(), bd.stride(0), xd.data_ptr(),
+                                   xd.stride(0), 3, scr.data_ptr(), nscr))
 
 
 @pytest.mark.parametrize("N,n,m", [(400, 300, 10), (1000, 50, 5), (77, 513, 30), (2000, 5, 1), (130, 1000, 100)])

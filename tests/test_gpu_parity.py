@@ -76,15 +76,15 @@ def test_single_calls_ns(name):
         L.check(lib.lcx_details_ns(sess.h, C.byref(a), C.byref(b)))
         wantf = golden_moments(z, tag + "f_")
         assert_close(a.value, wantf["TC_no_overlap"], RTOL, "TC_no_overlap")
-        assert_close(b.value, wantf["additivity"], 1e-8, "additivity", floor=abs(float(wantf["TC"])))
+        assert_close(b.value, wantf["additivity"], RTOL, "additivity", floor=abs(float(wantf["TC"])))
         assert_close(sess.host(L.A_MI), wantf["MI"], RTOL, "MI")
         assert_close(sess.host(L.A_XY).T, wantf["X_i Y_j"], RTOL, "X_i Y_j")
-        assert_close(sess.host(L.A_XZ).T, wantf["X_i Z_j"], 1e-8, "X_i Z_j")
-        assert_close(sess.host(L.A_X2Y, squeeze=True), wantf["X_i^2 | Y"], 1e-8, "X_i^2 | Y")
-        assert_close(sess.host(L.A_IXY, squeeze=True), wantf["I(X_i ; Y)"], 1e-8, "I(X_i ; Y)")
+        assert_close(sess.host(L.A_XZ).T, wantf["X_i Z_j"], RTOL, "X_i Z_j")
+        assert_close(sess.host(L.A_X2Y, squeeze=True), wantf["X_i^2 | Y"], RTOL, "X_i^2 | Y")
+        assert_close(sess.host(L.A_IXY, squeeze=True), wantf["I(X_i ; Y)"], RTOL, "I(X_i ; Y)")
         assert_close(sess.host(L.A_IYX, squeeze=True), wantf["I(Y_j ; X)"], RTOL, "I(Y_j ; X)")
         assert_close(sess.host(L.A_TCS, squeeze=True), wantf["TCs"], RTOL, "TCs")
-        assert_close(sess.host(L.A_TCDIRECT, squeeze=True), wantf["TC_direct"], 1e-8, "TC_direct")
+        assert_close(sess.host(L.A_TCDIRECT, squeeze=True), wantf["TC_direct"], RTOL, "TC_direct")
         assert_close(sess.host(L.A_YJ2, squeeze=True), wantf["Y_j^2"], RTOL, "Y_j^2")
         # _sig (:196-213)
         u = z[tag + "sig_u"]
@@ -127,13 +127,13 @@ def test_single_calls_syn():
     L.check(sess.lib.lcx_moments_syn(sess.h, C.byref(tc), C.byref(add)))
     want = golden_moments(z, "e00_f_")
     assert_close(tc.value, want["TC"], RTOL, "TC")
-    assert_close(add.value, want["additivity"], 1e-8, "additivity")
+    assert_close(add.value, want["additivity"], RTOL, "additivity", floor=abs(float(want["TC"])))
     for key, aid, tr in (("rho", "A_RHO", 0), ("ry", "A_RY", 0), ("cy", "A_CY", 0), ("Qij", "A_QIJ", 0), ("MI", "A_MI", 0),
                          ("X_i Y_j", "A_XY", 1), ("X_i Z_j", "A_XZ", 1), ("invrho", "A_INVRHO", 0)):
         got = sess.host(getattr(L, aid))
-        assert_close(got.T if tr else got, want[key], 1e-8 if key == "X_i Z_j" else RTOL, key)
+        assert_close(got.T if tr else got, want[key], RTOL, key)
     for key, aid in (("Qi", "A_QISI2"), ("Si", "A_SI"), ("X_i^2 | Y", "A_X2Y"), ("TCs", "A_TCS"), ("Y_j^2", "A_YJ2")):
-        assert_close(sess.host(getattr(L, aid), squeeze=True), want[key], 1e-8, key)
+        assert_close(sess.host(getattr(L, aid), squeeze=True), want[key], RTOL, key)
     L.check(sess.lib.lcx_update_syn(sess.h, 0.1, C.byref(tc), C.byref(add)))
     assert_close(sess.host(L.A_W), z["e00_w_next"], RTOL, "w_next")
     assert_close(tc.value, z["e00_n_TC"], RTOL, "TC next")
@@ -160,10 +160,9 @@ def _check_fit(z, mdl, x, tol, check_counts=True):
     assert_close(mdl.ws, z["ws"], tol, "ws")
     gm = golden_moments(z)
     assert set(gm) == set(mdl.moments), set(gm) ^ set(mdl.moments)
-    loose = {"X_i Z_j", "X_i^2 | Y", "I(X_i ; Y)", "TC_direct", "additivity", "Qi"}
     tc_scale = abs(float(z["m_TC"]))
     for key, val in gm.items():
-        assert_close(mdl.moments[key], val, 1e-7 if key in loose else tol, key,
+        assert_close(mdl.moments[key], val, tol, key,
                      floor=tc_scale if key in ("additivity", "TC_direct", "TC_no_overlap") else 0.0)
     assert_close(mdl.tcs, z["m_TCs"], tol, "TCs")
     assert_close(mdl.theta[0], z["theta_mean"], 1e-12, "theta mean", floor=float(np.abs(z["theta_std"]).max()))
@@ -172,7 +171,7 @@ def _check_fit(z, mdl, x, tol, check_counts=True):
     if "covariance" in z:
         assert_close(mdl.get_covariance(), z["covariance"], tol, "covariance")
     if "predict7" in z:
-        assert_close(mdl.predict(z["transform"][:7]), z["predict7"], 1e-7, "predict")
+        assert_close(mdl.predict(z["transform"][:7]), z["predict7"], tol, "predict")
     assert_close(mdl.mis, z["mis"], tol, "mis")
 
 
@@ -199,7 +198,7 @@ def test_full_fit_linear_trials(name):
 @pytest.mark.parametrize("precision", ["fp64", "fp64_split"])
 def test_full_fit_synergy(name, precision):
     z, mdl, x = _fit(name, precision=precision)
-    _check_fit(z, mdl, x, 1e-8)
+    _check_fit(z, mdl, x, RTOL)
 
 
 def test_toy_duplicate_columns_known_answer():
@@ -301,12 +300,13 @@ def test_synthetic_4000x2000x20_fp64_split():
 
 
 def test_adni_layer0_missing_values():
-    """566 x 200, 3.1 % missing, 30 factors, ~2400 iterations: long trajectories amplify rounding, so this one
-    is held to the iteration count, TC at 1e-9 and cluster labels."""
+    """566 x 200, 3.1 % missing, 30 factors, 2414 iterations in the DMMA mode: same bar as the split mode above."""
     z, mdl, x = _fit("adni_l0_f64", precision="fp64")
-    assert abs(len(mdl.history["TC"]) - len(z["history_TC"])) <= 2
-    assert_close(mdl.tc, z["m_TC"], 1e-8, "TC")
-    assert np.mean(mdl.clusters() == z["clusters"]) > 0.99
+    assert len(mdl.history["TC"]) == len(z["history_TC"])
+    assert_close(mdl.ws, z["ws"], RTOL, "ws")
+    assert_close(mdl.tc, z["m_TC"], RTOL, "TC")
+    assert_close(mdl.tcs, z["m_TCs"], RTOL, "TCs")
+    np.testing.assert_array_equal(mdl.clusters(), z["clusters"])
 
 
 def test_synthetic_4000x2000x20():
@@ -326,13 +326,13 @@ def test_layer_stacking_matches_reference_chain():
     assert [m.m for m in models] == [5, 1]
     assert_close(models[0].tc, z0["m_TC"], RTOL, "layer 0 TC")
     assert_close(models[0].ws, z0["ws"], RTOL, "layer 0 ws")
-    assert_close(models[1].tc, z1["m_TC"], 1e-8, "layer 1 TC")
-    assert_close(models[1].ws, z1["ws"], 1e-8, "layer 1 ws")
+    assert_close(models[1].tc, z1["m_TC"], RTOL, "layer 1 TC")
+    assert_close(models[1].ws, z1["ws"], RTOL, "layer 1 ws")
     za, kwa, xa = load_golden("adni_l1_f64")   # its X is the stored transform of adni layer 0
     zb, _, _ = load_golden("adni_l2_f64")
     upper = fit_layers(xa, [5, 1], seed=0)
     assert_close(upper[0].tc, za["m_TC"], RTOL, "adni layer 1 TC")
-    assert_close(upper[1].tc, zb["m_TC"], 1e-7, "adni layer 2 TC")
+    assert_close(upper[1].tc, zb["m_TC"], RTOL, "adni layer 2 TC")
 
 
 def test_refit_and_second_model_release_device_state():
@@ -373,6 +373,9 @@ def test_pickle_and_warm_start():
     clone = pickle.loads(pickle.dumps(mdl))
     assert_close(clone.ws, mdl.ws, 0, "pickled ws")
     assert_close(clone.transform(x), z["transform"], RTOL, "transform after unpickle")
+    # the reference's get_covariance / predict read only host state (:440-455): they must survive pickling
+    assert_close(clone.get_covariance(), z["covariance"], RTOL, "covariance after unpickle")
+    assert_close(clone.predict(z["transform"][:7]), z["predict7"], RTOL, "predict after unpickle")
     warm = Corex(n_hidden=10, seed=0)
     warm.ws = mdl.ws.copy()           # pre-set ws = warm start, anneal schedule collapses to [0.] (:113-119)
     warm.fit(x)
@@ -388,3 +391,43 @@ def test_aliases_and_errors():
     z, mdl, x = _fit("test_data_f64")
     with pytest.raises(AssertionError):
         mdl.transform(np.zeros((3, 4)))
+
+
+@pytest.mark.parametrize("name", ["syn_400x300x10_f64", "syn_400x300x10_synergy_f64"])
+def test_get_covariance_outputs(name):
+    """get_covariance into a caller-provided host array, a CUDA tensor, and through a block callback (n = 50 000 never
+    needs a 20 GB host array), ns and synergy formulas (:447-451 / :453-454)."""
+    import torch
+    z, mdl, x = _fit(name, precision="fp64")
+    n = mdl.nv
+    want = z["covariance"]
+    host = np.full((n, n), np.nan)
+    assert mdl.get_covariance(block_rows=64, out=host) is host
+    assert_close(host, want, RTOL, "out=ndarray")
+    dev = torch.full((n, n + 2), float("nan"), dtype=torch.float64, device="cuda")[:, :n]
+    mdl.get_covariance(block_rows=100, out=dev)
+    assert_close(dev.cpu().numpy(), want, RTOL, "out=CUDA tensor")
+    seen = {}
+    assert mdl.get_covariance(block_rows=128, block_callback=lambda r0, blk: seen.__setitem__(r0, blk.cpu().numpy())) is None
+    assert_close(np.vstack([seen[k] for k in sorted(seen)]), want, RTOL, "block callback")
+
+
+def test_get_covariance_at_scale_row_block():
+    """n = 20 000 variables (3.2 GB covariance): blocks stay on the device; one row block is checked against numpy."""
+    import corex_oracle as oc
+    from linearcorex_b200 import Corex
+    n, m = 20000, 40
+    x = oc.latent_factor_data(600, n, m, seed=3, snr=1.0, snr_spread=0.3)
+    mdl = Corex(n_hidden=m, seed=0, max_iter=4, tol=1e-12, precision="fp64_split").fit(x)
+    got = {}
+    mdl.get_covariance(block_rows=2048, block_callback=lambda r0, blk: got.__setitem__(r0, blk[:3].cpu().numpy()) if r0 in (0, 18432) else None)
+    mo = mdl.moments
+    zf = mo["rhoinvrho"] / (1 + mo["Si"])
+    for r0, blk in got.items():
+        want = zf[:, r0:r0 + 3].T.dot(zf) / (1. - mdl.eps ** 2)
+        for k in range(3):
+            want[k, r0 + k] = 1.0
+        want *= mdl.theta[1][r0:r0 + 3, None] * mdl.theta[1]
+        assert_close(blk, want, 1e-12, "covariance rows at %d" % r0)
+    y = mdl.transform(x[:5])
+    assert_close(mdl.predict(y), mdl.invert(np.dot(mo["X_i Z_j"], y.T).T), 1e-12, "predict on device")
