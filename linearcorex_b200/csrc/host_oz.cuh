@@ -34,27 +34,25 @@ static int oz_prepare(lcx_session* s, bool streamed) {
     // D = X~^T Y (MN-major: inner = variables, 128 B boxes over 64 sample rows); the factor-side operands are K-major:
     // A slices (inner = variables) and the transposed Y slices (inner = samples).
     LCX_TRY(oz::make_slice_map(&s->map_x_k1, s->xs(), s->n, s->Nl, L.S, L.ld8, s->Nl * L.ld8, oz::kBK, oz::kBM, false));
+    // the factors are split into equal tiles: m = 100, bn_max = 64 -> 2 tiles of 56 (not 64 + 48), so the CTAs that share an
+    // X~ tile by multicast carry the same work; widths of 8 mod 16 use the spill form of the wide MMAs (ozaki_i8.cuh)
     const int bnm = oz::bn_max(L.S);
-    LCX_TRY(oz::make_slice_map(&s->map_a_k1, s->as(), s->n, s->m, L.S, L.ld8, (long long)s->m * L.ld8, oz::kBK, bnm, false));
-    s->oz_bn_tail = (int)round_up(s->m - (cdiv(s->m, bnm) - 1) * bnm, 16);
-    LCX_TRY(oz::make_slice_map(&s->map_a_k1_tail, s->as(), s->n, s->m, L.S, L.ld8, (long long)s->m * L.ld8, oz::kBK, s->oz_bn_tail,
-                               false));
+    const int n_tiles = cdiv(s->m, bnm);
+    s->oz_bn = (int)max(16LL, round_up(cdiv(s->m, n_tiles), bnm > 64 ? 16 : 8));
+    const int bn = s->oz_bn;
+    LCX_TRY(oz::make_slice_map(&s->map_a_k1, s->as(), s->n, s->m, L.S, L.ld8, (long long)s->m * L.ld8, oz::kBK, bn, false));
     LCX_TRY(oz::make_slice_map(&s->map_x_k2, s->xs(), s->n, s->Nl, L.S, L.ld8, s->Nl * L.ld8, oz::kBM, oz::kBK, true));
-    LCX_TRY(oz::make_slice_map(&s->map_y_k2, s->ys(), s->Nl, s->m, L.S, L.ldk8, (long long)s->m * L.ldk8, oz::kBK, bnm, false));
-    LCX_TRY(oz::make_slice_map(&s->map_y_k2_tail, s->ys(), s->Nl, s->m, L.S, L.ldk8, (long long)s->m * L.ldk8, oz::kBK,
-                               s->oz_bn_tail, false));
+    LCX_TRY(oz::make_slice_map(&s->map_y_k2, s->ys(), s->Nl, s->m, L.S, L.ldk8, (long long)s->m * L.ldk8, oz::kBK, bn, false));
     if (L.mm_i8) {
         LCX_REQUIRE(L.mm_chunk <= L.oz_kmax && round_up(s->m, oz::kBK) <= L.oz_kmax, "contraction chunk exceeds the int32-exact length");
         const long long st_n = (long long)s->m * L.ld8, st_q = (long long)s->m * L.ldm8;
         // ry = W rho^T, H = T rinv^T: both operands K-major over the variables (M side 128-row boxes, N side bn-row boxes)
         LCX_TRY(oz::make_slice_map(&s->map_mm_a, s->mma(), s->n, s->m, L.S, L.ld8, st_n, oz::kBK, oz::kBM, false));
-        LCX_TRY(oz::make_slice_map(&s->map_mm_b, s->mmb(), s->n, s->m, L.S, L.ld8, st_n, oz::kBK, bnm, false));
-        LCX_TRY(oz::make_slice_map(&s->map_mm_b_tail, s->mmb(), s->n, s->m, L.S, L.ld8, st_n, oz::kBK, s->oz_bn_tail, false));
+        LCX_TRY(oz::make_slice_map(&s->map_mm_b, s->mmb(), s->n, s->m, L.S, L.ld8, st_n, oz::kBK, bn, false));
         // Qij = ry rinv, grad += H W: M side = variables of the m x n operand (MN-major, contraction over its m rows),
         // N side = the m x m factor, K-major
         LCX_TRY(oz::make_slice_map(&s->map_mn_c, s->mmc(), s->n, s->m, L.S, L.ld8, st_n, oz::kBM, oz::kBK, true));
-        LCX_TRY(oz::make_slice_map(&s->map_mn_q, s->mmq(), s->m, s->m, L.S, L.ldm8, st_q, oz::kBK, bnm, false));
-        LCX_TRY(oz::make_slice_map(&s->map_mn_q_tail, s->mmq(), s->m, s->m, L.S, L.ldm8, st_q, oz::kBK, s->oz_bn_tail, false));
+        LCX_TRY(oz::make_slice_map(&s->map_mn_q, s->mmq(), s->m, s->m, L.S, L.ldm8, st_q, oz::kBK, bn, false));
     }
     return 0;
 }
@@ -87,8 +85,8 @@ static int oz_pair_t(lcx_session* s, const double* A, double* svec, cudaEvent_t*
         p.col_scale = s->oz_cscale();
         p.inv_radix = 1.0 / (double)L.radix;
         p.rows = (int)s->Nl; p.cols = m; p.k_total = n; p.k_chunk = L.oz1_chunk;
-        p.bn_tail = s->oz_bn_tail;
-        LCX_TRY((oz::launch_oz_gemm<S, true>(s->map_x_k1, s->map_a_k1, s->map_a_k1_tail, p,
+        p.bn = s->oz_bn;
+        LCX_TRY((oz::launch_oz_gemm<S, true>(s->map_x_k1, s->map_a_k1, p,
                                              dim3(cdiv(m, oz::bn_max(S)), cdiv(s->Nl, oz::kBM), L.oz1_splits), s->stream, oz_cluster())));
         LAUNCHED(s);
         if (split1) {
@@ -122,9 +120,9 @@ static int oz_pair_t(lcx_session* s, const double* A, double* svec, cudaEvent_t*
         p.col_scale = s->oz_dscale();
         p.inv_radix = 1.0 / (double)L.radix;
         p.rows = n; p.cols = m; p.k_total = (int)s->Nl; p.k_chunk = L.oz_chunk;
-        p.bn_tail = s->oz_bn_tail;
+        p.bn = s->oz_bn;
         p.trans_out = 1;
-        LCX_TRY((oz::launch_oz_gemm<S, false>(s->map_x_k2, s->map_y_k2, s->map_y_k2_tail, p,
+        LCX_TRY((oz::launch_oz_gemm<S, false>(s->map_x_k2, s->map_y_k2, p,
                                               dim3(cdiv(m, oz::bn_max(S)), cdiv(n, oz::kBM), L.oz_splits), s->stream, oz_cluster())));
         LAUNCHED(s);
         if (ev) LCX_CUDA(cudaEventRecord(ev[4], s->stream));
@@ -175,8 +173,8 @@ static int oz_square_t(lcx_session* s, const double* left, const double* right, 
     p.col_scale = s->mm_scale_b();
     p.inv_radix = 1.0 / (double)L.radix;
     p.rows = m; p.cols = m; p.k_total = n; p.k_chunk = L.mm_chunk;
-    p.bn_tail = s->oz_bn_tail;
-    LCX_TRY((oz::launch_oz_gemm<S, true>(s->map_mm_a, s->map_mm_b, s->map_mm_b_tail, p,
+    p.bn = s->oz_bn;
+    LCX_TRY((oz::launch_oz_gemm<S, true>(s->map_mm_a, s->map_mm_b, p,
                                          dim3(cdiv(m, oz::bn_max(S)), cdiv(m, oz::kBM), L.mm_splits), s->stream, oz_cluster())));
     LAUNCHED(s);
     LCX_TRY(launch_reduce_splits(s->ptr(I_PART), L.mm_splits, out_count, out, m, m, L.ldm, s->stream,
@@ -220,10 +218,10 @@ static int oz_mn_t(lcx_session* s, const double* Q, const double* V, double* out
     p.col_scale = s->mm_scale_q();
     p.inv_radix = 1.0 / (double)L.radix;
     p.rows = n; p.cols = m; p.k_total = m; p.k_chunk = (int)round_up(m, oz::kBK);
-    p.bn_tail = s->oz_bn_tail;
+    p.bn = s->oz_bn;
     p.trans_out = 1;
     p.c_add = c_add;
-    LCX_TRY((oz::launch_oz_gemm<S, false, true>(s->map_mn_c, s->map_mn_q, s->map_mn_q_tail, p,
+    LCX_TRY((oz::launch_oz_gemm<S, false, true>(s->map_mn_c, s->map_mn_q, p,
                                           dim3(cdiv(m, oz::bn_max(S)), cdiv(n, oz::kBM), 1), s->stream, oz_cluster())));
     LAUNCHED(s);
     LCX_CUDA(cudaGetLastError());

@@ -120,6 +120,15 @@ constexpr int kAmaxCtas = 592;
 
 static long long align16(long long v) { return round_up(v, 16); }
 
+// Cost of one work unit of the persistent split-integer contraction beyond its K blocks, in units of one 64-deep K block
+// (drain of the accumulators that the next unit's operand fill does not hide + the ring restart).  With one cluster per
+// unit (LCX_OZ_PERSISTENT=0) barrier set-up, TMEM allocation, the cluster handshake and the CTA launch add up to ~16.
+static double oz_unit_fixed_kb() {
+    if (const char* env = getenv("LCX_OZ_FIXED_KB")) return atof(env);
+    const char* per = getenv("LCX_OZ_PERSISTENT");
+    return (per && atoi(per) == 0) ? 16.0 : 4.0;
+}
+
 static Layout make_layout(long long Nl, int n, int m, int precision) {
     Layout L;
     memset(&L, 0, sizeof(L));
@@ -213,7 +222,7 @@ static Layout make_layout(long long Nl, int n, int m, int precision) {
             const long long ctas = tiles * sp;
             const long long waves = (ctas + kSMs - 1) / kSMs;
             const double kb = ceil((double)kblocks / sp);
-            const double cost = (double)waves * (kb + 16.0) + (sp > 1 ? 1.5 * sp : 0.0);
+            const double cost = (double)waves * (kb + oz_unit_fixed_kb()) + (sp > 1 ? 1.5 * sp : 0.0);
             if (cost < best_cost - 1e-9) { best_cost = cost; best = sp; }
         }
         if (const char* env = getenv("LCX_OZ_SPLITS")) {  // experiment override; never below the int32-exact minimum
@@ -230,7 +239,7 @@ static Layout make_layout(long long Nl, int n, int m, int precision) {
             const int s1min = cdiv(n, L.oz_kmax);  // int32 exactness of every accumulator group
             for (int sp = s1min; sp <= max(s1min, min(8, kblocks1 / 16)); ++sp) {
                 const long long waves = (tiles1 * sp + kSMs - 1) / kSMs;
-                const double cost = (double)waves * (ceil((double)kblocks1 / sp) + 16.0) + (sp > 1 ? 4.0 * sp : 0.0);
+                const double cost = (double)waves * (ceil((double)kblocks1 / sp) + oz_unit_fixed_kb()) + (sp > 1 ? 4.0 * sp : 0.0);
                 if (cost < c1best - 1e-9) { c1best = cost; b1 = sp; }
             }
             L.oz1_chunk = (int)round_up(cdiv(n, b1), oz::kBK);
@@ -258,7 +267,7 @@ static Layout make_layout(long long Nl, int n, int m, int precision) {
                 double cbest = 1e300;
                 for (int sp = smin_mm; sp <= max(smin_mm, min(64, kblocks_mm / 8)); ++sp) {
                     const long long waves = (tiles_mm * sp + kSMs - 1) / kSMs;
-                    const double cost = (double)waves * (ceil((double)kblocks_mm / sp) + 16.0) + 1.5 * sp;
+                    const double cost = (double)waves * (ceil((double)kblocks_mm / sp) + oz_unit_fixed_kb()) + 1.5 * sp;
                     if (cost < cbest - 1e-9) { cbest = cost; bmm = sp; }
                 }
                 L.mm_chunk = (int)round_up(cdiv(n, bmm), oz::kBK);
@@ -307,10 +316,10 @@ struct lcx_session {
     far::Peers peers;
     unsigned long long ar_calls;
     // split-integer modes: TMA descriptors over the digit slices
-    CUtensorMap map_x_k1, map_a_k1, map_a_k1_tail, map_x_k2, map_y_k2, map_y_k2_tail;
-    int oz_bn_tail;   // width of the last factor tile of the first contraction (multiple of 16)
+    CUtensorMap map_x_k1, map_a_k1, map_x_k2, map_y_k2;
+    int oz_bn;        // width of every factor tile (equal split of the m factors; multiple of 8, >= 16)
     // m x m x n products on the int8 engine (L.mm_i8)
-    CUtensorMap map_mm_a, map_mm_b, map_mm_b_tail, map_mn_c, map_mn_q, map_mn_q_tail;
+    CUtensorMap map_mm_a, map_mm_b, map_mn_c, map_mn_q;
     int8_t* mma() const { return (int8_t*)(ws + L.slot[I_MMA][0].off); }
     int8_t* mmb() const { return (int8_t*)(ws + L.slot[I_MMB][0].off); }
     int8_t* mmc() const { return (int8_t*)(ws + L.slot[I_MMC][0].off); }
@@ -330,6 +339,9 @@ struct lcx_session {
     double* oz_dscale() const { return ws + L.slot[I_OZV][0].off + 16 + 3 * L.ldm; }
 
     double* ptr(int id, int set = 0) const {
+        // with NVLink peers the exchanged block (D and the column sums of squares behind it) IS the output region of this
+        // rank's symmetric buffer: the exchange kernel's last phase stores the sums there directly, no copy-out
+        if (id == LCX_A_D && peers.world > 1) return peers.base[peers.rank] + 2 * peers.count;
         const int phys = (id <= LCX_A_UJ) ? (set ^ cur) : 0;
         return ws + L.slot[id][phys].off;
     }

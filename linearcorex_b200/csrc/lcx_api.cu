@@ -172,6 +172,7 @@ extern "C" int lcx_bind(lcx_session* s, const double* xt, long long n_rows_local
     s->L = L;
     s->cur = 0;
     s->bound = true;
+    s->peers.world = 0;  // a new problem starts single-rank until lcx_set_peer_allreduce is called for it
     // everything except Y starts at zero so padding never carries NaNs into an all-reduce
     const long long y_off = L.slot[LCX_A_Y][0].off;
     LCX_CUDA(cudaMemsetAsync(workspace, 0, (size_t)y_off * sizeof(double), s->stream));
@@ -223,7 +224,7 @@ extern "C" int lcx_array_info(lcx_session* s, int array_id, int set, long long* 
     LCX_REQUIRE(array_id >= 0 && array_id < LCX_A_COUNT && (set == 0 || set == 1), "bad array id / set");
     const int phys = (array_id <= LCX_A_UJ) ? (set ^ s->cur) : 0;
     const Slot& sl = s->L.slot[array_id][phys];
-    if (offset) *offset = sl.off;
+    if (offset) *offset = (array_id == LCX_A_D) ? (long long)(s->ptr(LCX_A_D) - s->ws) : sl.off;  // (peer buffer when sharded)
     if (rows) *rows = (array_id == LCX_A_D) ? s->m : sl.rows;
     if (cols) *cols = sl.cols;
     if (ld) *ld = sl.ld;

@@ -245,14 +245,14 @@ inline int solve(const double* A, long long lda, int m, const double* B, long lo
     if (m <= kSmemMaxM) {
         const size_t smem = (((size_t)m * 4 + 15) & ~(size_t)15) + (size_t)m * (m | 1) * sizeof(double);
         if (attr_f_smem.first_time())
-            LCX_CUDA(cudaFuncSetAttribute(lu_factor_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            LCX_CUDA(cudaFuncSetAttribute(lu_factor_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024));
         lu_factor_kernel<true><<<1, kFactorThreads, smem, st>>>(A, lda, m, nullptr, sc.lup, m, sc.perm, sc.status);
     } else {
         int grid = (m + 15) / 16;
         if (grid > 64) grid = 64;
         const size_t smem = ((size_t)m * 4 + 15) & ~(size_t)15;
         if (attr_f_coop.first_time())
-            LCX_CUDA(cudaFuncSetAttribute(lu_factor_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            LCX_CUDA(cudaFuncSetAttribute(lu_factor_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024));
         const double* a = A;
         double* work = sc.work;
         double* lup = sc.lup;
@@ -268,7 +268,7 @@ inline int solve(const double* A, long long lda, int m, const double* B, long lo
     if (m <= kSolveSmemMaxM) {
         const size_t smem = (size_t)m * kSolveCols * sizeof(double);
         if (attr_s.first_time())
-            LCX_CUDA(cudaFuncSetAttribute(lu_solve_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            LCX_CUDA(cudaFuncSetAttribute(lu_solve_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024));
         lu_solve_kernel<true><<<tiles, kSolveCols * kSolveRows, smem, st>>>(sc.lup, m, sc.perm, m, B, ldb, X, ldx, n, sc.status,
                                                                           status_out);
     } else {

@@ -51,6 +51,9 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     asm volatile(
         "{\n\t"
@@ -156,10 +159,12 @@ struct GemmParams {
     int k_total;                 // contraction length
     int k_chunk;                 // contraction range per blockIdx.z (multiple of kBK)
     double inv_radix;            // 1 / R: group g carries weight R^-(g+2)
-    int n_tiles;                 // number of real N tiles (gridDim.x may be padded up to a multiple of the cluster size)
+    int n_tiles;                 // number of real N tiles of the product
+    int n_groups, m_tiles, k_splits;  // work units of THIS launch: n_groups clusters' worth of N tiles x M tiles x K splits
     int n_tile0;                 // first N tile of this launch (a product may be split into launches of different cluster size)
-    int bn_tail;                 // width (multiple of 16, <= bn_max(S)) of the LAST N tile, loaded through mapBt;
-                                 // 0 or bn_max = full width.  m = 100 factors, S = 6 -> tiles of 64 + 48 instead of 64 + 64
+    int bn;                      // width of EVERY N tile (multiple of 8, 16 <= bn <= bn_max(S)): the factors are split into
+                                 // equal tiles (m = 100, S = 6 -> 56 + 56, not 64 + 48) so the CTAs that share an X~ tile by
+                                 // multicast -- and therefore run in lock-step -- carry the same work
     int trans_out;               // 1: store C[col][row] (the second contraction writes (X~^T Y)^T factor-major)
     const double* c_add;         // optional (with trans_out, no split): C = c_add + product, c_add laid out like C (may be C
                                  // itself: grad = G0 + H W, linearcorex.py:300; Qij = rinv + (ry - I) rinv, :266)
@@ -170,19 +175,33 @@ struct GemmParams {
 // KMAJOR = true : A tile = [128 rows][64 B of K]   (SW64),  tensor map (K, rows, slice),      coordinates (k0, m0, s);
 // KMAJOR = false: A tile = [64 K rows][128 B of M] (SW128), tensor map (M, K rows, slice),    coordinates (m0, k0, s).
 // All MMAs of one 64-deep K block for a tile of compile-time width BN (multiple of 16, <= bn_max(S)).
+// BN % 16 == 8 (equal-width tiles such as 56): N = BN c is a legal UMMA N only for even c, so an odd plane count issues its
+// last plane as one instruction of N = BN + 8.  That plane always lands in the LAST group (g = S - 1): the 8 extra columns
+// fall into unused TMEM above the accumulators, and the 8 extra B rows it reads are whatever follows that plane in the stage.
 template <int S, bool KMAJOR, int BN>
 __device__ __forceinline__ void issue_kblock(uint32_t sa, uint32_t sb, uint32_t tmem_base, bool first_block) {
     constexpr int A_BYTES = kBM * kBK;
     constexpr int B_BYTES = BN * kBK;        // digit planes of B are packed at the tile's own width
-    constexpr int CMAX = 256 / BN;           // digit planes of B per instruction (N <= 256)
+    constexpr bool ODD8 = (BN % 16) != 0;
+    constexpr int CMAX = ODD8 ? ((256 / BN) & ~1) : (256 / BN);  // digit planes of B per instruction (N <= 256)
+    static_assert(BN % 8 == 0 && BN >= 16 && CMAX >= 1, "tile width");
 #pragma unroll
     for (int kk = 0; kk < kBK / 32; ++kk) {
 #pragma unroll
         for (int ka = 0; ka < S; ++ka) {
+            constexpr int kMaxInstr = S;     // upper bound on instructions per (kk, ka); the loop below exits on q0
+            int q0 = 0;
 #pragma unroll
-            for (int q0 = 0; q0 < S - ka; q0 += CMAX) {
-                const int cnt = (S - ka - q0) < CMAX ? (S - ka - q0) : CMAX;
-                const uint32_t idesc = make_idesc_i8(kBM, BN * cnt, KMAJOR ? 0 : 1, 0);
+            for (int it = 0; it < kMaxInstr; ++it) {
+                const int left = S - ka - q0;
+                if (left <= 0) break;
+                int cnt = left < CMAX ? left : CMAX;
+                int n = BN * cnt;
+                if (ODD8) {
+                    if (cnt >= 2) { cnt &= ~1; n = BN * cnt; }
+                    else n = BN + 8;         // the row's last plane: spills 8 columns above group S - 1
+                }
+                const uint32_t idesc = make_idesc_i8(kBM, n, KMAJOR ? 0 : 1, 0);
                 // K-major: rows at 64 B pitch, 8-row swizzle atoms of 512 B (SBO); a K step is +32 B inside the span; the
                 // next B plane starts BN/8 atoms further, i.e. N simply continues.
                 // MN-major A: K rows of 128 B (SW128, atoms of 8 rows = 1 KB); a K step is 32 rows = 4 KB.
@@ -191,28 +210,35 @@ __device__ __forceinline__ void issue_kblock(uint32_t sa, uint32_t sb, uint32_t 
                 const uint64_t db = make_smem_desc(sb + q0 * B_BYTES + kk * 32, 16, 512, 4);
                 const uint32_t acc = (!first_block || kk > 0 || ka > 0) ? 1u : 0u;
                 umma_i8(tmem_base + (uint32_t)((ka + q0) * BN), da, db, idesc, acc);
+                q0 += cnt;
             }
         }
     }
 }
 
-// CL = thread-block cluster size along the N tiles (1, 2 or 4).  The CL CTAs of a cluster share the M-side operand
+// CL = thread-block cluster size along the N tiles (1, 2, 3 or 4).  The CL CTAs of a cluster share the M-side operand
 // (the X~ planes, in both contractions): each CTA fetches S/CL of its digit planes and TMA
 // multicasts them into every CTA of the cluster, which divides the L2 -> SM traffic of that operand by CL (the kernel
 // ran at the L2 throughput cap without it: 18 GB per launch at config 3).  A stage is released to the producers only
 // when every CTA of the cluster has finished reading it (multicast tcgen05.commit on all empty barriers).
 // CADD: the epilogue adds p.c_add (transposed stores only).  Its values are fetched one 16-column chunk ahead -- the first
 // chunk while the MMAs are still running -- so the global-load latency is not paid once per column by a single resident CTA.
+//
+// PERSISTENT: the grid is one cluster per CL SMs and every cluster walks the work units u = cluster, cluster + #clusters, ...
+// of the launch (unit = one M tile x one K split x CL adjacent N tiles).  Barriers, tensor-map prefetch, the TMEM allocation
+// and the cluster handshake are paid once per SM instead of once per tile, and the mbarrier ring simply keeps running across
+// units: while warps 2-5 drain the accumulators of unit i, warp 0 is already filling the stages of unit i + 1 (the K loop
+// is bound by shared-memory traffic -- operand fetch of the MMAs plus the TMA fill -- not by the tensor pipe, so what has
+// to overlap with the drain is the fill).  The MMA warp waits for the drain (tmem_empty) before it touches TMEM again.
 template <int S, bool KMAJOR, int CL, bool CADD = false>
 __global__ void __launch_bounds__(kThreads, 1)
-oz_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
-               const __grid_constant__ CUtensorMap mapBt, const GemmParams p) {
+oz_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const GemmParams p) {
     constexpr int kBN = bn_max(S);
     constexpr int kStages = stages_for(S);
     constexpr int A_BYTES = kBM * kBK;          // 8 KB per slice either way
     constexpr int B_BYTES = kBN * kBK;          // 4 KB (8 KB) per slice (full-width tile)
     constexpr int STAGE_BYTES = S * (A_BYTES + B_BYTES);
-    constexpr uint32_t TMEM_COLS = (S * kBN <= 128) ? 128 : (S * kBN <= 256 ? 256 : 512);
+    constexpr uint32_t TMEM_COLS = (S * kBN + 8 <= 128) ? 128 : (S * kBN + 8 <= 256 ? 256 : 512);  // (+ 8 spill columns)
     static_assert(S * kBN <= 512, "accumulators exceed TMEM");
     static_assert(kStages >= 2, "pipeline needs two stages");
 
@@ -221,30 +247,28 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     __shared__ __align__(8) uint64_t full_bar[kStages];
     __shared__ __align__(8) uint64_t empty_bar[kStages];
     __shared__ __align__(8) uint64_t tmem_full_bar;
+    __shared__ __align__(8) uint64_t tmem_empty_bar;
     __shared__ uint32_t tmem_base_smem;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n_tile = p.n_tile0 + (int)blockIdx.x, m_tile = blockIdx.y;
-    const int kbeg = blockIdx.z * p.k_chunk;
-    const int kend = min(p.k_total, kbeg + p.k_chunk);
-    const int num_kb = (kend > kbeg) ? (kend - kbeg + kBK - 1) / kBK : 0;
-    // width of this CTA's N tile: the last factor tile may be narrower (fewer padded factor columns
-    // = proportionally fewer tensor cycles and operand bytes); digit planes of B are then packed at bn * 64 bytes
-    const bool tail = p.bn_tail > 0 && p.bn_tail < kBN && n_tile == p.n_tiles - 1;
     const uint32_t crank = (CL > 1) ? cluster_ctarank() : 0u;
     constexpr uint16_t kMask = (uint16_t)((1u << CL) - 1u);
-    const int bn = tail ? p.bn_tail : kBN;
+    // every N tile has the same width bn <= kBN (the factors are split evenly); digit planes of B are packed at bn * 64 bytes
+    const int bn = p.bn;
     const int b_bytes = bn * kBK;
+    // work units of this launch: u -> (N group, M tile, K split), N groups fastest
+    const int cluster_id = (int)blockIdx.x / CL, n_clusters = (int)gridDim.x / CL;
+    const int units = p.n_groups * p.m_tiles * p.k_splits;
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB) : "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&mapBt) : "memory");
         for (int i = 0; i < kStages; ++i) {
             mbar_init(&full_bar[i], 1);
             mbar_init(&empty_bar[i], CL);  // one arrival per CTA of the cluster (multicast commit)
         }
         mbar_init(&tmem_full_bar, 1);
+        mbar_init(&tmem_empty_bar, 4);     // one arrival per epilogue warp
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) tmem_alloc(&tmem_base_smem, TMEM_COLS);
@@ -254,28 +278,45 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_smem;
 
+    // decode of unit u for this CTA (its own N tile of the cluster's group)
+    auto unit_of = [&](int u, int& n_tile, int& m_tile, int& z, int& kbeg, int& num_kb) {
+        const int g = u % p.n_groups;
+        const int r = u / p.n_groups;
+        m_tile = r % p.m_tiles;
+        z = r / p.m_tiles;
+        n_tile = p.n_tile0 + g * CL + (int)crank;
+        kbeg = z * p.k_chunk;
+        const int kend = min(p.k_total, kbeg + p.k_chunk);
+        num_kb = (kend > kbeg) ? (kend - kbeg + kBK - 1) / kBK : 0;
+    };
+
     if (warp == 0) {
         // ===== TMA producer =====
         if (lane == 0) {
-            for (int kb = 0; kb < num_kb; ++kb) {
-                const int st = kb % kStages;
-                const uint32_t ph = (kb / kStages) & 1;
-                mbar_wait(&empty_bar[st], ph ^ 1);
-                uint8_t* sa = smem + st * STAGE_BYTES;
-                uint8_t* sb = sa + S * A_BYTES;
-                mbar_expect_tx(&full_bar[st], S * (A_BYTES + b_bytes));
-                const int k0 = kbeg + kb * kBK;
+            uint32_t kbg = 0;  // K blocks issued so far by this CTA: stage and phase of the ring
+            for (int u = cluster_id; u < units; u += n_clusters) {
+                int n_tile, m_tile, z, kbeg, num_kb;
+                unit_of(u, n_tile, m_tile, z, kbeg, num_kb);
+                for (int kb = 0; kb < num_kb; ++kb, ++kbg) {
+                    const uint32_t st = kbg % kStages;
+                    const uint32_t ph = (kbg / kStages) & 1;
+                    mbar_wait(&empty_bar[st], ph ^ 1);
+                    uint8_t* sa = smem + st * STAGE_BYTES;
+                    uint8_t* sb = sa + S * A_BYTES;
+                    mbar_expect_tx(&full_bar[st], S * (A_BYTES + b_bytes));
+                    const int k0 = kbeg + kb * kBK;
 #pragma unroll
-                for (int s = 0; s < S; ++s) {
-                    // shared operand: plane s is fetched by cluster rank s % CL and multicast to all CL CTAs
-                    if (CL == 1) {
-                        if (KMAJOR) tma_load_3d(sa + s * A_BYTES, &mapA, &full_bar[st], k0, m_tile * kBM, s);
-                        else tma_load_3d(sa + s * A_BYTES, &mapA, &full_bar[st], m_tile * kBM, k0, s);
-                    } else if ((uint32_t)(s % CL) == crank) {
-                        if (KMAJOR) tma_load_3d_mc(sa + s * A_BYTES, &mapA, &full_bar[st], k0, m_tile * kBM, s, kMask);
-                        else tma_load_3d_mc(sa + s * A_BYTES, &mapA, &full_bar[st], m_tile * kBM, k0, s, kMask);
+                    for (int s = 0; s < S; ++s) {
+                        // shared operand: plane s is fetched by cluster rank s % CL and multicast to all CL CTAs
+                        if (CL == 1) {
+                            if (KMAJOR) tma_load_3d(sa + s * A_BYTES, &mapA, &full_bar[st], k0, m_tile * kBM, s);
+                            else tma_load_3d(sa + s * A_BYTES, &mapA, &full_bar[st], m_tile * kBM, k0, s);
+                        } else if ((uint32_t)(s % CL) == crank) {
+                            if (KMAJOR) tma_load_3d_mc(sa + s * A_BYTES, &mapA, &full_bar[st], k0, m_tile * kBM, s, kMask);
+                            else tma_load_3d_mc(sa + s * A_BYTES, &mapA, &full_bar[st], m_tile * kBM, k0, s, kMask);
+                        }
+                        tma_load_3d(sb + s * b_bytes, &mapB, &full_bar[st], k0, n_tile * bn, s);
                     }
-                    tma_load_3d(sb + s * b_bytes, tail ? &mapBt : &mapB, &full_bar[st], k0, n_tile * kBN, s);
                 }
             }
         }
@@ -285,101 +326,130 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             // Digit ka of A meets digits 0..S-1-ka of B, landing in groups ka..S-1 = CONSECUTIVE TMEM columns, and
             // the B digit planes are consecutive in shared memory, so those S-ka products are issued as one wide
             // MMA (N = bn (S-ka), at most 256 per instruction): A is re-read from shared memory 8 times per K step
-            // instead of 21 -- an N = 64 instruction occupies the tensor pipe for ~60 cycles while doing 32 cycles of work.
+            // instead of 21 -- an N = 64 instruction occupies the tensor pipe for ~55 cycles while doing 32 cycles of work.
             // The issue sequence is fully unrolled per tile width (one elected thread issues everything).
-            for (int kb = 0; kb < num_kb; ++kb) {
-                const int st = kb % kStages;
-                const uint32_t ph = (kb / kStages) & 1;
-                mbar_wait(&full_bar[st], ph);
-                tc_fence_after();
-                const uint32_t sa = smem_u32(smem + st * STAGE_BYTES);
-                const uint32_t sb = sa + S * A_BYTES;
-                bool wide = false;
-                if constexpr (kBN > 64) {
-                    wide = bn > 64;
-                    if (bn == 128) issue_kblock<S, KMAJOR, 128>(sa, sb, tmem_base, kb == 0);
-                    else if (bn == 112) issue_kblock<S, KMAJOR, 112>(sa, sb, tmem_base, kb == 0);
-                    else if (bn == 96) issue_kblock<S, KMAJOR, 96>(sa, sb, tmem_base, kb == 0);
-                    else if (bn == 80) issue_kblock<S, KMAJOR, 80>(sa, sb, tmem_base, kb == 0);
+            uint32_t kbg = 0, it = 0;  // it = units with a non-empty K range so far (phase of the two TMEM barriers)
+            for (int u = cluster_id; u < units; u += n_clusters) {
+                int n_tile, m_tile, z, kbeg, num_kb;
+                unit_of(u, n_tile, m_tile, z, kbeg, num_kb);
+                if (num_kb == 0) continue;  // (the epilogue stores zeros without consulting TMEM)
+                if (it > 0) {               // the epilogue warps have drained the accumulators of the previous unit
+                    mbar_wait(&tmem_empty_bar, (it - 1) & 1);
+                    tc_fence_after();
                 }
-                if (wide) {
-                } else if (bn == 64) issue_kblock<S, KMAJOR, 64>(sa, sb, tmem_base, kb == 0);
-                else if (bn == 48) issue_kblock<S, KMAJOR, 48>(sa, sb, tmem_base, kb == 0);
-                else if (bn == 32) issue_kblock<S, KMAJOR, 32>(sa, sb, tmem_base, kb == 0);
-                else issue_kblock<S, KMAJOR, 16>(sa, sb, tmem_base, kb == 0);
-                // frees the stage (in every CTA of the cluster) once these MMAs have read it
-                if (CL == 1) umma_commit(&empty_bar[st]);
-                else umma_commit_mc(&empty_bar[st], kMask);
+                ++it;
+                for (int kb = 0; kb < num_kb; ++kb, ++kbg) {
+                    const uint32_t st = kbg % kStages;
+                    const uint32_t ph = (kbg / kStages) & 1;
+                    mbar_wait(&full_bar[st], ph);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + st * STAGE_BYTES);
+                    const uint32_t sb = sa + S * A_BYTES;
+                    bool wide = false;
+                    if constexpr (kBN > 64) {
+                        wide = bn > 64;
+                        if (bn == 128) issue_kblock<S, KMAJOR, 128>(sa, sb, tmem_base, kb == 0);
+                        else if (bn == 112) issue_kblock<S, KMAJOR, 112>(sa, sb, tmem_base, kb == 0);
+                        else if (bn == 96) issue_kblock<S, KMAJOR, 96>(sa, sb, tmem_base, kb == 0);
+                        else if (bn == 80) issue_kblock<S, KMAJOR, 80>(sa, sb, tmem_base, kb == 0);
+                    }
+                    if (wide) {
+                    } else if (bn == 64) issue_kblock<S, KMAJOR, 64>(sa, sb, tmem_base, kb == 0);
+                    else if (bn == 56) issue_kblock<S, KMAJOR, 56>(sa, sb, tmem_base, kb == 0);
+                    else if (bn == 48) issue_kblock<S, KMAJOR, 48>(sa, sb, tmem_base, kb == 0);
+                    else if (bn == 40) issue_kblock<S, KMAJOR, 40>(sa, sb, tmem_base, kb == 0);
+                    else if (bn == 32) issue_kblock<S, KMAJOR, 32>(sa, sb, tmem_base, kb == 0);
+                    else if (bn == 24) issue_kblock<S, KMAJOR, 24>(sa, sb, tmem_base, kb == 0);
+                    else issue_kblock<S, KMAJOR, 16>(sa, sb, tmem_base, kb == 0);
+                    // frees the stage (in every CTA of the cluster) once these MMAs have read it
+                    if (CL == 1) umma_commit(&empty_bar[st]);
+                    else umma_commit_mc(&empty_bar[st], kMask);
+                }
+                umma_commit(&tmem_full_bar);
             }
-            umma_commit(&tmem_full_bar);
         }
     } else {
         // ===== epilogue: TMEM -> registers -> fp64 recombination -> global =====
         const int quarter = warp & 3;              // TMEM lane quarter this warp may read
         const int row_in_tile = quarter * 32 + lane;
-        const int row = m_tile * kBM + row_in_tile;
-        double cadd[16];
-        auto fetch_cadd = [&](int c0) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                const int col = n_tile * kBN + c0 + j;
-                cadd[j] = (row < p.rows && col < p.cols) ? p.c_add[(long long)col * p.ldc + row] : 0.0;
-            }
-        };
-        if (CADD) fetch_cadd(0);
-        mbar_wait(&tmem_full_bar, 0);
-        tc_fence_after();
-        double* C = p.C + (long long)blockIdx.z * p.c_split_stride;
-        const double rs = (p.row_scale != nullptr && row < p.rows) ? p.row_scale[row] : 1.0;
         const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
-#pragma unroll 1
-        for (int c0 = 0; c0 < bn; c0 += 16) {
-            double acc[16];
-            double cur[16];
-            if (CADD) {  // this chunk's addends are in registers; request the next chunk's before touching TMEM
+        uint32_t it = 0;  // units with a non-empty K range so far
+        for (int u = cluster_id; u < units; u += n_clusters) {
+            int n_tile, m_tile, z, kbeg, num_kb;
+            unit_of(u, n_tile, m_tile, z, kbeg, num_kb);
+            const int row = m_tile * kBM + row_in_tile;
+            double cadd[16];
+            auto fetch_cadd = [&](int c0) {
 #pragma unroll
-                for (int j = 0; j < 16; ++j) cur[j] = cadd[j];
-                if (c0 + 16 < bn) fetch_cadd(c0 + 16);
-            }
-            if (num_kb > 0) {
-                // all S group loads of this chunk in flight before the one wait (a wait per load serialised S TMEM round trips)
-                uint32_t r[S][16];
-#pragma unroll
-                for (int g = 0; g < S; ++g) tmem_ld16(lane_addr + (uint32_t)(g * bn + c0), r[g]);
-                tmem_ld_wait();
-#pragma unroll
-                for (int j = 0; j < 16; ++j) acc[j] = (double)(int)r[S - 1][j];
-#pragma unroll
-                for (int g = S - 2; g >= 0; --g) {
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) acc[j] = acc[j] * p.inv_radix + (double)(int)r[g][j];  // 1/R per group
+                for (int j = 0; j < 16; ++j) {
+                    const int col = n_tile * bn + c0 + j;
+                    cadd[j] = (row < p.rows && col < p.cols && c0 + j < bn) ? p.c_add[(long long)col * p.ldc + row] : 0.0;
                 }
-            } else {
-#pragma unroll
-                for (int j = 0; j < 16; ++j) acc[j] = 0.0;
+            };
+            if (CADD) fetch_cadd(0);
+            if (num_kb > 0) {
+                mbar_wait(&tmem_full_bar, it & 1);
+                tc_fence_after();
+                ++it;
             }
-            if (row < p.rows) {
-                const int col0 = n_tile * kBN + c0;
+            double* C = p.C + (long long)z * p.c_split_stride;
+            const double rs = (p.row_scale != nullptr && row < p.rows) ? p.row_scale[row] : 1.0;
+#pragma unroll 1
+            for (int c0 = 0; c0 < bn; c0 += 16) {
+                double acc[16];
+                double cur[16];
+                if (CADD) {  // this chunk's addends are in registers; request the next chunk's before touching TMEM
 #pragma unroll
-                for (int j = 0; j < 16; j += 2) {
-                    const int col = col0 + j;
-                    // group g = 0 carries weight R^-2 (digits k = l = 1)
-                    double v0 = acc[j] * (p.inv_radix * p.inv_radix) * rs, v1 = acc[j + 1] * (p.inv_radix * p.inv_radix) * rs;
-                    if (p.col_scale != nullptr) {
-                        if (col < p.cols) v0 *= p.col_scale[col];
-                        if (col + 1 < p.cols) v1 *= p.col_scale[col + 1];
+                    for (int j = 0; j < 16; ++j) cur[j] = cadd[j];
+                    if (c0 + 16 < bn) fetch_cadd(c0 + 16);
+                }
+                if (num_kb > 0) {
+                    // all S group loads of this chunk in flight before the one wait (a wait per load serialised S TMEM round trips)
+                    uint32_t r[S][16];
+#pragma unroll
+                    for (int g = 0; g < S; ++g) tmem_ld16(lane_addr + (uint32_t)(g * bn + c0), r[g]);
+                    tmem_ld_wait();
+                    if (c0 + 16 >= bn) {  // last chunk read: hand TMEM back to the MMA warp before the arithmetic and the stores
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&tmem_empty_bar);
                     }
-                    if (p.trans_out) {  // a warp's 32 rows are 32 consecutive doubles of one output row: coalesced
-                        if (CADD) {
-                            v0 += cur[j];
-                            v1 += cur[j + 1];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) acc[j] = (double)(int)r[S - 1][j];
+#pragma unroll
+                    for (int g = S - 2; g >= 0; --g) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) acc[j] = acc[j] * p.inv_radix + (double)(int)r[g][j];  // 1/R per group
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) acc[j] = 0.0;
+                }
+                if (row < p.rows) {
+                    const int col0 = n_tile * bn + c0;
+                    // columns of this tile that are real outputs (a width of 8 mod 16 ends in the middle of the last chunk)
+                    const int cend = min(p.cols, n_tile * bn + bn);
+#pragma unroll
+                    for (int j = 0; j < 16; j += 2) {
+                        const int col = col0 + j;
+                        // group g = 0 carries weight R^-2 (digits k = l = 1)
+                        double v0 = acc[j] * (p.inv_radix * p.inv_radix) * rs, v1 = acc[j + 1] * (p.inv_radix * p.inv_radix) * rs;
+                        if (p.col_scale != nullptr) {
+                            if (col < cend) v0 *= p.col_scale[col];
+                            if (col + 1 < cend) v1 *= p.col_scale[col + 1];
                         }
-                        if (col < p.cols) C[(long long)col * p.ldc + row] = v0;
-                        if (col + 1 < p.cols) C[(long long)(col + 1) * p.ldc + row] = v1;
-                    } else if (col + 1 < p.cols) {
-                        *reinterpret_cast<double2*>(C + (long long)row * p.ldc + col) = make_double2(v0, v1);
-                    } else if (col < p.cols) {
-                        C[(long long)row * p.ldc + col] = v0;
+                        if (p.trans_out) {  // a warp's 32 rows are 32 consecutive doubles of one output row: coalesced
+                            if (CADD) {
+                                v0 += cur[j];
+                                v1 += cur[j + 1];
+                            }
+                            if (col < cend) C[(long long)col * p.ldc + row] = v0;
+                            if (col + 1 < cend) C[(long long)(col + 1) * p.ldc + row] = v1;
+                        } else if (col + 1 < cend) {
+                            *reinterpret_cast<double2*>(C + (long long)row * p.ldc + col) = make_double2(v0, v1);
+                        } else if (col < cend) {
+                            C[(long long)row * p.ldc + col] = v0;
+                        }
                     }
                 }
             }
@@ -689,18 +759,31 @@ inline int make_slice_map(CUtensorMap* map, const void* base, long long inner, l
     return 0;
 }
 
+// LCX_OZ_PERSISTENT=0 launches one cluster per work unit (the pre-persistent behaviour) for A/B measurements.
+inline bool oz_persistent() {
+    static int v = -1;
+    if (v < 0) {
+        const char* env = getenv("LCX_OZ_PERSISTENT");
+        v = (env && atoi(env) == 0) ? 0 : 1;
+    }
+    return v != 0;
+}
+
 template <int S, bool KMAJOR, int CL, bool CADD = false>
-inline int launch_oz_gemm_cl(const CUtensorMap& mapA, const CUtensorMap& mapB, const CUtensorMap& mapBt, GemmParams p, dim3 grid,
-                             cudaStream_t st) {
+inline int launch_oz_gemm_cl(const CUtensorMap& mapA, const CUtensorMap& mapB, GemmParams p, dim3 grid, cudaStream_t st) {
     constexpr int SMEM = stages_for(S) * S * (kBM * kBK + bn_max(S) * kBK) + 1024;
     static PerDeviceOnce configured = {};
+    static int resident[64] = {};  // clusters of this kernel that fit on the device at once, per device ordinal
     auto kern = oz_gemm_kernel<S, KMAJOR, CL, CADD>;
     if (configured.first_time()) LCX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-    // grid.x = N tiles of THIS launch (starting at p.n_tile0); p.n_tiles = all N tiles of the product
-    grid.x = (unsigned)round_up(grid.x, CL);  // padded tiles load zeros (TMA OOB fill) and store nothing
+    // grid = (N tiles of THIS launch starting at p.n_tile0, M tiles, K splits); p.n_tiles = all N tiles of the product.
+    // Padded N tiles (to a multiple of the cluster size) load zeros (TMA OOB fill) and store nothing.
+    p.n_groups = (int)round_up(grid.x, CL) / CL;
+    p.m_tiles = (int)grid.y;
+    p.k_splits = (int)grid.z;
+    const long long units = (long long)p.n_groups * p.m_tiles * p.k_splits;
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = grid;
     cfg.blockDim = dim3(kThreads);
     cfg.dynamicSmemBytes = SMEM;
     cfg.stream = st;
@@ -711,7 +794,23 @@ inline int launch_oz_gemm_cl(const CUtensorMap& mapA, const CUtensorMap& mapB, c
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    LCX_CUDA(cudaLaunchKernelEx(&cfg, kern, mapA, mapB, mapBt, p));
+    int dev = 0;
+    LCX_CUDA(cudaGetDevice(&dev));
+    dev &= 63;
+    if (resident[dev] == 0) {
+        int n = 0, sms = 0;
+        cfg.gridDim = dim3(CL * 1024);
+        if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess || n <= 0) {
+            cudaGetLastError();
+            LCX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+            n = sms / CL;
+        }
+        resident[dev] = n > 0 ? n : 1;
+    }
+    const long long clusters = oz_persistent() ? (units < resident[dev] ? units : resident[dev]) : units;
+    LCX_REQUIRE(clusters * CL < (1LL << 31), "grid too large");
+    cfg.gridDim = dim3((unsigned)(clusters * CL));
+    LCX_CUDA(cudaLaunchKernelEx(&cfg, kern, mapA, mapB, p));
     return 0;
 }
 
@@ -719,25 +818,25 @@ inline int launch_oz_gemm_cl(const CUtensorMap& mapA, const CUtensorMap& mapB, c
 // slot would occupy an SM for the whole K loop and take a full copy of the X~ tile for nothing, so an odd tile count
 // under pairs runs as pairs plus one final cluster of three (m = 192: 3 tiles in 5.9 ms instead of 7.0 ms).
 template <int S, bool KMAJOR, bool CADD = false>
-inline int launch_oz_gemm(const CUtensorMap& mapA, const CUtensorMap& mapB, const CUtensorMap& mapBt, GemmParams p,
-                          dim3 grid, cudaStream_t st, int cluster) {
+inline int launch_oz_gemm(const CUtensorMap& mapA, const CUtensorMap& mapB, GemmParams p, dim3 grid, cudaStream_t st,
+                          int cluster) {
     const int n_tiles = (int)grid.x;
     p.n_tiles = n_tiles;
     p.n_tile0 = 0;
     if (CADD) cluster = cluster > 2 ? 2 : cluster;  // (the c_add variant is built for clusters of 1, 2 and 3 only)
-    if (!CADD && cluster >= 4 && n_tiles >= 4) return launch_oz_gemm_cl<S, KMAJOR, 4, false>(mapA, mapB, mapBt, p, grid, st);
+    if (!CADD && cluster >= 4 && n_tiles >= 4) return launch_oz_gemm_cl<S, KMAJOR, 4, false>(mapA, mapB, p, grid, st);
     if (cluster >= 2 && n_tiles >= 2) {
-        if (n_tiles % 2 == 0) return launch_oz_gemm_cl<S, KMAJOR, 2, CADD>(mapA, mapB, mapBt, p, grid, st);
+        if (n_tiles % 2 == 0) return launch_oz_gemm_cl<S, KMAJOR, 2, CADD>(mapA, mapB, p, grid, st);
         if (n_tiles > 3) {
             grid.x = (unsigned)(n_tiles - 3);
-            const int rc = launch_oz_gemm_cl<S, KMAJOR, 2, CADD>(mapA, mapB, mapBt, p, grid, st);
+            const int rc = launch_oz_gemm_cl<S, KMAJOR, 2, CADD>(mapA, mapB, p, grid, st);
             if (rc != 0) return rc;
         }
         p.n_tile0 = n_tiles - 3;
         grid.x = 3;
-        return launch_oz_gemm_cl<S, KMAJOR, 3, CADD>(mapA, mapB, mapBt, p, grid, st);
+        return launch_oz_gemm_cl<S, KMAJOR, 3, CADD>(mapA, mapB, p, grid, st);
     }
-    return launch_oz_gemm_cl<S, KMAJOR, 1, CADD>(mapA, mapB, mapBt, p, grid, st);
+    return launch_oz_gemm_cl<S, KMAJOR, 1, CADD>(mapA, mapB, p, grid, st);
 }
 
 }  // namespace oz

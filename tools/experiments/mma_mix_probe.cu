@@ -21,38 +21,7 @@ using namespace lcx::oz;
 
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); return 2; } } while (0)
 
-// Equal-width tiles of BN = 56 (m = 100 -> 56 + 56 instead of 64 + 48): N = 56 c is a legal UMMA N for even c only, so an
-// odd plane count issues its last plane as an N = 64 instruction.  That plane lands in the LAST group (g = S - 1), so the 8
-// extra columns fall into unused TMEM above the accumulators, and the 8 extra B rows it reads are whatever follows in smem.
-template <int S, bool KMAJOR, int BN>
-__device__ __forceinline__ void issue_kblock_spill(uint32_t sa, uint32_t sb, uint32_t tmem_base, bool first_block) {
-    constexpr int A_BYTES = kBM * kBK;
-    constexpr int B_BYTES = BN * kBK;
-    constexpr int CMAX = (256 / BN) & ~1;    // even plane count per instruction
-#pragma unroll
-    for (int kk = 0; kk < kBK / 32; ++kk) {
-#pragma unroll
-        for (int ka = 0; ka < S; ++ka) {
-            const int total = S - ka;
-#pragma unroll
-            for (int q0 = 0; q0 < total;) {
-                int cnt = (total - q0) < CMAX ? (total - q0) : CMAX;
-                int n;
-                if (cnt >= 2) { cnt &= ~1; n = BN * cnt; }
-                else { cnt = 1; n = (BN + 15) & ~15; }  // last plane, spills into free TMEM columns
-                const uint32_t idesc = make_idesc_i8(kBM, n, KMAJOR ? 0 : 1, 0);
-                const uint64_t da = KMAJOR ? make_smem_desc(sa + ka * A_BYTES + kk * 32, 16, 512, 4)
-                                           : make_smem_desc(sa + ka * A_BYTES + kk * 4096, 8192, 1024, 2);
-                const uint64_t db = make_smem_desc(sb + q0 * B_BYTES + kk * 32, 16, 512, 4);
-                const uint32_t acc = (!first_block || kk > 0 || ka > 0) ? 1u : 0u;
-                umma_i8(tmem_base + (uint32_t)((ka + q0) * BN), da, db, idesc, acc);
-                q0 += cnt;
-            }
-        }
-    }
-}
-
-// MODE 0: production issue_kblock<S, KMAJOR, BN>; 1: spill variant; 2: single width N = BN repeated 8 x 2 per "block"
+// MODE 0: production issue_kblock<S, KMAJOR, BN> (widths of 8 mod 16 use its spill form); 2: single width N = BN, 16 per "block"
 template <int MODE, int S, bool KMAJOR, int BN>
 __global__ void __launch_bounds__(128, 1) mix_kernel(int iters, long long* cycles_out) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -79,7 +48,6 @@ __global__ void __launch_bounds__(128, 1) mix_kernel(int iters, long long* cycle
             const uint32_t sa = smem_u32(smem + (it & 1) * STAGE);
             const uint32_t sb = sa + 7 * kBM * kBK;
             if (MODE == 0) issue_kblock<S, KMAJOR, BN>(sa, sb, tmem_base, it == 0);
-            else if (MODE == 1) issue_kblock_spill<S, KMAJOR, BN>(sa, sb, tmem_base, it == 0);
             else {
                 const uint32_t idesc = make_idesc_i8(kBM, BN, KMAJOR ? 0 : 1, 0);
 #pragma unroll
@@ -154,8 +122,8 @@ int main() {
     if (run<0, 6, false, 64>("S=6 bn=64 MN-major A (second contraction)", 21 * 64.0, sms, d_cycles)) return 2;
     if (run<0, 6, true, 48>("S=6 bn=48 K-major A  (tail tile of m = 100)", 21 * 48.0, sms, d_cycles)) return 2;
     if (run<0, 6, false, 48>("S=6 bn=48 MN-major A", 21 * 48.0, sms, d_cycles)) return 2;
-    if (run<1, 6, true, 56>("S=6 bn=56 K-major A, equal tiles + spill", 21 * 56.0, sms, d_cycles)) return 2;
-    if (run<1, 6, false, 56>("S=6 bn=56 MN-major A, equal tiles + spill", 21 * 56.0, sms, d_cycles)) return 2;
+    if (run<0, 6, true, 56>("S=6 bn=56 K-major A, equal tiles + spill", 21 * 56.0, sms, d_cycles)) return 2;
+    if (run<0, 6, false, 56>("S=6 bn=56 MN-major A, equal tiles + spill", 21 * 56.0, sms, d_cycles)) return 2;
     if (run<0, 5, true, 64>("S=5 bn=64 K-major A", 15 * 64.0, sms, d_cycles)) return 2;
     if (run<0, 3, true, 128>("S=3 bn=128 K-major A", 6 * 128.0, sms, d_cycles)) return 2;
     if (run<0, 7, true, 64>("S=7 bn=64 K-major A", 28 * 64.0, sms, d_cycles)) return 2;
