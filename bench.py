@@ -403,7 +403,7 @@ def resident_run(torch, dist, shape, args, steps, warmup, world, rank, local, de
     x_dev = DeviceRows(n_total, n_vars, n_factors, lo, hi) if device_source else torch.from_numpy(x_host).cuda()
     mdl = Corex(n_hidden=n_factors, seed=0, tol=1e-12, max_iter=10 ** 9, precision=args.precision,
                 gaussianize=args.gaussianize, comm=True if world > 1 else None,
-                stream_rows=32768 if device_source else None)
+                stream_rows=32768 if device_source else None, algorithm=args.algorithm)
     schedule = mdl._prepare(x_dev)
     prep = dict(mdl.timings)
     del x_dev
@@ -444,7 +444,7 @@ def resident_run(torch, dist, shape, args, steps, warmup, world, rank, local, de
     res = {"ms": ms, "it_s": steps / (ms / 1e3), "k1_ms": k1.value / np_, "k2_ms": k2.value / np_, "exchange_ms": kx.value / np_,
            "pairs": pairs.value, "launches": sess.launches() - launches0, "prep": prep,
            "trials": float(np.mean([t["trials"] for t in trace])) if trace else 0.0, "tc": float(mdl.tc),
-           "clocks": clocks.summary(), "peer": sess._peer_buf is not None, "ranks_bit_identical": identical,
+           "clocks": clocks.summary(), "peer": sess._peer_buf is not None, "algorithm": mdl.algorithm_used, "ranks_bit_identical": identical,
            "n_local": hi - lo}
     del mdl, sess
     torch.cuda.empty_cache()
@@ -539,7 +539,8 @@ def run_ours(args, shape):
         # contract's host-buffer e2e figure -- the default workload (config3) carries that.
         barrier()
         e2e_mdl = Corex(n_hidden=n_factors, seed=0, tol=1e-12, max_iter=per_stage, precision=args.precision,
-                        gaussianize=args.gaussianize, comm=True if world > 1 else None, stream_rows=32768)
+                        gaussianize=args.gaussianize, comm=True if world > 1 else None, stream_rows=32768,
+                        algorithm=args.algorithm)
         t0 = time.perf_counter()
         e2e_mdl.fit(DeviceRows(n_total, n_vars, n_factors, lo, hi))
         torch.cuda.synchronize()
@@ -557,7 +558,7 @@ def run_ours(args, shape):
         # (tol=1e-5, max_iter=10000; 410 iterations at config 3).  "budget" = K iterations spread over the 7 stages.
         converge = args.e2e_fit == "converge"
         e2e_kw = dict(n_hidden=n_factors, seed=0, precision=args.precision, gaussianize=args.gaussianize,
-                      comm=True if world > 1 else None)
+                      comm=True if world > 1 else None, algorithm=args.algorithm)
         if not converge:
             e2e_kw.update(tol=1e-12, max_iter=per_stage)
         # The timed call is the SECOND fit in this process: one untimed fit of a single iteration per stage runs first, so
@@ -716,6 +717,8 @@ def main():
     ap.add_argument("--workload", default="config3", choices=sorted(WORKLOADS))
     ap.add_argument("--precision", default="fp64_split", choices=["fp64", "fp64_split", "fp64_split5", "fp64_split7", "fast"])
     ap.add_argument("--gaussianize", default="standard")
+    ap.add_argument("--algorithm", default="stream", choices=["stream", "gram", "auto"],
+                    help="stream: every pass pair reads X~ (the north star's formulation); gram: X~^T X~ / N formed once")
     ap.add_argument("--rows", type=int, default=0)
     ap.add_argument("--vars", type=int, default=0)
     ap.add_argument("--factors", type=int, default=0)

@@ -141,6 +141,22 @@ int lcx_bind(lcx_session* s, const double* xt, long long n_rows_local, long long
  * scale: every product then comes out NaN, which is what the reference's float64 path does with such data. */
 int lcx_set_x_scale(lcx_session* s, double max_abs);
 int lcx_slice_block(lcx_session* s, const double* xt, long long row0, long long rows, long long ldx);
+/* ---- Gram route (N >= n) ------------------------------------------------------------------------------------------
+ * Every quantity of the fit depends on the data only through X~^T X~ / N: _sig (linearcorex.py:196-213) is
+ * u -> (X~^T X~ / N) u^T and sum_l Y_lj^2 / N = a_j^T (X~^T X~ / N) a_j (:248, :227).  The reference avoids the n x n matrix
+ * because it targets n >> N (:197-198); for N >= n forming it once replaces the two N x n x m contractions of every
+ * iteration by one n x n x m product.
+ * lcx_gram_build: g (n x ldg fp64 device, ldg = lcx_ld(n)) = this rank's X~^T X~ / n_rows_total, from the digit planes of a
+ *   split-mode session bound to X~ (exact int8 digit products on tcgen05, upper triangle computed and mirrored).  The
+ *   caller sums g over ranks.  block_cols (multiple of 128) = variables per pass over X~.
+ * lcx_bind_gram: bind a (second) split-mode session to the summed matrix; every fit-loop entry point below then works
+ *   unchanged on it -- lcx_sig, lcx_moments_*, lcx_direction_*, lcx_trial_ns, lcx_update_syn -- and needs no exchange
+ *   between ranks (each rank holds the same matrix).  g may be released after the call. */
+long long lcx_gram_scratch_doubles(lcx_session* s, int block_cols);
+int lcx_gram_build(lcx_session* s, double* g, long long ldg, int block_cols, double* scratch, long long scratch_doubles);
+long long lcx_gram_workspace_doubles(int n_vars, int n_factors, int precision);
+int lcx_bind_gram(lcx_session* s, const double* g, long long ldg, int n_vars, int n_factors, double* workspace,
+                  long long workspace_doubles);
 /* Split modes: location of the int8 digit planes ([digits][rows][ld_bytes], offset in doubles from the workspace base) of
  * which = 0: X~ (rows = local samples, cols = variables), 1: the last small operand A (W or grad; rows = factors,
  * cols = variables), 2: Y, stored transposed (rows = factors, cols = local samples); and of their scales (1 value for

@@ -45,6 +45,10 @@ SIGNATURES = {
     "lcx_ldy": (_ll, [_i]),
     "lcx_workspace_doubles": (_ll, [_ll, _i, _i, _i]),
     "lcx_bind": (_i, [_p, _p, _ll, _ll, _i, _ll, _i, _p, _ll]),
+    "lcx_gram_scratch_doubles": (_ll, [_p, _i]),
+    "lcx_gram_build": (_i, [_p, _p, _ll, _i, _p, _ll]),
+    "lcx_gram_workspace_doubles": (_ll, [_i, _i, _i]),
+    "lcx_bind_gram": (_i, [_p, _p, _ll, _i, _i, _p, _ll]),
     "lcx_array_info": (_i, [_p, _i, _i, _pll, _pll, _pll, _pll]),
     "lcx_digit_planes_info": (_i, [_p, _i, _pll, C.POINTER(C.c_int), _pll, _pll, _pll, _pll, C.POINTER(C.c_int)]),
     "lcx_colstats_sum": (_i, [_p, _p, _i, _ll, _i, _ll, _i, _d, _p, _p, _p, _ll]),

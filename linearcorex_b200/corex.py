@@ -29,6 +29,13 @@ behaviour):
                       'auto' (default): 'fp64_split', except for problems so small (N n m < 3e7: the README demo, big5,
                       adni) that an iteration is launch-bound -- there 'fp64' (DMMA) has fewer launches and is
                       10-50 % quicker (tools/small_configs.py).  Both are FP64-faithful; `precision_used` tells which ran.
+  algorithm           'stream': every pass pair reads X~ (Y = X~ A^T, then X~^T Y), the reference's own formulation, which
+                      it chose for n >> N (:197-198).  'gram': the fit only ever needs X~^T X~ / N, so that n x n matrix
+                      is formed ONCE on the int8 tcgen05 engine (exact digit products) and every pass pair becomes one
+                      n x n x m product -- independent of the number of samples, and with no exchange between ranks
+                      after the one-off sum of the matrix.  Split precisions only.  'auto' (default): 'gram' when
+                      N >= n, the problem is large enough to be bound by the passes over X (N n m >= 1e9) and the matrix
+                      fits; `algorithm_used` tells which ran.
   exact_trials        False (default): backtracking trials are evaluated through the linearity of
                       `_sig` (rho(W + eta U) = rho(W) + eta _sig(U)) -- one pass pair over X per
                       iteration instead of one per trial.  True: every trial
@@ -99,7 +106,7 @@ class _DeviceSession(object):
     def launches(self):
         v = C.c_longlong(0)
         _lib.check(self.lib.lcx_launch_count(self.h, C.byref(v)))
-        return v.value
+        return v.value + getattr(self, "launches_before", 0)
 
     def bind(self, xt, n_rows_total, n_vars, n_factors, reducer, n_local=None):
         """xt = preprocessed fp64 block, or None (split modes) when the digit planes are filled block by block
@@ -136,6 +143,21 @@ class _DeviceSession(object):
         else:
             self._hook = None
             _lib.check(self.lib.lcx_set_allreduce(self.h, C.cast(None, _lib.ALLREDUCE_FN), None), "lcx_set_allreduce")
+
+    def bind_gram(self, g, n_vars, n_factors):
+        """Bind to the n x n matrix X~^T X~ / N (lcx_bind_gram): its digit planes live in the workspace, `g` is released."""
+        torch = _torch()
+        need = self.lib.lcx_gram_workspace_doubles(n_vars, n_factors, self.precision)
+        if need <= 0:
+            raise _lib.LcxError("bad problem shape")
+        self.ws = torch.zeros(need, dtype=torch.float64, device=self.device)
+        self.xt = None
+        self.n, self.m = n_vars, n_factors
+        _lib.check(self.lib.lcx_bind_gram(self.h, g.data_ptr(), g.stride(0), n_vars, n_factors, self.ws.data_ptr(), need),
+                   "lcx_bind_gram")
+        self._peer_buf = None
+        self._hook = None
+        _lib.check(self.lib.lcx_set_allreduce(self.h, C.cast(None, _lib.ALLREDUCE_FN), None), "lcx_set_allreduce")
 
     def _bind_peers(self, reducer, n_vars, n_factors):
         """Map one symmetric buffer on every rank (torch symmetric memory: CUDA VMM handles exchanged over the process
@@ -208,7 +230,7 @@ class Corex(object):
     def __init__(self, n_hidden=10, max_iter=10000, tol=1e-5, anneal=True, missing_values=None,
                  discourage_overlap=True, gaussianize='standard', gpu=True, verbose=False, seed=None,
                  eliminate_synergy=None, precision='auto', exact_trials=False, input_dtype='float64',
-                 comm=None, device=None, stream_rows=None):
+                 comm=None, device=None, stream_rows=None, algorithm='auto'):
         self.m = n_hidden
         self.max_iter = max_iter
         self.tol = tol
@@ -228,6 +250,10 @@ class Corex(object):
             raise ValueError("precision must be 'auto' or one of %s" % sorted(_lib.PRECISIONS))
         if input_dtype not in ('float64', 'float32'):
             raise ValueError("input_dtype must be 'float64' or 'float32'")
+        if algorithm not in ('auto', 'stream', 'gram'):
+            raise ValueError("algorithm must be 'auto', 'stream' or 'gram'")
+        self.algorithm = algorithm
+        self.algorithm_used = None
         self.precision = precision
         self.precision_used = None if precision == 'auto' else precision  # 'auto' is resolved when fit sees the shape
         self.exact_trials = bool(exact_trials)
@@ -462,6 +488,10 @@ class Corex(object):
             sess.bind(xt, self.n_samples, self.nv, self.m, red)
             _torch().cuda.synchronize()
             self.timings["bind_s"] = time.perf_counter() - t0
+        self.algorithm_used = 'gram' if self._want_gram(red) else 'stream'
+        if self.algorithm_used == 'gram':
+            self._to_gram(red)
+            sess = self._sess
         schedule = [0.]
         if self.ws.size == 0:  # :114-121
             if self.discourage_overlap:
@@ -478,6 +508,65 @@ class Corex(object):
             self._set_w(self.ws)
         self.moments = {"TC": self._moments_from_x()}  # :122
         return schedule
+
+    GRAM_MIN_WORK = 1e9  # N n m from which an iteration is bound by the passes over X~ rather than by launches
+
+    def _want_gram(self, red):
+        """Resolve `algorithm` for the bound problem; every rank sees the same totals and takes the same route."""
+        if getattr(self, "algorithm", "stream") == 'stream':
+            return False
+        split = self._active_precision() != 'fp64'
+        if self.algorithm == 'gram':
+            if not split:
+                raise ValueError("algorithm='gram' runs on the split-integer engine: choose a split precision, not 'fp64'")
+            return True
+        if not split or self.n_samples < self.nv or float(self.n_samples) * self.nv * self.m < self.GRAM_MIN_WORK:
+            return False
+        torch = _torch()
+        sess = self._sess
+        free, _total = torch.cuda.mem_get_info(sess.device)
+        need = 8 * (self.nv * sess.lib.lcx_ld(self.nv) + sess.lib.lcx_gram_workspace_doubles(self.nv, self.m, sess.precision)
+                    + sess.lib.lcx_gram_scratch_doubles(sess.h, 128))
+        fits = 1 if need < 0.8 * free else 0
+        return bool(red.min_scalar(fits)) if red.world > 1 else bool(fits)
+
+    def _to_gram(self, red):
+        """G = X~^T X~ / N from the bound digit planes (summed over ranks), then re-bind the fit loop to G: the digit planes
+        of X~ are released, and from here on no step touches the samples or exchanges anything between ranks."""
+        torch = _torch()
+        sess = self._sess
+        lib = sess.lib
+        t0 = time.perf_counter()
+        n = self.nv
+        ldg = lib.lcx_ld(n)
+        g = torch.zeros((n, ldg), dtype=torch.float64, device=sess.device)
+        free, _total = torch.cuda.mem_get_info(sess.device)
+        block = 128
+        for cand in (1024, 512, 256):
+            if cand <= max(128, ((n + 127) // 128) * 128) and 8 * lib.lcx_gram_scratch_doubles(sess.h, cand) < 0.5 * free:
+                block = cand
+                break
+        nscr = lib.lcx_gram_scratch_doubles(sess.h, block)
+        scratch = torch.empty(nscr, dtype=torch.float64, device=sess.device)
+        _lib.check(lib.lcx_gram_build(sess.h, g.data_ptr(), ldg, block, scratch.data_ptr(), nscr), "lcx_gram_build")
+        if red.world > 1:
+            red.sum_(g)
+        torch.cuda.synchronize(sess.device)
+        self.timings["gram_build_s"] = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        del scratch
+        launches = sess.launches()
+        precision, device = sess.precision, sess.device.index
+        sess.close()
+        sess.ws = None
+        self._sess = None
+        torch.cuda.empty_cache()
+        gs = _DeviceSession(precision, device)
+        gs.bind_gram(g, n, self.m)
+        gs.launches_before = launches
+        self._sess = gs
+        torch.cuda.synchronize(gs.device)
+        self.timings["gram_bind_s"] = time.perf_counter() - t0
 
     def _stream_rows_for(self, x):
         """Row-block size for streamed preparation, or 0 for the one-shot path.  Streaming applies to the split modes

@@ -129,7 +129,9 @@ static double oz_unit_fixed_kb() {
     return (per && atoi(per) == 0) ? 16.0 : 4.0;
 }
 
-static Layout make_layout(long long Nl, int n, int m, int precision) {
+// gram: the bound "data" is the n x n matrix X~^T X~ / N (Nl = n rows); only the first contraction runs, with its output stored
+// factor-major (transposed), so its split-K partials are m x ld each.
+static Layout make_layout(long long Nl, int n, int m, int precision, bool gram = false) {
     Layout L;
     memset(&L, 0, sizeof(L));
     L.S = digits_for(precision);
@@ -245,7 +247,8 @@ static Layout make_layout(long long Nl, int n, int m, int precision) {
             L.oz1_chunk = (int)round_up(cdiv(n, b1), oz::kBK);
             L.oz1_splits = cdiv(n, L.oz1_chunk);
         }
-        const long long part = max((long long)L.oz_splits * mn * L.ld, L.oz1_splits > 1 ? (long long)L.oz1_splits * Nl * L.ldy : 0LL);
+        long long part = max((long long)L.oz_splits * mn * L.ld, L.oz1_splits > 1 ? (long long)L.oz1_splits * Nl * L.ldy : 0LL);
+        if (gram) part = max(part, (long long)L.oz1_splits * mn * L.ld);
         if (part > L.slot[I_PART][0].cols) {  // grow the split-K partial buffer (it is the last big slot before these)
             put1(I_PART, 1, part, part);
         }
@@ -299,6 +302,7 @@ struct lcx_session {
     double* mailbox;  // pinned host, 16 doubles
     bool bound;
     const double* xt;
+    bool gram;        // the bound matrix is X~^T X~ / N (lcx_bind_gram): a "pass pair" is ONE product G A^T (host_gram.cuh)
     long long Nl, Nt, ldx;
     int n, m;
     double* ws;

@@ -2,6 +2,7 @@
 // the X pass pair + exchange, the moment tail, direction and trial.  Included by lcx_api.cu after host_oz.cuh.
 #pragma once
 #include "host_oz.cuh"
+#include "host_gram.cuh"
 
 // ---- GEMM plumbing -----------------------------------------------------------------------------
 // Sum over ranks of [body = sum_z part[z] (rows x ld, valid cols) | tail (ntail doubles)] -> dst_body / dst_tail.
@@ -107,7 +108,13 @@ static int xpair(lcx_session* s, const double* A, bool want_colsq) {
     cudaEvent_t* ev = nullptr;
     if (s->prof_on && s->prof_pending < s->prof_cap) ev = s->prof_ev + kProfEv * s->prof_pending;
     if (ev) LCX_CUDA(cudaEventRecord(ev[0], s->stream));
-    if (L.S > 0) {
+    if (s->gram) {  // one product with the n x n Gram matrix instead of the two passes over X~ (host_gram.cuh)
+        LCX_TRY(gram_pair(s, A, want_colsq ? svec : nullptr, ev));
+        if (ev) {
+            LCX_CUDA(cudaEventRecord(ev[2], s->stream));
+            s->prof_pending++;
+        }
+    } else if (L.S > 0) {
         LCX_TRY(oz_pair(s, A, svec, ev, false, want_colsq));
         if (ev) {
             LCX_CUDA(cudaEventRecord(ev[2], s->stream));

@@ -148,21 +148,22 @@ extern "C" long long lcx_workspace_doubles(long long n_rows_local, int n_vars, i
     return make_layout(n_rows_local, n_vars, n_factors, precision).total;
 }
 
-extern "C" int lcx_bind(lcx_session* s, const double* xt, long long n_rows_local, long long n_rows_total, int n_vars,
-                        long long ldx, int n_factors, double* workspace, long long workspace_doubles) {
+static int bind_common(lcx_session* s, const double* xt, long long n_rows_local, long long n_rows_total, int n_vars,
+                       long long ldx, int n_factors, double* workspace, long long workspace_doubles, bool gram) {
     LCX_REQUIRE(s != nullptr, "null session");
     LCX_REQUIRE(workspace != nullptr, "null device pointer");
     LCX_REQUIRE(xt != nullptr || s->precision != LCX_PRECISION_FP64,
                 "xt may be NULL only in the split modes (digit planes are then filled by lcx_slice_block)");
-    LCX_REQUIRE(n_rows_local > 0 && n_rows_local < (1LL << 31) && n_rows_total >= n_rows_local, "bad row counts");
+    LCX_REQUIRE(n_rows_local > 0 && n_rows_local < (1LL << 31) && n_rows_total >= (gram ? 1 : n_rows_local), "bad row counts");
     LCX_REQUIRE(n_vars > 0 && n_factors > 0, "bad shape");
     LCX_REQUIRE(ldx >= n_vars && ldx % 2 == 0, "ldx must be even and >= n_vars");
     LCX_REQUIRE(((uintptr_t)xt % 16 == 0) && ((uintptr_t)workspace % 128 == 0), "misaligned device pointer");
     const bool streamed = (xt == nullptr);
-    Layout L = make_layout(n_rows_local, n_vars, n_factors, s->precision);
+    Layout L = make_layout(n_rows_local, n_vars, n_factors, s->precision, gram);
     LCX_REQUIRE(workspace_doubles >= L.total, "workspace too small (see lcx_workspace_doubles)");
     LCX_CUDA(cudaSetDevice(s->device));
     s->xt = xt;
+    s->gram = gram;
     s->Nl = n_rows_local;
     s->Nt = n_rows_total;
     s->ldx = ldx;
@@ -184,6 +185,40 @@ extern "C" int lcx_bind(lcx_session* s, const double* xt, long long n_rows_local
         s->xt = nullptr;
     }
     return 0;
+}
+
+extern "C" int lcx_bind(lcx_session* s, const double* xt, long long n_rows_local, long long n_rows_total, int n_vars,
+                        long long ldx, int n_factors, double* workspace, long long workspace_doubles) {
+    return bind_common(s, xt, n_rows_local, n_rows_total, n_vars, ldx, n_factors, workspace, workspace_doubles, false);
+}
+
+// ---- Gram route (host_gram.cuh) -----------------------------------------------------------------------------------
+extern "C" long long lcx_gram_scratch_doubles(lcx_session* s, int block_cols) {
+    if (!s || !s->bound || s->L.S <= 0 || s->gram || block_cols < 128 || block_cols % 128 != 0) return -1;
+    return gram_scratch_doubles(s, block_cols, round_up(s->n, 16));
+}
+
+extern "C" int lcx_gram_build(lcx_session* s, double* g, long long ldg, int block_cols, double* scratch, long long scratch_doubles) {
+    S_REQUIRE_BOUND(s);
+    LCX_REQUIRE(s->L.S > 0 && !s->gram, "lcx_gram_build needs a split-mode session bound to X~");
+    LCX_REQUIRE(g != nullptr && scratch != nullptr, "null device pointer");
+    LCX_REQUIRE(block_cols >= 128 && block_cols % 128 == 0, "block_cols must be a positive multiple of 128");
+    LCX_REQUIRE(ldg == round_up(s->n, 16), "ldg must be lcx_ld(n_vars)");
+    LCX_REQUIRE(((uintptr_t)g % 128 == 0) && ((uintptr_t)scratch % 128 == 0), "misaligned device pointer");
+    LCX_REQUIRE(scratch_doubles >= gram_scratch_doubles(s, block_cols, ldg), "scratch too small (see lcx_gram_scratch_doubles)");
+    return gram_build(s, g, ldg, block_cols, scratch);
+}
+
+extern "C" long long lcx_gram_workspace_doubles(int n_vars, int n_factors, int precision) {
+    if (n_vars <= 0 || n_factors <= 0 || precision <= LCX_PRECISION_FP64 || precision > LCX_PRECISION_FP64_SPLIT7) return -1;
+    return make_layout(n_vars, n_vars, n_factors, precision, true).total;
+}
+
+extern "C" int lcx_bind_gram(lcx_session* s, const double* g, long long ldg, int n_vars, int n_factors, double* workspace,
+                             long long workspace_doubles) {
+    LCX_REQUIRE(s != nullptr && g != nullptr, "null argument");
+    LCX_REQUIRE(s->precision != LCX_PRECISION_FP64, "the Gram route runs on the split-integer engine (choose a split precision)");
+    return bind_common(s, g, n_vars, 1, n_vars, ldg, n_factors, workspace, workspace_doubles, true);
 }
 
 // ---- streamed digit slicing (X~ never materialised as a whole: the 1M x 20k target on one GPU) -------------------
@@ -448,7 +483,9 @@ extern "C" int lcx_init_scale(lcx_session* s, double eps) {
     const int m = s->m, n = s->n;
     double* W = s->ptr(LCX_A_W);
     double* svec = s->ptr(LCX_A_D) + (long long)m * L.ld;
-    if (L.S > 0) {
+    if (s->gram) {
+        LCX_TRY(gram_pair(s, W, svec, nullptr));
+    } else if (L.S > 0) {
         LCX_TRY(oz_pair(s, W, svec, nullptr, true, true));
     } else {
         LCX_TRY(lcx_project(s, s->xt, s->Nl, n, s->ldx, W, L.ld, m, s->ptr(LCX_A_Y), L.ldy, svec, s->ptr(I_COLSQ),

@@ -166,6 +166,8 @@ struct GemmParams {
                                  // equal tiles (m = 100, S = 6 -> 56 + 56, not 64 + 48) so the CTAs that share an X~ tile by
                                  // multicast -- and therefore run in lock-step -- carry the same work
     int trans_out;               // 1: store C[col][row] (the second contraction writes (X~^T Y)^T factor-major)
+    int debug;                   // experiments only (LCX_OZ_DEBUG): bit 0 skip the MMAs, bit 1 skip the M-side loads, bit 2 skip the
+                                 // N-side loads -- results are garbage, timings isolate the operand feed from the tensor work
     const double* c_add;         // optional (with trans_out, no split): C = c_add + product, c_add laid out like C (may be C
                                  // itself: grad = G0 + H W, linearcorex.py:300; Qij = rinv + (ry - I) rinv, :266)
 };
@@ -303,19 +305,21 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                     mbar_wait(&empty_bar[st], ph ^ 1);
                     uint8_t* sa = smem + st * STAGE_BYTES;
                     uint8_t* sb = sa + S * A_BYTES;
-                    mbar_expect_tx(&full_bar[st], S * (A_BYTES + b_bytes));
+                    const bool load_a = !(p.debug & 2), load_b = !(p.debug & 4);
+                    mbar_expect_tx(&full_bar[st], S * ((load_a ? A_BYTES : 0) + (load_b ? b_bytes : 0)));
                     const int k0 = kbeg + kb * kBK;
 #pragma unroll
                     for (int s = 0; s < S; ++s) {
                         // shared operand: plane s is fetched by cluster rank s % CL and multicast to all CL CTAs
-                        if (CL == 1) {
+                        if (!load_a) {
+                        } else if (CL == 1) {
                             if (KMAJOR) tma_load_3d(sa + s * A_BYTES, &mapA, &full_bar[st], k0, m_tile * kBM, s);
                             else tma_load_3d(sa + s * A_BYTES, &mapA, &full_bar[st], m_tile * kBM, k0, s);
                         } else if ((uint32_t)(s % CL) == crank) {
                             if (KMAJOR) tma_load_3d_mc(sa + s * A_BYTES, &mapA, &full_bar[st], k0, m_tile * kBM, s, kMask);
                             else tma_load_3d_mc(sa + s * A_BYTES, &mapA, &full_bar[st], m_tile * kBM, k0, s, kMask);
                         }
-                        tma_load_3d(sb + s * b_bytes, &mapB, &full_bar[st], k0, n_tile * bn, s);
+                        if (load_b) tma_load_3d(sb + s * b_bytes, &mapB, &full_bar[st], k0, n_tile * bn, s);
                     }
                 }
             }
@@ -345,10 +349,11 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                     tc_fence_after();
                     const uint32_t sa = smem_u32(smem + st * STAGE_BYTES);
                     const uint32_t sb = sa + S * A_BYTES;
-                    bool wide = false;
+                    bool wide = (p.debug & 1) != 0;   // (debug: no MMAs at all)
                     if constexpr (kBN > 64) {
-                        wide = bn > 64;
-                        if (bn == 128) issue_kblock<S, KMAJOR, 128>(sa, sb, tmem_base, kb == 0);
+                        wide = wide || bn > 64;
+                        if (p.debug & 1) {
+                        } else if (bn == 128) issue_kblock<S, KMAJOR, 128>(sa, sb, tmem_base, kb == 0);
                         else if (bn == 112) issue_kblock<S, KMAJOR, 112>(sa, sb, tmem_base, kb == 0);
                         else if (bn == 96) issue_kblock<S, KMAJOR, 96>(sa, sb, tmem_base, kb == 0);
                         else if (bn == 80) issue_kblock<S, KMAJOR, 80>(sa, sb, tmem_base, kb == 0);
@@ -726,6 +731,67 @@ __global__ void absmax_finish_kernel(const double* __restrict__ part, int nparts
     if (threadIdx.x == 0) scale[0] = pow2_above(mx);
 }
 
+// ---- Gram route (N >= n: the fit depends on X~ only through X~^T X~ / N, linearcorex.py:196-213 builds the same products
+// "without explicitly constructing the covariance matrix" because it targets n >> N) -------------------------------------
+// Digit planes of a column block of X~, turned around: out[s][c][r] = in[s][r][c0 + c] for c < ncols -- the K-major
+// factor-side operand (samples contiguous) of X~^T X~[:, block].  One CTA of 32 x 8 threads per 128 x 128 byte tile and
+// plane (coalesced 128 B reads along the variables, 128 B writes along the samples).
+__global__ void __launch_bounds__(256) transpose_planes_kernel(const int8_t* __restrict__ in, long long ld_in, long long rows,
+                                                               long long in_slice_stride, int c0, int ncols,
+                                                               int8_t* __restrict__ out, long long ld_out,
+                                                               long long out_slice_stride) {
+    constexpr int PITCH = 132;
+    __shared__ __align__(4) int8_t t[128][PITCH];
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const long long r0 = (long long)blockIdx.x * 128;
+    const int cb = blockIdx.y * 128;   // column offset inside the block
+    const int8_t* src = in + (long long)blockIdx.z * in_slice_stride;
+    int8_t* dst = out + (long long)blockIdx.z * out_slice_stride;
+#pragma unroll 4
+    for (int i = 0; i < 16; ++i) {
+        const int rr = ty + 8 * i;
+        const long long r = r0 + rr;
+        uint32_t w = 0;
+        if (r < rows && c0 + cb + 4 * tx < ld_in) w = *reinterpret_cast<const uint32_t*>(src + r * ld_in + c0 + cb + 4 * tx);
+        t[4 * tx + 0][rr] = (int8_t)(w & 0xff);
+        t[4 * tx + 1][rr] = (int8_t)((w >> 8) & 0xff);
+        t[4 * tx + 2][rr] = (int8_t)((w >> 16) & 0xff);
+        t[4 * tx + 3][rr] = (int8_t)((w >> 24) & 0xff);
+    }
+    __syncthreads();
+    if (r0 + 4 * tx >= ld_out) return;
+    for (int c = ty; c < 128; c += 8) {
+        if (cb + c < ncols)
+            *reinterpret_cast<uint32_t*>(dst + (long long)(cb + c) * ld_out + r0 + 4 * tx) =
+                *reinterpret_cast<const uint32_t*>(&t[c][4 * tx]);
+    }
+}
+
+// out[i] = x_scale^2 * factor  (output scale of X~^T X~ / N: both operands carry the exponent of X~)
+__global__ void gram_scale_kernel(const double* __restrict__ x_scale, double factor, double* __restrict__ out, int count) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) out[i] = x_scale[0] * x_scale[0] * factor;
+}
+
+// g[i][j] = g[j][i] for i > j (the build fills row a from the start of a's column block to n: the upper triangle)
+__global__ void __launch_bounds__(256) mirror_upper_kernel(double* __restrict__ g, long long ld, int n) {
+    __shared__ double t[32][33];
+    const int ti = blockIdx.y, tj = blockIdx.x;   // destination tile (rows ti, cols tj), ti >= tj
+    if (ti < tj) return;
+    const int tx = threadIdx.x, ty = threadIdx.y;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {   // source tile (rows tj, cols ti)
+        const int r = tj * 32 + ty + 8 * k, c = ti * 32 + tx;
+        t[ty + 8 * k][tx] = (r < n && c < n) ? g[(long long)r * ld + c] : 0.0;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int r = ti * 32 + ty + 8 * k, c = tj * 32 + tx;
+        if (r < n && c < n && r > c) g[(long long)r * ld + c] = t[tx][ty + 8 * k];
+    }
+}
+
 // ---- host side -----------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -752,9 +818,15 @@ inline int make_slice_map(CUtensorMap* map, const void* base, long long inner, l
     cuuint64_t strides[2] = {(cuuint64_t)ld, (cuuint64_t)slice_stride};
     cuuint32_t box[3] = {(cuuint32_t)box_inner, (cuuint32_t)box_rows, 1};
     cuuint32_t estr[3] = {1, 1, 1};
+    CUtensorMapL2promotion promo = CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
+    if (const char* env = getenv("LCX_OZ_L2PROMO")) {  // experiment knob: 0 none, 64, 128, 256 (default)
+        const int v = atoi(env);
+        promo = v == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : v == 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+              : v == 128 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
+    }
     CUresult rc = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void*>(base), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
-                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, promo,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (rc != CUDA_SUCCESS) return fail(-2, "cuTensorMapEncodeTiled", "encode failed (check alignment / strides)");
     return 0;
 }
@@ -782,6 +854,14 @@ inline int launch_oz_gemm_cl(const CUtensorMap& mapA, const CUtensorMap& mapB, G
     p.m_tiles = (int)grid.y;
     p.k_splits = (int)grid.z;
     const long long units = (long long)p.n_groups * p.m_tiles * p.k_splits;
+    {
+        static int dbg = -1;
+        if (dbg < 0) {
+            const char* env = getenv("LCX_OZ_DEBUG");
+            dbg = env ? atoi(env) : 0;
+        }
+        p.debug = dbg;
+    }
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.blockDim = dim3(kThreads);

@@ -48,6 +48,10 @@ class Reducer(object):
         dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
         return t.item()
 
+    def min_scalar(self, value):
+        """Minimum of a host scalar over the ranks."""
+        return -self.max_scalar(-value)
+
     def sum_scalar(self, value):
         if self.world == 1:
             return value

@@ -72,6 +72,89 @@ __global__ void __launch_bounds__(128, 1) mix_kernel(int iters, long long* cycle
     if (warp == 0) tmem_dealloc(tmem_base, 512);
 }
 
+// The production K block issued back to back (as in mix_kernel MODE 0) WHILE a second thread streams `fill_bytes` per K block
+// from an L2-resident buffer into other shared memory with bulk copies (the TMA fill of the real kernel, minus any
+// dependency between the two).  If MMA operand fetch and the fill share one shared-memory port, the K block slows down
+// from its resident-operand time towards (operand bytes read + bytes filled) / port width.
+template <int S, bool KMAJOR, int BN>
+__global__ void __launch_bounds__(128, 1) mix_fill_kernel(int iters, int fill_bytes, const uint8_t* __restrict__ src,
+                                                         long long* cycles_out, long long* fill_cycles_out) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ __align__(8) uint64_t fbar[2];
+    __shared__ uint32_t tmem_base_smem;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    constexpr int STAGE = 6 * (kBM * kBK + 64 * kBK);          // 72 KB
+    uint8_t* fill_dst = smem + 2 * STAGE;                       // 2 x 36 KB landing buffers
+    for (int i = tid; i < 2 * STAGE; i += 128) smem[i] = (uint8_t)((i * 7 + blockIdx.x) & 3);
+    if (tid == 0) {
+        mbar_init(&bar, 1);
+        mbar_init(&fbar[0], 1);
+        mbar_init(&fbar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    if (warp == 0) tmem_alloc(&tmem_base_smem, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_smem;
+    if (tid == 0) {
+        const long long t0 = clock64();
+        for (int it = 0; it < iters; ++it) {
+            const uint32_t sa = smem_u32(smem + (it & 1) * STAGE);
+            const uint32_t sb = sa + 6 * kBM * kBK;
+            issue_kblock<S, KMAJOR, BN>(sa, sb, tmem_base, it == 0);
+        }
+        umma_commit(&bar);
+        mbar_wait(&bar, 0);
+        cycles_out[blockIdx.x] = clock64() - t0;
+    } else if (tid == 32 && fill_bytes > 0) {
+        // each iteration = fill_bytes in two halves, each half one mbarrier phase; a half is re-issued once it has landed
+        const int half = fill_bytes / 2;
+        const uint8_t* mine = src + (size_t)blockIdx.x * (256 << 10);
+        const long long t0 = clock64();
+        for (int it = 0; it < 2 * iters; ++it) {
+            const int b = it & 1;
+            if (it >= 2) mbar_wait(&fbar[b], ((it >> 1) - 1) & 1);
+            mbar_expect_tx(&fbar[b], half);
+            for (int off = 0; off < half; off += 9216) {
+                const int n = (half - off) < 9216 ? (half - off) : 9216;
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                                 smem_u32(fill_dst + b * 36864 + off)),
+                             "l"(mine + ((size_t)(it * 36864 + off) & ((256 << 10) - 1) & ~(size_t)1023)), "r"(n), "r"(smem_u32(&fbar[b]))
+                             : "memory");
+            }
+        }
+        mbar_wait(&fbar[0], ((2 * iters - 2) >> 1) & 1);
+        mbar_wait(&fbar[1], ((2 * iters - 1) >> 1) & 1);
+        fill_cycles_out[blockIdx.x] = clock64() - t0;
+    }
+    __syncthreads();
+    tc_fence_after();
+    if (warp == 0) tmem_dealloc(tmem_base, 512);
+}
+
+template <int S, bool KMAJOR, int BN>
+static int run_fill(const char* label, int fill_bytes, int sms, long long* d_cycles, const uint8_t* src) {
+    const int smem = 220 * 1024;
+    auto kern = mix_fill_kernel<S, KMAJOR, BN>;
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    const int iters = 20000;
+    kern<<<sms, 128, smem>>>(200, fill_bytes, src, d_cycles, d_cycles + 512);
+    CK(cudaDeviceSynchronize());
+    kern<<<sms, 128, smem>>>(iters, fill_bytes, src, d_cycles, d_cycles + 512);
+    CK(cudaDeviceSynchronize());
+    static long long h[1024];
+    CK(cudaMemcpy(h, d_cycles, 1024 * sizeof(long long), cudaMemcpyDeviceToHost));
+    double a = 0, b = 0;
+    for (int i = 0; i < sms; ++i) { a += (double)h[i]; b += (double)h[512 + i]; }
+    printf("%-58s MMA %8.1f cycles per block;  fill of %3d KB per block: %8.1f cycles per block (%5.1f B/clk)\n", label,
+           a / sms / iters, fill_bytes >> 10, fill_bytes ? b / sms / iters : 0.0, fill_bytes ? fill_bytes / (b / sms / iters) : 0.0);
+    return 0;
+}
+
 template <int MODE, int S, bool KMAJOR, int BN>
 static int run(const char* label, double ideal_cycles, int sms, long long* d_cycles) {
     const int smem = 210 * 1024;
@@ -127,5 +210,16 @@ int main() {
     if (run<0, 5, true, 64>("S=5 bn=64 K-major A", 15 * 64.0, sms, d_cycles)) return 2;
     if (run<0, 3, true, 128>("S=3 bn=128 K-major A", 6 * 128.0, sms, d_cycles)) return 2;
     if (run<0, 7, true, 64>("S=7 bn=64 K-major A", 28 * 64.0, sms, d_cycles)) return 2;
+    printf("# production K block with a concurrent bulk-copy fill of shared memory from an L2-resident buffer\n");
+    uint8_t* src;
+    CK(cudaMalloc(&src, (size_t)sms * (256 << 10) + (64 << 10)));
+    CK(cudaMemset(src, 1, (size_t)sms * (256 << 10)));
+    if (run_fill<6, true, 64>("S=6 bn=64 K-major A, no fill", 0, sms, d_cycles, src)) return 2;
+    if (run_fill<6, true, 64>("S=6 bn=64 K-major A + 36 KB fill", 36864, sms, d_cycles, src)) return 2;
+    if (run_fill<6, true, 64>("S=6 bn=64 K-major A + 72 KB fill (production ratio)", 73728, sms, d_cycles, src)) return 2;
+    if (run_fill<6, false, 64>("S=6 bn=64 MN-major A + 72 KB fill", 73728, sms, d_cycles, src)) return 2;
+    if (run_fill<6, true, 56>("S=6 bn=56 K-major A + 72 KB fill", 73728, sms, d_cycles, src)) return 2;
+    if (run_fill<5, true, 64>("S=5 bn=64 K-major A + 60 KB fill (production ratio)", 61440, sms, d_cycles, src)) return 2;
+    if (run_fill<7, true, 64>("S=7 bn=64 K-major A + 72 KB fill (production: 84 KB)", 73728, sms, d_cycles, src)) return 2;
     return 0;
 }
