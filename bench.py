@@ -390,8 +390,10 @@ def ncu_evidence(precision):
     return out
 
 
-def resident_run(torch, dist, shape, args, steps, warmup, world, rank, local, device_source, x_host, lo, hi):
-    """Exactly `steps` fit iterations with X~ resident in HBM, timed by CUDA events, max over ranks."""
+def resident_run(torch, dist, shape, args, steps, warmup, world, rank, local, device_source, x_host, lo, hi, algorithm=None):
+    """Exactly `steps` fit iterations with X~ (or, on the Gram route, X~^T X~ / N) resident in HBM, timed by CUDA events, max
+    over ranks."""
+    algorithm = algorithm or args.algorithm or "stream"
     from linearcorex_b200 import Corex, _lib
     n_total, n_vars, n_factors = shape
 
@@ -403,14 +405,19 @@ def resident_run(torch, dist, shape, args, steps, warmup, world, rank, local, de
     x_dev = DeviceRows(n_total, n_vars, n_factors, lo, hi) if device_source else torch.from_numpy(x_host).cuda()
     mdl = Corex(n_hidden=n_factors, seed=0, tol=1e-12, max_iter=10 ** 9, precision=args.precision,
                 gaussianize=args.gaussianize, comm=True if world > 1 else None,
-                stream_rows=32768 if device_source else None, algorithm=args.algorithm)
+                stream_rows=32768 if device_source else None, algorithm=algorithm)
     schedule = mdl._prepare(x_dev)
     prep = dict(mdl.timings)
     del x_dev
     mdl._begin_stage(schedule[0], rescale=False)
     sess = mdl._sess
-    for _ in range(warmup):
-        mdl._iterate()
+    def iterate(k):  # exactly k iterations of the current stage, the way fit() runs them (lcx_run_stage_ns)
+        n0 = len(mdl.trace)
+        mdl.max_iter = k
+        ok = mdl._run_stage_native()
+        assert ok and len(mdl.trace) - n0 == k, "the timed region must run exactly %d iterations" % k
+
+    iterate(warmup)
     sess.lib.lcx_profile_enable(sess.h, 1)
     k1, k2, kx, pairs = C.c_double(), C.c_double(), C.c_double(), C.c_longlong()
     sess.lib.lcx_profile_read_phases(sess.h, C.byref(k1), C.byref(k2), C.byref(kx), C.byref(pairs), 1)
@@ -420,8 +427,7 @@ def resident_run(torch, dist, shape, args, steps, warmup, world, rank, local, de
     with ClockSampler(local) as clocks:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for _ in range(steps):
-            mdl._iterate()
+        iterate(steps)
         e1.record()
         barrier()
     ms = e0.elapsed_time(e1)
@@ -492,6 +498,61 @@ def roofline_of(res, shape, args, peaks, dgemm_peak, i8_peak):
     return out
 
 
+def gram_record(res, shape, args, peaks, i8_peak, steps):
+    """Sub-record of a resident run on the Gram route: the per-iteration product G A^T and the one-off build of G."""
+    n_total, n_vars, n_factors = shape
+    digits = DIGITS[args.precision]
+    planes = digits * (digits + 1) / 2
+    peak = 2.0 * float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1400.0)))
+    prod_ops = 2.0 * n_vars * n_vars * n_factors * planes           # one n x n x m product as int8 digit-plane products
+    prod_ms = res["k1_ms"]
+    build_s = res["prep"].get("gram_build_s")
+    # the build computes the upper triangle of X~^T X~ on this rank's rows: n (n + block) / 2 outputs, ~half of 2 N n^2
+    build_ops = 2.0 * res["n_local"] * n_vars * n_vars * planes / 2.0
+    ms_step = res["ms"] / steps
+    out = {"what": "Gram route (Corex(algorithm='gram'); 'auto' picks it for N >= n): X~^T X~ / N is formed once from the int8 "
+                   "digit planes (exact products on tcgen05, upper triangle), then every pass pair of the fit is ONE "
+                   "n x n x m product with it -- results equal to the streaming route and the reference to 1e-9 "
+                   "(tests/test_gpu_gram.py)",
+           "metric": METRIC, "value": res["it_s"], "unit": UNIT, "ms_per_step": ms_step, "steps": steps,
+           "algorithm_used": res.get("algorithm"),
+           "phases_ms_per_step": {"product_G_At": res["pairs"] / steps * prod_ms,
+                                  "split_k_combine": res["pairs"] / steps * res["exchange_ms"],
+                                  "m_x_n_phase_and_host_sync": ms_step - res["pairs"] / steps * (prod_ms + res["k2_ms"] + res["exchange_ms"])},
+           "one_off_s": {k: round(v, 4) for k, v in res["prep"].items()},
+           "roofline_product": {"bound": "tensor", "achieved": prod_ops / (prod_ms / 1e3) / 1e12 if prod_ms > 0 else None,
+                                "peak": peak, "unit": "TOP/s",
+                                "frac": prod_ops / (prod_ms / 1e3) / 1e12 / peak if prod_ms > 0 else None,
+                                "kernel": "oz_gemm_kernel<%d,true,2> (G planes K-major x digit planes of A, output stored "
+                                          "factor-major) incl. digit slicing of A" % digits},
+           "trials_per_iteration": res["trials"], "TC_after_timed_region": res["tc"], "clocks": res["clocks"],
+           "ranks_bit_identical": res["ranks_bit_identical"], "gpu_launches": int(res["launches"])}
+    if build_s:
+        out["roofline_build"] = {"bound": "tensor", "achieved": build_ops / build_s / 1e12, "peak": peak, "unit": "TOP/s",
+                                 "frac": build_ops / build_s / 1e12 / peak,
+                                 "kernel": "oz_gemm_kernel<%d,false,2> over column blocks of X~ (variables on M) + plane transposes, "
+                                           "split-K combine, mirror%s" % (digits, "; incl. the sum over ranks" if res["n_local"] < n_total else "")}
+        if i8_peak and i8_peak.get("sustained_tops"):
+            out["roofline_build"]["frac_of_int8_measured_in_run"] = build_ops / build_s / 1e12 / i8_peak["sustained_tops"]
+    return out
+
+
+def timed_fit(torch, dist, world, kw, x, barrier):
+    """One end-to-end `Corex(**kw).fit(x)`: wall seconds (max over ranks) and the fitted model."""
+    from linearcorex_b200 import Corex
+    barrier()
+    mdl = Corex(**kw)
+    t0 = time.perf_counter()
+    mdl.fit(x)
+    torch.cuda.synchronize()
+    sec = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([sec], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        sec = t.item()
+    return sec, mdl
+
+
 def run_ours(args, shape):
     import torch
     import torch.distributed as dist
@@ -527,6 +588,13 @@ def run_ours(args, shape):
     # ---- device-resident timing: exactly K iterations ----------------------------------------------
     res = resident_run(torch, dist, shape, args, args.steps, args.warmup, world, rank, local, device_source, x_host, lo, hi)
     ms, it_s, n_local = res["ms"], res["it_s"], res["n_local"]
+    # the Gram route on the same data, as a sub-record (N >= n, split modes): the default of the public API at this shape
+    gram = None
+    if args.algorithm is None and digits and n_total >= n_vars:
+        barrier()
+        gres = resident_run(torch, dist, shape, args, args.steps, args.warmup, world, rank, local, device_source, x_host, lo, hi,
+                            algorithm="gram")
+        gram = gram_record(gres, shape, args, peaks, i8_peak, args.steps)
     exchange = ("none (single rank)" if world == 1 else
                 "fused split-K combine + two-shot all-reduce kernel over NVLink peer memory" if res["peer"]
                 else "split-K combine kernel + NCCL all-reduce (torch.distributed hook)")
@@ -540,7 +608,7 @@ def run_ours(args, shape):
         barrier()
         e2e_mdl = Corex(n_hidden=n_factors, seed=0, tol=1e-12, max_iter=per_stage, precision=args.precision,
                         gaussianize=args.gaussianize, comm=True if world > 1 else None, stream_rows=32768,
-                        algorithm=args.algorithm)
+                        algorithm=args.algorithm or "auto")
         t0 = time.perf_counter()
         e2e_mdl.fit(DeviceRows(n_total, n_vars, n_factors, lo, hi))
         torch.cuda.synchronize()
@@ -549,46 +617,54 @@ def run_ours(args, shape):
         e2e = {"value": e2e_iters / e2e_s, "unit": UNIT, "h2d_bytes_per_step": 0,
                "d2h_bytes_per_step": int(sum(np.asarray(v).nbytes for v in e2e_mdl.moments.values()) / e2e_iters),
                "iterations": e2e_iters, "seconds": e2e_s, "phases_s": {k: round(v, 4) for k, v in e2e_mdl.timings.items()},
+               "algorithm": e2e_mdl.algorithm_used,
                "what": "Corex.fit(device row generator), streamed preparation; not a host-buffer e2e (see config3)"}
+        del e2e_mdl
+        e2e_stream = None
     else:
         # the e2e input lives in page-locked host memory (the contract's "from pinned host memory"); --pageable times
         # the pageable-numpy path (an extra pipelined host memcpy into pinned staging) instead
         x_pin = None if args.pageable else torch.from_numpy(x_host).pin_memory()
+        x_in = x_pin if x_pin is not None else x_host
         # "converge" = the call a user makes: Corex(n_hidden=m).fit(X) with the reference's default stopping rule
         # (tol=1e-5, max_iter=10000; 410 iterations at config 3).  "budget" = K iterations spread over the 7 stages.
         converge = args.e2e_fit == "converge"
-        e2e_kw = dict(n_hidden=n_factors, seed=0, precision=args.precision, gaussianize=args.gaussianize,
-                      comm=True if world > 1 else None, algorithm=args.algorithm)
-        if not converge:
-            e2e_kw.update(tol=1e-12, max_iter=per_stage)
-        # The timed call is the SECOND fit in this process: one untimed fit of a single iteration per stage runs first, so
-        # the caching allocator already holds its blocks (cudaMalloc of ~20 GB costs 0.2-0.3 s the first time) and the
-        # NVLink peer mapping exists -- a first call in a fresh process pays ~0.3 s more.
-        warm = Corex(**dict(e2e_kw, tol=1e-12, max_iter=1))
-        warm.fit(x_pin if x_pin is not None else x_host)
-        del warm
-        barrier()
-        e2e_mdl = Corex(**e2e_kw)
-        t0 = time.perf_counter()
-        e2e_mdl.fit(x_pin if x_pin is not None else x_host)
-        torch.cuda.synchronize()
-        e2e_s = time.perf_counter() - t0
-        if world > 1:
-            t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            e2e_s = t.item()
-        e2e_iters = len(e2e_mdl.history["TC"])
-        d2h = sum(np.asarray(v).nbytes for v in e2e_mdl.moments.values()) + e2e_mdl.ws.nbytes + 16 * 8 * 4 * e2e_iters
-        e2e = {"value": e2e_iters / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(x_host.nbytes * world / e2e_iters),
-               "d2h_bytes_per_step": int(d2h / e2e_iters), "iterations": e2e_iters, "seconds": e2e_s,
-               "phases_s": {k: round(v, 4) for k, v in e2e_mdl.timings.items()},
-               "what": "second fit in the process: Corex(n_hidden=%d%s).fit(pinned host float32 X): H2D of X, preprocess, digit "
-                       "slicing, 7 anneal stages%s, final sort + full moments, D2H of ws and every moments key"
-                       % (n_factors, "" if converge else ", tol=1e-12, max_iter=%d" % per_stage,
-                          " run to the reference's default stopping rule (tol=1e-5, max_iter=10000)" if converge else "")}
+
+        def e2e_record(algorithm):
+            kw = dict(n_hidden=n_factors, seed=0, precision=args.precision, gaussianize=args.gaussianize,
+                      comm=True if world > 1 else None, algorithm=algorithm)
+            if not converge:
+                kw.update(tol=1e-12, max_iter=per_stage)
+            # The timed call is the SECOND fit in this process: one untimed fit of a single iteration per stage runs first,
+            # so the caching allocator already holds its blocks (cudaMalloc of ~20 GB costs 0.2-0.3 s the first time) and
+            # the NVLink peer mapping exists -- a first call in a fresh process pays ~0.3 s more.
+            warm = Corex(**dict(kw, tol=1e-12, max_iter=1))
+            warm.fit(x_in)
+            del warm
+            sec, mdl = timed_fit(torch, dist, world, kw, x_in, barrier)
+            iters = len(mdl.history["TC"])
+            d2h = sum(np.asarray(v).nbytes for v in mdl.moments.values()) + mdl.ws.nbytes + 16 * 8 * 4 * iters
+            rec = {"value": iters / sec, "unit": UNIT, "h2d_bytes_per_step": int(x_host.nbytes * world / iters),
+                   "d2h_bytes_per_step": int(d2h / iters), "iterations": iters, "seconds": sec,
+                   "algorithm": "%s -> %s" % (algorithm, mdl.algorithm_used) if algorithm == "auto" else mdl.algorithm_used,
+                   "TC": float(mdl.tc), "phases_s": {k: round(v, 4) for k, v in mdl.timings.items()},
+                   "what": "second fit in the process: Corex(n_hidden=%d%s%s).fit(pinned host float32 X): H2D of X, preprocess, "
+                           "digit slicing%s, 7 anneal stages%s, final sort + full moments, D2H of ws and every moments key"
+                           % (n_factors, "" if converge else ", tol=1e-12, max_iter=%d" % per_stage,
+                              "" if algorithm == "auto" else ", algorithm='%s'" % algorithm,
+                              ", X~^T X~ / N formed once (Gram route)" if mdl.algorithm_used == "gram" else "",
+                              " run to the reference's default stopping rule (tol=1e-5, max_iter=10000)" if converge else "")}
+            del mdl
+            torch.cuda.empty_cache()
+            return rec
+
+        # the headline e2e is the call a user makes (all defaults: algorithm='auto'); when that resolves to the Gram route
+        # the same call pinned to the streaming route is timed next to it
+        e2e = e2e_record(args.algorithm or "auto")
+        e2e_stream = None
+        if args.algorithm is None and e2e["algorithm"].endswith("gram"):
+            e2e_stream = e2e_record("stream")
         del x_pin
-    del e2e_mdl
-    x_host = None
     torch.cuda.empty_cache()
 
     # ---- the north-star shape (BASELINE.json target: 1M x 20k x 100) as a sub-record of the same line -------------------
@@ -614,6 +690,10 @@ def run_ours(args, shape):
                   "clocks": tres["clocks"], "TC_after_timed_region": tres["tc"], "prepare_s": {k: round(v, 3) for k, v in tres["prep"].items()},
                   "trials_per_iteration": tres["trials"], "ranks_bit_identical": tres["ranks_bit_identical"],
                   "gpu_launches": int(tres["launches"])}
+        if args.algorithm is None:
+            barrier()
+            tg = resident_run(torch, dist, tshape, args, 20, 5, world, rank, local, True, None, tlo, thi, algorithm="gram")
+            target["gram"] = gram_record(tg, tshape, args, peaks, i8_peak, 20)
 
     if rank != 0:
         if world > 1:
@@ -681,6 +761,19 @@ def run_ours(args, shape):
         "e2e": e2e,
         "gpu_launches": int(res["launches"]),
     }
+    if res.get("algorithm") == "gram":  # --algorithm gram: the main arm itself ran the Gram route
+        g = gram_record(res, shape, args, peaks, i8_peak, args.steps)
+        line["roofline"] = dict(g["roofline_product"], share_of_step=g["phases_ms_per_step"]["product_G_At"] / g["ms_per_step"],
+                                build=g.get("roofline_build"), traffic=None)
+        line["phases_ms_per_step"] = g["phases_ms_per_step"]
+        line["config"]["algorithm"] = "gram"
+    else:
+        line["config"]["algorithm"] = "stream (every pass pair reads X~: the north star's formulation); see `gram` for the route "\
+                                      "the public API picks at this shape"
+    if gram is not None:
+        line["gram"] = gram
+    if e2e_stream is not None:
+        line["e2e_stream"] = e2e_stream
     if target is not None:
         line["target"] = target
     if cpu is not None:
@@ -717,8 +810,10 @@ def main():
     ap.add_argument("--workload", default="config3", choices=sorted(WORKLOADS))
     ap.add_argument("--precision", default="fp64_split", choices=["fp64", "fp64_split", "fp64_split5", "fp64_split7", "fast"])
     ap.add_argument("--gaussianize", default="standard")
-    ap.add_argument("--algorithm", default="stream", choices=["stream", "gram", "auto"],
-                    help="stream: every pass pair reads X~ (the north star's formulation); gram: X~^T X~ / N formed once")
+    ap.add_argument("--algorithm", default=None, choices=["stream", "gram", "auto"],
+                    help="stream: every pass pair reads X~ (the north star's formulation); gram: X~^T X~ / N formed once.  "
+                         "Default: `value` / `roofline` / `target` time the streaming route, `gram` sub-records time the Gram "
+                         "route, and `e2e` is the all-defaults public call (algorithm='auto')")
     ap.add_argument("--rows", type=int, default=0)
     ap.add_argument("--vars", type=int, default=0)
     ap.add_argument("--factors", type=int, default=0)

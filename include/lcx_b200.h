@@ -220,6 +220,12 @@ int lcx_trial_ns(lcx_session* s, double eps, double eta, int exact, double* tc, 
 /* direction + first (linear) trial at `eta` enqueued back to back with ONE host synchronisation; the trial is
  * speculative -- discard it when tangent >= 0 (:306-311) */
 int lcx_direction_trial_ns(lcx_session* s, double eps, double eta, double* tangent, double* tc, double* max_uj);
+/* Up to max_iter iterations of one annealing stage -- the loop body of fit (:137-151) including _update_ns's backtracking
+ * (:312-334) -- without returning to the caller between iterations.  Outputs per iteration i < *n_done: tc[i], tangent[i],
+ * eta[i] (accepted step; 0 when tangent >= 0, :306-311), trials[i], quick_fails[i].  *stop_reason: 0 = max_iter done,
+ * 1 = |delta TC| < tol (:152), 2 = the update yielded invalid moments (:144-149; iteration *n_done - 1, not applied). */
+int lcx_run_stage_ns(lcx_session* s, double eps, double tol, int exact_trials, int max_iter, double tc_start, int* n_done,
+                     int* stop_reason, double* tc, double* tangent, double* eta, int* trials, int* quick_fails);
 int lcx_accept_trial(lcx_session* s);                                            /* set 0 <-> set 1 (:333-334)   */
 /* _calculate_moments_syn (:336-373) for set 0; host output TC */
 int lcx_moments_syn(lcx_session* s, double* tc, double* additivity);

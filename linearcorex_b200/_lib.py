@@ -72,6 +72,8 @@ SIGNATURES = {
     "lcx_direction_ns": (_i, [_p, _d, _pd]),
     "lcx_trial_ns": (_i, [_p, _d, _d, _i, _pd, _pd]),
     "lcx_direction_trial_ns": (_i, [_p, _d, _d, _pd, _pd, _pd]),
+    "lcx_run_stage_ns": (_i, [_p, _d, _d, _i, _i, _d, C.POINTER(C.c_int), C.POINTER(C.c_int), _pd, _pd, _pd,
+                                C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "lcx_accept_trial": (_i, [_p]),
     "lcx_moments_syn": (_i, [_p, _pd, _pd]),
     "lcx_update_syn": (_i, [_p, _d, _pd, _pd]),

@@ -446,6 +446,11 @@ class Corex(object):
         schedule = self._prepare(x)
         for i_eps, eps in enumerate(schedule):
             self._begin_stage(eps, rescale=i_eps > 0)
+            if self.discourage_overlap and not self.verbose:
+                if not self._run_stage_native():
+                    self.ws = self._get_w()
+                    return self
+                continue
             delta = 0.0
             for i_loop in range(self.max_iter):
                 ok, delta = self._iterate()
@@ -461,6 +466,49 @@ class Corex(object):
                     print("Warning: Convergence not achieved in {:d} iterations. Final delta: {:f}".format(
                         self.max_iter, float(delta)))
         return self._finish()
+
+    STAGE_CHUNK = 1024
+
+    def _run_stage_native(self):
+        """The iterations of one annealing stage inside the library (lcx_run_stage_ns: same control flow as `_iterate` +
+        `_update_ns`, no interpreter between iterations).  Returns False where the reference returns early (:144-149)."""
+        sess = self._sess
+        lib = sess.lib
+        left = int(self.max_iter)
+        cap = max(1, min(self.STAGE_CHUNK, left))
+        tc, tang, eta = ((C.c_double * cap)() for _ in range(3))
+        trials, qf = ((C.c_int * cap)() for _ in range(2))
+        n_done, reason = C.c_int(), C.c_int()
+        hist = self.history.setdefault("TC", [])
+        while left > 0:
+            chunk = min(cap, left)
+            _lib.check(lib.lcx_run_stage_ns(sess.h, float(self.eps), float(self.tol), int(self.exact_trials), chunk,
+                                            float(self.tc), C.byref(n_done), C.byref(reason), tc, tang, eta, trials, qf),
+                       "lcx_run_stage_ns")
+            k = n_done.value
+            invalid = reason.value == 2
+            for i in range(k):
+                if tang[i] >= 0:  # :306-311
+                    print('Warning: covariance is nearly singular and this causes a loss of numerical precision.'
+                          'For this reason, we can no longer find an update that increases the objective. '
+                          'Hopefully this is a good solution. If not, this is caused by having many variables that are '
+                          'near duplicates. You could try again with the duplicates removed to look for other structure.')
+                if invalid and i == k - 1:
+                    break
+                if not np.isfinite(tc[i]):
+                    print("Error: TC is no longer finite: {}".format(tc[i]))
+                self.trace.append({"eps": self.eps, "tangent": tang[i], "eta": eta[i], "trials": trials[i],
+                                   "quick_fails": qf[i], "TC": tc[i]})
+                hist.append(tc[i])
+            if k > 0 and not (invalid and k == 1):
+                self.moments = {"TC": tc[k - 2] if invalid else tc[k - 1]}
+            if invalid:
+                print("Error... updates giving invalid solutions?")
+                return False
+            if reason.value == 1:
+                return True
+            left -= k
+        return True
 
     def _prepare(self, x):
         """Preprocess, bind the device problem and initialise W (:108-122).  Returns the anneal schedule."""
@@ -560,7 +608,9 @@ class Corex(object):
         sess.close()
         sess.ws = None
         self._sess = None
-        torch.cuda.empty_cache()
+        need = 8 * lib.lcx_gram_workspace_doubles(n, self.m, precision)
+        if need > 0.5 * torch.cuda.mem_get_info(g.device)[0]:  # hand the digit planes of X~ back before the next allocation
+            torch.cuda.empty_cache()
         gs = _DeviceSession(precision, device)
         gs.bind_gram(g, n, self.m)
         gs.launches_before = launches

@@ -218,11 +218,13 @@ __global__ void direction_stage1_kernel(const double* __restrict__ W, const doub
 
 // update = -rj (G - 2 W/(2-rj) Bj) (:303);  sigG = c1 D_G + e2 G (:212);  tangent = sum sigG*update (:305).
 // Rdir = -rj (sigG - 2 rho/(2-rj) Bj) = _sig(update): rho(W + eta U) = rho + eta Rdir by linearity.
-// part[blockIdx.y * gridDim.x + blockIdx.x] = partial tangent.
+// part[blockIdx.y * gridDim.x + blockIdx.x] = partial tangent.  DG may be given as dg_splits split-K partials (dg_stride apart),
+// summed here in index order -- the Gram route's product hands its partials over without a combine pass.
 __global__ void __launch_bounds__(256) direction_stage2_kernel(
     const double* __restrict__ W, const double* __restrict__ rho, const double* __restrict__ G,
     const double* __restrict__ DG, const double* __restrict__ uj, const double* __restrict__ Bj, double c1, double e2,
-    double* __restrict__ U, double* __restrict__ Rdir, double* __restrict__ part, int m, int n, long long ld) {
+    double* __restrict__ U, double* __restrict__ Rdir, double* __restrict__ part, int m, int n, long long ld,
+    int dg_splits = 1, long long dg_stride = 0) {
     __shared__ double scratch[8];
     const int i = blockIdx.x * 256 + threadIdx.x;
     const int j = blockIdx.y;
@@ -232,7 +234,9 @@ __global__ void __launch_bounds__(256) direction_stage2_kernel(
         const double rj = 1.0 - uj[j];
         const double bj = Bj[j];
         const double gval = G[o];
-        const double sg = c1 * DG[o] + e2 * gval;
+        double dg = DG[o];
+        for (int z = 1; z < dg_splits; ++z) dg += DG[(long long)z * dg_stride + o];  // split-K partials, fixed order
+        const double sg = c1 * dg + e2 * gval;
         const double u = -rj * (gval - 2.0 * W[o] / (2.0 - rj) * bj);
         U[o] = u;
         Rdir[o] = -rj * (sg - 2.0 * rho[o] / (2.0 - rj) * bj);

@@ -79,16 +79,17 @@ static int gram_build(lcx_session* s, double* g, long long ldg, int B, double* s
     return fail(LCX_ERR_STATE, "gram_build", "bad digit count");
 }
 
+// dot_b / dot_out: dot_out_j = sum_i A_ji dot_b_ji rides on the row-maximum pass over A.  leave_partials: with a split product
+// the m x ld partials stay in I_PART (s->d_splits of them) for a consumer that adds them itself.
 // D = (G A^T)^T (m x ld, factor-major) and optionally svec_j = sum_i A_ji D_ji = a_j^T G a_j (the column sums of squares of
 // Y = X~ A^T divided by N).  ev (optional): [0] recorded by the caller; [1]/[3]/[4]/[2] after the product.
 template <int S>
-static int gram_pair_t(lcx_session* s, const double* A, double* svec, cudaEvent_t* ev) {
+static int gram_pair_t(lcx_session* s, const double* A, double* svec, cudaEvent_t* ev, const double* dot_b, double* dot_out,
+                       bool leave_partials) {
     const Layout& L = s->L;
     const int m = s->m, n = s->n;
     double* D = s->ptr(LCX_A_D);
-    oz::row_scale_kernel<<<m, 256, 0, s->stream>>>(A, L.ld, n, s->oz_ascale());
-    LAUNCHED(s);
-    oz::mul_scale_kernel<<<cdiv(m, 128), 128, 0, s->stream>>>(s->oz_xscale(), s->oz_ascale(), s->oz_cscale(), m);
+    oz::row_scale_kernel<<<m, 256, 0, s->stream>>>(A, L.ld, n, s->oz_ascale(), 0, s->oz_xscale(), s->oz_cscale(), dot_b, dot_out);
     LAUNCHED(s);
     oz::slice_rows_kernel<S><<<dim3(m, cdiv(L.ld8, 4 * 128)), 128, 0, s->stream>>>(A, L.ld, m, n, s->oz_ascale(), nullptr, s->as(), L.ld8,
                                                                               (long long)m * L.ld8, (double)L.radix);
@@ -96,6 +97,7 @@ static int gram_pair_t(lcx_session* s, const double* A, double* svec, cudaEvent_
     oz::GemmParams p;
     memset(&p, 0, sizeof(p));
     const bool split = L.oz1_splits > 1;
+    s->d_splits = 1;
     p.C = split ? s->ptr(I_PART) : D;
     p.ldc = L.ld;
     p.c_split_stride = split ? (long long)m * L.ld : 0;
@@ -110,7 +112,9 @@ static int gram_pair_t(lcx_session* s, const double* A, double* svec, cudaEvent_
     if (ev) LCX_CUDA(cudaEventRecord(ev[1], s->stream));
     if (ev) LCX_CUDA(cudaEventRecord(ev[3], s->stream));
     if (ev) LCX_CUDA(cudaEventRecord(ev[4], s->stream));
-    if (split) {
+    if (split && leave_partials && svec == nullptr) {
+        s->d_splits = L.oz1_splits;  // the consumer (direction_stage2) adds the partials itself, in index order
+    } else if (split) {
         LCX_TRY(launch_reduce_splits(s->ptr(I_PART), L.oz1_splits, (long long)m * L.ld, D, m, n, L.ld, s->stream));
         LAUNCHED(s);
     }
@@ -122,13 +126,14 @@ static int gram_pair_t(lcx_session* s, const double* A, double* svec, cudaEvent_
     return 0;
 }
 
-static int gram_pair(lcx_session* s, const double* A, double* svec, cudaEvent_t* ev) {
+static int gram_pair(lcx_session* s, const double* A, double* svec, cudaEvent_t* ev, const double* dot_b = nullptr,
+                     double* dot_out = nullptr, bool leave_partials = false) {
     switch (s->L.S) {
-        case 3: return gram_pair_t<3>(s, A, svec, ev);
-        case 4: return gram_pair_t<4>(s, A, svec, ev);
-        case 5: return gram_pair_t<5>(s, A, svec, ev);
-        case 6: return gram_pair_t<6>(s, A, svec, ev);
-        case 7: return gram_pair_t<7>(s, A, svec, ev);
+        case 3: return gram_pair_t<3>(s, A, svec, ev, dot_b, dot_out, leave_partials);
+        case 4: return gram_pair_t<4>(s, A, svec, ev, dot_b, dot_out, leave_partials);
+        case 5: return gram_pair_t<5>(s, A, svec, ev, dot_b, dot_out, leave_partials);
+        case 6: return gram_pair_t<6>(s, A, svec, ev, dot_b, dot_out, leave_partials);
+        case 7: return gram_pair_t<7>(s, A, svec, ev, dot_b, dot_out, leave_partials);
     }
     return fail(LCX_ERR_STATE, "gram_pair", "bad digit count");
 }

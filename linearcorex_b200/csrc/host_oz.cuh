@@ -63,15 +63,14 @@ static int oz_cluster() {  // LCX_OZ_CLUSTER=1|2|4 overrides the cluster size of
 }
 
 template <int S>
-static int oz_pair_t(lcx_session* s, const double* A, double* svec, cudaEvent_t* ev, bool first_only, bool want_tail) {
+static int oz_pair_t(lcx_session* s, const double* A, double* svec, cudaEvent_t* ev, bool first_only, bool want_tail,
+                     const double* dot_b, double* dot_out) {
     const Layout& L = s->L;
     const int m = s->m, n = s->n;
     double* Y = s->ptr(LCX_A_Y);
     double* D = s->ptr(LCX_A_D);
     // ---- Y = X~ A^T ----
-    oz::row_scale_kernel<<<m, 256, 0, s->stream>>>(A, L.ld, n, s->oz_ascale());
-    LAUNCHED(s);
-    oz::mul_scale_kernel<<<cdiv(m, 128), 128, 0, s->stream>>>(s->oz_xscale(), s->oz_ascale(), s->oz_cscale(), m);
+    oz::row_scale_kernel<<<m, 256, 0, s->stream>>>(A, L.ld, n, s->oz_ascale(), 0, s->oz_xscale(), s->oz_cscale(), dot_b, dot_out);
     LAUNCHED(s);
     oz::slice_rows_kernel<S><<<dim3(m, cdiv(L.ld8, 4 * 128)), 128, 0, s->stream>>>(A, L.ld, m, n, s->oz_ascale(), nullptr, s->as(), L.ld8,
                                                                               (long long)m * L.ld8, (double)L.radix);
@@ -133,13 +132,14 @@ static int oz_pair_t(lcx_session* s, const double* A, double* svec, cudaEvent_t*
     return 0;
 }
 
-static int oz_pair(lcx_session* s, const double* A, double* svec, cudaEvent_t* ev, bool first_only, bool want_tail) {
+static int oz_pair(lcx_session* s, const double* A, double* svec, cudaEvent_t* ev, bool first_only, bool want_tail,
+                   const double* dot_b = nullptr, double* dot_out = nullptr) {
     switch (s->L.S) {
-        case 3: return oz_pair_t<3>(s, A, svec, ev, first_only, want_tail);
-        case 4: return oz_pair_t<4>(s, A, svec, ev, first_only, want_tail);
-        case 5: return oz_pair_t<5>(s, A, svec, ev, first_only, want_tail);
-        case 6: return oz_pair_t<6>(s, A, svec, ev, first_only, want_tail);
-        case 7: return oz_pair_t<7>(s, A, svec, ev, first_only, want_tail);
+        case 3: return oz_pair_t<3>(s, A, svec, ev, first_only, want_tail, dot_b, dot_out);
+        case 4: return oz_pair_t<4>(s, A, svec, ev, first_only, want_tail, dot_b, dot_out);
+        case 5: return oz_pair_t<5>(s, A, svec, ev, first_only, want_tail, dot_b, dot_out);
+        case 6: return oz_pair_t<6>(s, A, svec, ev, first_only, want_tail, dot_b, dot_out);
+        case 7: return oz_pair_t<7>(s, A, svec, ev, first_only, want_tail, dot_b, dot_out);
     }
     return fail(LCX_ERR_STATE, "oz_pair", "bad digit count");
 }

@@ -304,6 +304,7 @@ struct lcx_session {
     const double* xt;
     bool gram;        // the bound matrix is X~^T X~ / N (lcx_bind_gram): a "pass pair" is ONE product G A^T (host_gram.cuh)
     long long Nl, Nt, ldx;
+    int d_splits;     // > 1: the last Gram product left its split-K partials in I_PART for the consumer to add (host_gram.cuh)
     int n, m;
     double* ws;
     Layout L;

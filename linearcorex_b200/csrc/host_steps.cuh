@@ -99,7 +99,10 @@ static int run_square_gemm(lcx_session* s, GemmArgs a, double diag_value, double
 }
 
 // Y = X~ A^T (+ colsq into D's tail), D = X~^T Y summed over splits, then the rank all-reduce.
-static int xpair(lcx_session* s, const double* A, bool want_colsq) {
+// dot_b / dot_out (optional): dot_out_j = sum_i A_ji dot_b_ji, taken in the first pass over A where the route has one (split
+// modes), by a row_dot launch otherwise.  leave_partials: the Gram route may hand D over as split-K partials (s->d_splits).
+static int xpair(lcx_session* s, const double* A, bool want_colsq, const double* dot_b = nullptr, double* dot_out = nullptr,
+                 bool leave_partials = false) {
     const Layout& L = s->L;
     const int m = s->m, n = s->n;
     double* Y = s->ptr(LCX_A_Y);
@@ -109,18 +112,22 @@ static int xpair(lcx_session* s, const double* A, bool want_colsq) {
     if (s->prof_on && s->prof_pending < s->prof_cap) ev = s->prof_ev + kProfEv * s->prof_pending;
     if (ev) LCX_CUDA(cudaEventRecord(ev[0], s->stream));
     if (s->gram) {  // one product with the n x n Gram matrix instead of the two passes over X~ (host_gram.cuh)
-        LCX_TRY(gram_pair(s, A, want_colsq ? svec : nullptr, ev));
+        LCX_TRY(gram_pair(s, A, want_colsq ? svec : nullptr, ev, dot_b, dot_out, leave_partials));
         if (ev) {
             LCX_CUDA(cudaEventRecord(ev[2], s->stream));
             s->prof_pending++;
         }
     } else if (L.S > 0) {
-        LCX_TRY(oz_pair(s, A, svec, ev, false, want_colsq));
+        LCX_TRY(oz_pair(s, A, svec, ev, false, want_colsq, dot_b, dot_out));
         if (ev) {
             LCX_CUDA(cudaEventRecord(ev[2], s->stream));
             s->prof_pending++;
         }
     } else {
+    if (dot_out) {
+        row_dot_kernel<<<m, 256, 0, s->stream>>>(A, dot_b, dot_out, n, L.ld);
+        LAUNCHED(s);
+    }
     {   // K1
         GemmArgs a;
         memset(&a, 0, sizeof(a));
@@ -266,12 +273,14 @@ static int enqueue_direction(lcx_session* s, double eps) {
         LCX_TRY(run_gemm(s, kLayoutKN, L.plan_mn, a, nullptr, 0));
     }
     }
-    LCX_TRY(xpair(s, G, false));  // X~^T (X~ grad^T): the one pass over X of this iteration (:301)
-    row_dot_kernel<<<m, 256, 0, s->stream>>>(rho, G, s->ptr(I_BJ), n, L.ld);  // Bj (:302)
-    LAUNCHED(s);
+    // X~^T (X~ grad^T): the one pass over X of this iteration (:301); Bj = sum_i rho grad (:302) rides on its first pass over grad
+    s->d_splits = 1;
+    LCX_TRY(xpair(s, G, false, rho, s->ptr(I_BJ), true));
     const dim3 g2(cdiv(n, 256), m);
-    direction_stage2_kernel<<<g2, 256, 0, s->stream>>>(W, rho, G, s->ptr(LCX_A_D), s->ptr(LCX_A_UJ), s->ptr(I_BJ), c1, e2,
-                                                     s->ptr(LCX_A_UPDATE), s->ptr(LCX_A_RDIR), s->ptr(I_SPART), m, n, L.ld);
+    const bool parts = s->d_splits > 1;
+    direction_stage2_kernel<<<g2, 256, 0, s->stream>>>(W, rho, G, parts ? s->ptr(I_PART) : s->ptr(LCX_A_D), s->ptr(LCX_A_UJ),
+                                                     s->ptr(I_BJ), c1, e2, s->ptr(LCX_A_UPDATE), s->ptr(LCX_A_RDIR),
+                                                     s->ptr(I_SPART), m, n, L.ld, s->d_splits, (long long)m * L.ld);
     LAUNCHED(s);
     sum_partials_kernel<<<1, 256, 0, s->stream>>>(s->ptr(I_SPART), (int)(g2.x * g2.y), s->ptr(LCX_A_SCALARS) + 2);
     LAUNCHED(s);

@@ -573,6 +573,84 @@ extern "C" int lcx_direction_trial_ns(lcx_session* s, double eps, double eta, do
     return (s->mailbox[1] >= 1.0) ? LCX_QUICK_FAIL : LCX_OK;
 }
 
+// The loop body of fit (:137-151) with _update_ns's backtracking (:290-334) for up to max_iter iterations of ONE annealing
+// stage, entirely on this side of the ABI: between two iterations the GPU waits only for the mailbox read and a few
+// branches, not for an interpreter.  Per iteration i < *n_done: tc[i] (the objective after it), tangent[i], eta[i] (accepted
+// step, 0 if none), trials[i], quick_fails[i].  *stop_reason: 0 = max_iter iterations done, 1 = |delta TC| < tol (:152),
+// 2 = the update produced invalid moments (the reference prints an error and returns, :144-149; iteration *n_done - 1 is
+// the failing one and was not applied).  tc_start = TC of the current moments (the caller holds it).
+extern "C" int lcx_run_stage_ns(lcx_session* s, double eps, double tol, int exact_trials, int max_iter, double tc_start,
+                                int* n_done, int* stop_reason, double* tc, double* tangent, double* eta, int* trials,
+                                int* quick_fails) {
+    S_REQUIRE_BOUND(s);
+    LCX_REQUIRE(n_done && stop_reason && tc && tangent && eta && trials && quick_fails && max_iter >= 0, "bad argument");
+    double tc_cur = tc_start;
+    *n_done = 0;
+    *stop_reason = 0;
+    const double eta_min = tol < 1e-10 ? tol : 1e-10;
+    for (int it = 0; it < max_iter; ++it) {
+        const double last_tc = tc_cur;
+        bool have_first = false;
+        if (exact_trials) {
+            LCX_TRY(enqueue_direction(s, eps));
+        } else {  // direction and the eta = 1 trial share one host synchronisation (discarded if tangent >= 0)
+            LCX_TRY(enqueue_direction(s, eps));
+            LCX_TRY(enqueue_trial(s, eps, 1.0, 0));
+            have_first = true;
+        }
+        LCX_TRY(read_mailbox(s));
+        const double tang = s->mailbox[2];
+        tangent[it] = tang;
+        eta[it] = 0.0;
+        trials[it] = 0;
+        quick_fails[it] = 0;
+        *n_done = it + 1;
+        if (!(tang >= 0)) {  // (:306-311 returns the unchanged moments when tangent >= 0)
+            double e = 1.0;
+            int last_fail = -1;  // -1: no trial ran, 1: the last trial hit max uj >= 1, 0: it produced moments
+            double tc_trial = 0.0;
+            while (true) {
+                if (e < eta_min) break;  // :316-319
+                if (have_first) {
+                    have_first = false;
+                } else {
+                    LCX_TRY(enqueue_trial(s, eps, e, exact_trials));
+                    LCX_TRY(read_mailbox(s));
+                }
+                tc_trial = s->mailbox[0];
+                trials[it]++;
+                if (s->mailbox[1] >= 1.0) {  // TEST 1 (:322-326)
+                    last_fail = 1;
+                    quick_fails[it]++;
+                    e *= 0.5;
+                    continue;
+                }
+                last_fail = 0;
+                if (!(-tc_trial <= -tc_cur + 0.1 * e * tang)) {  // TEST 2, first Wolfe condition (:327-332)
+                    e *= 0.5;
+                    continue;
+                }
+                break;
+            }
+            eta[it] = e;
+            if (last_fail != 0) {
+                tc[it] = tc_cur;
+                *stop_reason = 2;
+                return 0;
+            }
+            s->cur ^= 1;  // accept (:333-334)
+            tc_cur = tc_trial;
+        }
+        tc[it] = tc_cur;
+        const double delta = fabs(tc_cur - last_tc);
+        if (delta < tol) {
+            *stop_reason = 1;
+            return 0;
+        }
+    }
+    return 0;
+}
+
 extern "C" int lcx_accept_trial(lcx_session* s) {
     S_REQUIRE_BOUND(s);
     s->cur ^= 1;

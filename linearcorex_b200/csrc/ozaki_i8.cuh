@@ -559,14 +559,23 @@ __global__ void __launch_bounds__(256) slice_cols_t_kernel(const double* __restr
 
 // max |a[r][c]| over a row (one CTA of 256 threads per row) -> scale[r] = 2^E;  used for A (W or grad).
 // skip_diag: leave a[r][r] out of the maximum (square matrices sliced with ZERO_DIAG).
+// x_scale / out_scale (optional): out_scale[r] = x_scale[0] * scale[r], the output scale of Y = X~ A^T.
+// dot_b / dot_out (optional): dot_out[r] = sum_c a[r][c] * dot_b[r][c] in the same pass (Bj of the search direction,
+// linearcorex.py:302, rides on the pass that finds the exponent of grad's row).
 __global__ void row_scale_kernel(const double* __restrict__ a, long long ld, int cols, double* __restrict__ scale,
-                                 int skip_diag = 0) {
+                                 int skip_diag = 0, const double* __restrict__ x_scale = nullptr,
+                                 double* __restrict__ out_scale = nullptr, const double* __restrict__ dot_b = nullptr,
+                                 double* __restrict__ dot_out = nullptr) {
     __shared__ double scratch[8];
     const double* ra = a + (long long)blockIdx.x * ld;
-    double mx = 0.0;
-    if (skip_diag || ((uintptr_t)ra & 15) != 0) {
-        for (int i = threadIdx.x; i < cols; i += 256)
-            if (!(skip_diag && i == (int)blockIdx.x)) mx = lcx::amax_acc(mx, ra[i]);
+    const double* rb = dot_b ? dot_b + (long long)blockIdx.x * ld : nullptr;
+    double mx = 0.0, dot = 0.0;
+    if (skip_diag || rb != nullptr || ((uintptr_t)ra & 15) != 0) {
+        for (int i = threadIdx.x; i < cols; i += 256) {
+            const double v = ra[i];
+            if (!(skip_diag && i == (int)blockIdx.x)) mx = lcx::amax_acc(mx, v);
+            if (rb) dot += v * rb[i];
+        }
     } else {  // 16-byte loads, eight values in flight per thread (a row of W is 400 KB at n = 50 000)
         const double2* ra2 = reinterpret_cast<const double2*>(ra);
         const int pairs = cols >> 1;
@@ -587,7 +596,13 @@ __global__ void row_scale_kernel(const double* __restrict__ a, long long ld, int
         mx = fmax(fmax(mx, m1), fmax(m2, m3));
     }
     mx = block_max_256(mx, scratch);
-    if (threadIdx.x == 0) scale[blockIdx.x] = pow2_above(mx);
+    if (rb) dot = block_sum_256(dot, scratch);
+    if (threadIdx.x == 0) {
+        const double sc = pow2_above(mx);
+        scale[blockIdx.x] = sc;
+        if (out_scale != nullptr) out_scale[blockIdx.x] = x_scale[0] * sc;
+        if (rb) dot_out[blockIdx.x] = dot;
+    }
 }
 
 // ---- per-COLUMN scales (the m x m x n products on the int8 engine: an operand contracted over its rows needs an
