@@ -25,13 +25,16 @@ def _worker(rank, world, port, ret, peer_mode):
         from conftest import load_golden
         from linearcorex_b200 import Corex, shard_rows
         out = {}
-        for name, prec in (("syn_400x300x10_f64", "fp64"), ("standard_missing_f64", "fp64"), ("syn_400x300x10_f64", "fp64_split")):
+        for name, prec, algo in (("syn_400x300x10_f64", "fp64", "stream"), ("standard_missing_f64", "fp64", "stream"),
+                                 ("syn_400x300x10_f64", "fp64_split", "stream"), ("syn_400x300x10_f64", "fp64_split", "gram"),
+                                 ("standard_missing_f64", "fp64_split", "gram")):
             z, kw, x = load_golden(name)
-            kw = dict(kw, precision=prec)
+            kw = dict(kw, precision=prec, algorithm=algo)
             lo, hi = shard_rows(x.shape[0], rank, world)
             mdl = Corex(comm=True, **kw).fit(x[lo:hi])
-            assert mdl.n_samples == x.shape[0]
-            assert (mdl._sess._peer_buf is not None) == (peer_mode == "require")
+            assert mdl.n_samples == x.shape[0] and mdl.algorithm_used == algo
+            # Gram route: the ranks' partial X~^T X~ / N are summed once (NCCL); the loop itself exchanges nothing
+            assert (mdl._sess._peer_buf is not None) == (peer_mode == "require" and algo == "stream")
             assert len(mdl.history["TC"]) == len(z["history_TC"])
             err = np.abs(mdl.ws - z["ws"]).max() / np.abs(z["ws"]).max()
             err_tc = np.abs(mdl.moments["TCs"] - z["m_TCs"]).max() / np.abs(z["m_TCs"]).max()
@@ -45,7 +48,7 @@ def _worker(rank, world, port, ret, peer_mode):
             dist.all_reduce(lo_t, op=dist.ReduceOp.MIN)
             dist.all_reduce(hi_t, op=dist.ReduceOp.MAX)
             assert torch.equal(lo_t, hi_t)
-            out[name] = float(err)
+            out[name + "/" + prec + "/" + algo] = float(err)
         ret[rank] = "ok %r" % (out,)
     except Exception as exc:
         import traceback

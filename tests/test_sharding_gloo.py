@@ -69,6 +69,17 @@ def _worker(rank, world, port, ret):
         np.testing.assert_allclose(rho, want["rho"], rtol=1e-11, atol=1e-13)
         uj = (1 - eps ** 2) * s_all / N + eps ** 2 * (w ** 2).sum(1)
         np.testing.assert_allclose(uj, want["uj"], rtol=1e-12)
+        # --- the Gram route's one-off exchange: per-shard X~^T X~ / N summed over ranks; afterwards every rank evaluates
+        #     _sig (linearcorex.py:196-213) and sum Y^2 / N from the same matrix with no further exchange ----------------
+        g = torch.from_numpy(xt.T.dot(xt) / N)
+        red.sum_(g)
+        g = g.numpy()
+        np.testing.assert_allclose(g, xt_full.T.dot(xt_full) / N, rtol=1e-11, atol=1e-13)
+        d_gram = g.dot(w.T).T
+        np.testing.assert_allclose(d_gram, d_all / N, rtol=1e-10, atol=1e-13)
+        np.testing.assert_allclose((w * d_gram).sum(1), s_all / N, rtol=1e-10)
+        # collective decisions (streamed preparation, Gram route) are taken with max / min over the ranks
+        assert red.max_scalar(rank) == world - 1 and red.min_scalar(rank + 1) == 1
         ret[rank] = "ok"
     except Exception as exc:  # surface the failure in the parent
         ret[rank] = "FAIL: %r" % (exc,)
@@ -90,4 +101,4 @@ def test_reducer_identity_single_rank():
     from linearcorex_b200 import Reducer
     r = Reducer(None)
     t = torch.arange(4, dtype=torch.float64)
-    assert r.world == 1 and r.sum_(t) is t and r.sum_scalar(5) == 5
+    assert r.world == 1 and r.sum_(t) is t and r.sum_scalar(5) == 5 and r.min_scalar(3) == 3 and r.max_scalar(3) == 3

@@ -43,13 +43,37 @@ def main():
     lib.lcx_profile_enable(sess.h, 1)
     k1, k2, kx, pairs = C.c_double(), C.c_double(), C.c_double(), C.c_longlong()
     lib.lcx_profile_read_phases(sess.h, C.byref(k1), C.byref(k2), C.byref(kx), C.byref(pairs), 1)
+    # SM clock and board power while the pairs run (NVML, sampled every 20 ms from a thread): tells a kernel held back by the
+    # power cap (clock far below the 1965 MHz maximum at ~1 kW) from one that stalls at full clock
+    import threading
+    import time
+    samples, stop = [], threading.Event()
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        hnd = pynvml.nvmlDeviceGetHandleByIndex(torch.cuda.current_device())
+
+        def poll():
+            while not stop.is_set():
+                samples.append((pynvml.nvmlDeviceGetClockInfo(hnd, pynvml.NVML_CLOCK_SM), pynvml.nvmlDeviceGetPowerUsage(hnd) / 1e3))
+                time.sleep(0.02)
+        th = threading.Thread(target=poll, daemon=True)
+        th.start()
+    except Exception:
+        th = None
     for _ in range(reps):
         _lib.check(lib.lcx_sig(sess.h, w.data_ptr(), 0.0, out_arr.data_ptr()))
     lib.lcx_profile_read_phases(sess.h, C.byref(k1), C.byref(k2), C.byref(kx), C.byref(pairs), 1)
+    stop.set()
+    if th is not None:
+        th.join()
     p = max(1, pairs.value)
     knobs = {k: v for k, v in os.environ.items() if k.startswith("LCX_")}
     print(json.dumps({"shape": [N, n, m], "precision": prec, "knobs": knobs, "k1_ms": round(k1.value / p, 4),
-                      "k2_ms": round(k2.value / p, 4), "combine_ms": round(kx.value / p, 4), "pairs": p}))
+                      "k2_ms": round(k2.value / p, 4), "combine_ms": round(kx.value / p, 4), "pairs": p,
+                      "sm_mhz_median": sorted(c for c, _ in samples[len(samples) // 3:])[len(samples[len(samples) // 3:]) // 2] if samples else None,
+                      "power_w_median": sorted(w_ for _, w_ in samples[len(samples) // 3:])[len(samples[len(samples) // 3:]) // 2] if samples else None,
+                      "nvml_samples": len(samples)}))
 
 
 if __name__ == "__main__":
