@@ -224,8 +224,9 @@ __global__ void __launch_bounds__(256) direction_stage2_kernel(
     const double* __restrict__ W, const double* __restrict__ rho, const double* __restrict__ G,
     const double* __restrict__ DG, const double* __restrict__ uj, const double* __restrict__ Bj, double c1, double e2,
     double* __restrict__ U, double* __restrict__ Rdir, double* __restrict__ part, int m, int n, long long ld,
-    int dg_splits = 1, long long dg_stride = 0) {
+    int dg_splits = 1, long long dg_stride = 0, unsigned* __restrict__ ticket = nullptr, double* __restrict__ out = nullptr) {
     __shared__ double scratch[8];
+    __shared__ int is_last;
     const int i = blockIdx.x * 256 + threadIdx.x;
     const int j = blockIdx.y;
     double tang = 0.0;
@@ -244,6 +245,24 @@ __global__ void __launch_bounds__(256) direction_stage2_kernel(
     }
     tang = block_sum_256(tang, scratch);
     if (threadIdx.x == 0) part[(long long)blockIdx.y * gridDim.x + blockIdx.x] = tang;
+    if (ticket == nullptr) return;
+    // the last CTA to arrive adds all partials in index order (sum_partials_kernel's arithmetic, one launch less)
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned total = gridDim.x * gridDim.y;
+        is_last = (atomicAdd(ticket, 1u) == total - 1) ? 1 : 0;
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    const int nparts = (int)(gridDim.x * gridDim.y);
+    double s = 0.0;
+    for (int b = threadIdx.x; b < nparts; b += 256) s += __ldcg(&part[b]);
+    s = block_sum_256(s, scratch);
+    if (threadIdx.x == 0) {
+        out[0] = s;
+        *ticket = 0u;
+    }
 }
 
 // out[0] = sum of partials (fixed order).  Single CTA.

@@ -70,11 +70,18 @@ static int oz_pair_t(lcx_session* s, const double* A, double* svec, cudaEvent_t*
     double* Y = s->ptr(LCX_A_Y);
     double* D = s->ptr(LCX_A_D);
     // ---- Y = X~ A^T ----
+    if (s->row_parts > 0 && dot_out != nullptr) {  // grad from the fused kernel: row maxima and partial Bj are in I_FROW
+        oz::slice_rows_part_kernel<S><<<dim3(m, cdiv(L.ld8, 4 * 128)), 128, 0, s->stream>>>(
+            A, L.ld, m, n, s->ptr(I_FROW), s->ptr(I_FROW) + (long long)kSMs * L.ldm, s->row_parts, L.ldm, s->oz_xscale(),
+            s->oz_ascale(), s->oz_cscale(), dot_out, s->as(), L.ld8, (long long)m * L.ld8, (double)L.radix);
+        LAUNCHED(s);
+    } else {
     oz::row_scale_kernel<<<m, 256, 0, s->stream>>>(A, L.ld, n, s->oz_ascale(), 0, s->oz_xscale(), s->oz_cscale(), dot_b, dot_out);
     LAUNCHED(s);
     oz::slice_rows_kernel<S><<<dim3(m, cdiv(L.ld8, 4 * 128)), 128, 0, s->stream>>>(A, L.ld, m, n, s->oz_ascale(), nullptr, s->as(), L.ld8,
                                                                               (long long)m * L.ld8, (double)L.radix);
     LAUNCHED(s);
+    }
     {
         oz::GemmParams p;
         memset(&p, 0, sizeof(p));

@@ -10,6 +10,7 @@
 #include "corex_kernels.cuh"
 #include "dgemm_mma.cuh"
 #include "fused_allreduce.cuh"
+#include "fused_strip_kernels.cuh"
 #include "lu_solve.cuh"
 #include "ozaki_i8.cuh"
 #include "preprocess_kernels.cuh"
@@ -64,6 +65,9 @@ enum {
     I_MMC,              //              column-scaled digit slices of the operand contracted over its rows (factors)
     I_MMQ,              //              row-scaled digit slices of the m x m factor (ry or H)  [S][m][ldm8]
     I_MMV,              //              scales: col partial max (32 x ld) | col scale (ld) | row scales a, b, q (3 x ldm)
+    I_FPART,            // fused m x n phase (m <= 128, fused_strip_kernels.cuh): per-CTA partials of ry / H  [kSMs][m][ldm]
+    I_FROW,             //              per-CTA row maxima and partial Bj of grad  [2][kSMs][ldm]
+    I_TICKET,           //              arrival counters of the last-CTA reductions (self-resetting)
     I_COUNT
 };
 
@@ -90,6 +94,7 @@ struct Layout {
     long long ldm8;              // byte leading dimension of the digit slices of an m x m matrix
     int mm_splits, mm_chunk;     // split-K over the variables of the m x m outputs
     int mm_slabs, mm_slab_rows;  // row slabs of the per-column maximum
+    int fused;                   // m x n phase through fused_strip_kernels.cuh (m <= 128)
 };
 
 static int radix_for() {
@@ -114,6 +119,17 @@ static int mm_i8_for(int S, int n, int m) {
     const char* env = getenv("LCX_MM_I8");
     if (env) return atoi(env) != 0;
     return m >= 384 && n >= 2048;
+}
+// LCX_FUSED=1 routes the m x n phase of m <= 128 problems through fused_strip_kernels.cuh (9 launches instead of 15 per
+// iteration).  Off by default: measured on a B200 at config 3 the fused phase takes 0.26 ms against 0.23 ms for the separate
+// kernels -- with one 8-warp CTA per SM the strip kernels expose the L2 latency of their elementwise operands and DMMA.8x8x4
+// sustains only ~1 instruction per 8-9 clocks per SM in them (profiles/r02_fused_mxn_phase.md).  Kept, tested, as the
+// starting point for a version with two CTAs per SM.
+static int fused_for(int n, int m, int mm_i8) {
+    (void)n;
+    if (m > fs::kMaxM || mm_i8) return 0;
+    const char* env = getenv("LCX_FUSED");
+    return (env && atoi(env) == 1) ? 1 : 0;
 }
 constexpr int kYStatRows = 512;
 constexpr int kAmaxCtas = 592;
@@ -289,6 +305,12 @@ static Layout make_layout(long long Nl, int n, int m, int precision, bool gram =
             put1(I_MMV, 1, 33 * L.ld + 3 * L.ldm, 33 * L.ld + 3 * L.ldm);
         }
     }
+    L.fused = fused_for(n, m, L.mm_i8);
+    if (L.fused) {
+        put1(I_FPART, 1, (long long)kSMs * mn * L.ldm, (long long)kSMs * mn * L.ldm);
+        put1(I_FROW, 1, 2LL * kSMs * L.ldm, 2LL * kSMs * L.ldm);
+    }
+    put1(I_TICKET, 1, 16, 16);
     L.total = cur;
     return L;
 }
@@ -304,6 +326,8 @@ struct lcx_session {
     const double* xt;
     bool gram;        // the bound matrix is X~^T X~ / N (lcx_bind_gram): a "pass pair" is ONE product G A^T (host_gram.cuh)
     long long Nl, Nt, ldx;
+    int tg_phys;      // physical moment set whose T / G0 (I_T, LCX_A_GRAD) the fused tail has already written, -1 = none
+    int row_parts;    // > 0: grad's row maxima / partial Bj wait in I_FROW as this many per-CTA partials (fused direction)
     int d_splits;     // > 1: the last Gram product left its split-K partials in I_PART for the consumer to add (host_gram.cuh)
     int n, m;
     double* ws;

@@ -172,6 +172,9 @@ static int bind_common(lcx_session* s, const double* xt, long long n_rows_local,
     s->ws = workspace;
     s->L = L;
     s->cur = 0;
+    s->tg_phys = -1;
+    s->row_parts = 0;
+    s->d_splits = 1;
     s->bound = true;
     s->peers.world = 0;  // a new problem starts single-rank until lcx_set_peer_allreduce is called for it
     // everything except Y starts at zero so padding never carries NaNs into an all-reduce
@@ -461,6 +464,7 @@ extern "C" int lcx_sig(lcx_session* s, const double* u, double eps, double* out)
 
 extern "C" int lcx_set_w(lcx_session* s, const double* host_w, long long host_ld) {
     S_REQUIRE_BOUND(s);
+    s->tg_phys = -1;  // (T / G0 of the fused moments tail no longer match the current set)
     LCX_REQUIRE(host_w && host_ld >= s->n, "bad host array");
     LCX_CUDA(cudaMemcpy2DAsync(s->ptr(LCX_A_W), s->L.ld * sizeof(double), host_w, host_ld * sizeof(double),
                                (size_t)s->n * sizeof(double), s->m, cudaMemcpyHostToDevice, s->stream));
@@ -479,6 +483,7 @@ extern "C" int lcx_get_w(lcx_session* s, double* host_w, long long host_ld) {
 
 extern "C" int lcx_init_scale(lcx_session* s, double eps) {
     S_REQUIRE_BOUND(s);
+    s->tg_phys = -1;  // (T / G0 of the fused moments tail no longer match the current set)
     const Layout& L = s->L;
     const int m = s->m, n = s->n;
     double* W = s->ptr(LCX_A_W);
@@ -505,6 +510,7 @@ extern "C" int lcx_init_scale(lcx_session* s, double eps) {
 
 extern "C" int lcx_stage_rescale(lcx_session* s, double eps, double eps_prev) {
     S_REQUIRE_BOUND(s);
+    s->tg_phys = -1;  // (T / G0 of the fused moments tail no longer match the current set)
     const Layout& L = s->L;
     const int m = s->m, n = s->n;
     double* W = s->ptr(LCX_A_W);
@@ -520,6 +526,7 @@ extern "C" int lcx_stage_rescale(lcx_session* s, double eps, double eps_prev) {
 
 extern "C" int lcx_permute_rows(lcx_session* s, const int* host_order) {
     S_REQUIRE_BOUND(s);
+    s->tg_phys = -1;  // (T / G0 of the fused moments tail no longer match the current set)
     LCX_REQUIRE(host_order != nullptr, "null order");
     const Layout& L = s->L;
     double* W = s->ptr(LCX_A_W);
@@ -678,6 +685,7 @@ extern "C" int lcx_details_ns(lcx_session* s, double* tc_no_overlap, double* add
 
 extern "C" int lcx_moments_syn(lcx_session* s, double* tc, double* additivity) {
     S_REQUIRE_BOUND(s);
+    s->tg_phys = -1;  // (T / G0 of the fused moments tail no longer match the current set)
     const Layout& L = s->L;
     const int m = s->m, n = s->n;
     double* W = s->ptr(LCX_A_W);
@@ -732,6 +740,7 @@ extern "C" int lcx_moments_syn(lcx_session* s, double* tc, double* additivity) {
 
 extern "C" int lcx_update_syn(lcx_session* s, double eta, double* tc, double* additivity) {
     S_REQUIRE_BOUND(s);
+    s->tg_phys = -1;  // (T / G0 of the fused moments tail no longer match the current set)
     const Layout& L = s->L;
     const int m = s->m, n = s->n;
     double* W = s->ptr(LCX_A_W);
@@ -783,6 +792,7 @@ static int covariance_rows(lcx_session* s, const double* left, const double* rig
 extern "C" int lcx_get_covariance(lcx_session* s, int synergy, double eps, const double* sd, int row0, int rows, double* out,
                                   long long ldc) {
     S_REQUIRE_BOUND(s);
+    s->tg_phys = -1;  // (T / G0 of the fused moments tail no longer match the current set)
     const Layout& L = s->L;
     const int m = s->m, n = s->n;
     LCX_REQUIRE(sd && out, "null argument");

@@ -519,6 +519,55 @@ __global__ void slice_rows_kernel(const double* __restrict__ in, long long ld_in
     }
 }
 
+// slice_rows_kernel for grad when its producer (fs::strip_apply_kernel, EPI 1) left per-CTA row maxima and partial dots:
+// the row's exponent comes from the nparts partial maxima, and the first block of each row also publishes the scales and
+// Bj = sum of the partial dots (fixed tree) -- no separate pass over grad for its maximum.
+template <int S>
+__global__ void __launch_bounds__(128) slice_rows_part_kernel(const double* __restrict__ in, long long ld_in, int rows, int cols,
+                                                              const double* __restrict__ pmax, const double* __restrict__ pdot,
+                                                              int nparts, long long ldp, const double* __restrict__ x_scale,
+                                                              double* __restrict__ a_scale, double* __restrict__ c_scale,
+                                                              double* __restrict__ bj, int8_t* __restrict__ out,
+                                                              long long ld_out, long long slice_stride, double radix) {
+    __shared__ double sh[4];
+    const long long r = blockIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double mx = 0.0;
+    for (int p = threadIdx.x; p < nparts; p += 128) mx = fmax(mx, pmax[(long long)p * ldp + r]);
+    mx = lcx::warp_max(mx);
+    if (lane == 0) sh[warp] = mx;
+    __syncthreads();
+    mx = fmax(fmax(sh[0], sh[1]), fmax(sh[2], sh[3]));
+    const double sc = pow2_above(mx);
+    if (blockIdx.y == 0 && warp == 0) {
+        double d = 0.0;
+        if (bj != nullptr) {
+            for (int p = lane; p < nparts; p += 32) d += pdot[(long long)p * ldp + r];
+            d = lcx::warp_sum(d);
+        }
+        if (lane == 0) {
+            a_scale[r] = sc;
+            c_scale[r] = x_scale[0] * sc;
+            if (bj != nullptr) bj[r] = d;
+        }
+    }
+    const int c4 = (blockIdx.y * blockDim.x + threadIdx.x) * 4;
+    if (r >= rows || c4 >= ld_out) return;
+    const double inv = 1.0 / sc;
+    int8_t d[4][S];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int c = c4 + j;
+        const double x = (c < cols) ? in[r * ld_in + c] : 0.0;
+        split_digits<S>(x, inv, radix, d[j]);
+    }
+#pragma unroll
+    for (int k = 0; k < S; ++k) {
+        char4 v = make_char4(d[0][k], d[1][k], d[2][k], d[3][k]);
+        *reinterpret_cast<char4*>(out + (long long)k * slice_stride + r * ld_out + c4) = v;
+    }
+}
+
 // Digit planes of Y (N x ldy, row-major fp64) with one scale per column (exponent per factor), written TRANSPOSED:
 // out[s][c][r], samples contiguous -- the K-major factor-side operand of the second contraction.  One CTA of 32 x 8
 // threads turns a 128-row x 32-column block of Y around through shared memory (coalesced 256 B reads of Y, 128 B
