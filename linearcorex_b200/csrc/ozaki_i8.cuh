@@ -90,6 +90,21 @@ __device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
                  "h"(mask)
                  : "memory");
 }
+// One lane of a converged warp (elect.sync).  The MMA warp runs its loop with all 32 lanes converged and lets the elected
+// lane issue: inside an `if (lane == 0)` region the compiler keeps the shared-memory descriptors in vector registers and
+// wraps every tcgen05.mma in an ELECT / 4 x R2UR.BROADCAST / BRA.U.ANY waterfall (~17 instructions per MMA); with
+// warp-uniform control flow they live in uniform registers and the instruction takes them directly.
+__device__ __forceinline__ bool elect_one_sync() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
@@ -293,8 +308,8 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     };
 
     if (warp == 0) {
-        // ===== TMA producer =====
-        if (lane == 0) {
+        // ===== TMA producer: the warp walks the loop converged, one elected lane issues (see elect_one_sync) =====
+        {
             uint32_t kbg = 0;  // K blocks issued so far by this CTA: stage and phase of the ring
             for (int u = cluster_id; u < units; u += n_clusters) {
                 int n_tile, m_tile, z, kbeg, num_kb;
@@ -306,32 +321,35 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                     uint8_t* sa = smem + st * STAGE_BYTES;
                     uint8_t* sb = sa + S * A_BYTES;
                     const bool load_a = !(p.debug & 2), load_b = !(p.debug & 4);
-                    mbar_expect_tx(&full_bar[st], S * ((load_a ? A_BYTES : 0) + (load_b ? b_bytes : 0)));
                     const int k0 = kbeg + kb * kBK;
+                    if (elect_one_sync()) {
+                        mbar_expect_tx(&full_bar[st], S * ((load_a ? A_BYTES : 0) + (load_b ? b_bytes : 0)));
 #pragma unroll
-                    for (int s = 0; s < S; ++s) {
-                        // shared operand: plane s is fetched by cluster rank s % CL and multicast to all CL CTAs
-                        if (!load_a) {
-                        } else if (CL == 1) {
-                            if (KMAJOR) tma_load_3d(sa + s * A_BYTES, &mapA, &full_bar[st], k0, m_tile * kBM, s);
-                            else tma_load_3d(sa + s * A_BYTES, &mapA, &full_bar[st], m_tile * kBM, k0, s);
-                        } else if ((uint32_t)(s % CL) == crank) {
-                            if (KMAJOR) tma_load_3d_mc(sa + s * A_BYTES, &mapA, &full_bar[st], k0, m_tile * kBM, s, kMask);
-                            else tma_load_3d_mc(sa + s * A_BYTES, &mapA, &full_bar[st], m_tile * kBM, k0, s, kMask);
+                        for (int s = 0; s < S; ++s) {
+                            // shared operand: plane s is fetched by cluster rank s % CL and multicast to all CL CTAs
+                            if (!load_a) {
+                            } else if (CL == 1) {
+                                if (KMAJOR) tma_load_3d(sa + s * A_BYTES, &mapA, &full_bar[st], k0, m_tile * kBM, s);
+                                else tma_load_3d(sa + s * A_BYTES, &mapA, &full_bar[st], m_tile * kBM, k0, s);
+                            } else if ((uint32_t)(s % CL) == crank) {
+                                if (KMAJOR) tma_load_3d_mc(sa + s * A_BYTES, &mapA, &full_bar[st], k0, m_tile * kBM, s, kMask);
+                                else tma_load_3d_mc(sa + s * A_BYTES, &mapA, &full_bar[st], m_tile * kBM, k0, s, kMask);
+                            }
+                            if (load_b) tma_load_3d(sb + s * b_bytes, &mapB, &full_bar[st], k0, n_tile * bn, s);
                         }
-                        if (load_b) tma_load_3d(sb + s * b_bytes, &mapB, &full_bar[st], k0, n_tile * bn, s);
                     }
+                    __syncwarp();
                 }
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer (one elected lane) =====
-        if (lane == 0) {
+        // ===== MMA issuer: the warp walks the loop converged, one elected lane issues =====
+        {
             // Digit ka of A meets digits 0..S-1-ka of B, landing in groups ka..S-1 = CONSECUTIVE TMEM columns, and
             // the B digit planes are consecutive in shared memory, so those S-ka products are issued as one wide
             // MMA (N = bn (S-ka), at most 256 per instruction): A is re-read from shared memory 8 times per K step
             // instead of 21 -- an N = 64 instruction occupies the tensor pipe for ~55 cycles while doing 32 cycles of work.
-            // The issue sequence is fully unrolled per tile width (one elected thread issues everything).
+            // The issue sequence is fully unrolled per tile width.
             uint32_t kbg = 0, it = 0;  // it = units with a non-empty K range so far (phase of the two TMEM barriers)
             for (int u = cluster_id; u < units; u += n_clusters) {
                 int n_tile, m_tile, z, kbeg, num_kb;
@@ -349,6 +367,7 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                     tc_fence_after();
                     const uint32_t sa = smem_u32(smem + st * STAGE_BYTES);
                     const uint32_t sb = sa + S * A_BYTES;
+                    if (elect_one_sync()) {
                     bool wide = (p.debug & 1) != 0;   // (debug: no MMAs at all)
                     if constexpr (kBN > 64) {
                         wide = wide || bn > 64;
@@ -369,8 +388,11 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                     // frees the stage (in every CTA of the cluster) once these MMAs have read it
                     if (CL == 1) umma_commit(&empty_bar[st]);
                     else umma_commit_mc(&empty_bar[st], kMask);
+                    }
+                    __syncwarp();
                 }
-                umma_commit(&tmem_full_bar);
+                if (elect_one_sync()) umma_commit(&tmem_full_bar);
+                __syncwarp();
             }
         }
     } else {

@@ -141,3 +141,37 @@ def test_auto_precision_resolution():
     assert AUTO_SPLIT_MIN_WORK == 3e7
     for mode in ("fp64", "fp64_split", "fp64_split5", "fp64_split7", "fast"):
         assert resolve_precision(mode, 10, 10, 1) == mode
+
+
+def test_lazy_moments_is_a_dict_of_arrays():
+    """LazyMoments (large models: m x n arrays fetched from the device on first read) must behave like the reference's plain
+    dict: lookup, membership, get, iteration order, len, equality, copy and pickling."""
+    import pickle
+    import numpy as np
+    from linearcorex_b200.corex import LazyMoments
+    calls = []
+
+    def fetch(name, value):
+        def f():
+            calls.append(name)
+            return value
+        return f
+    rho, qij = np.arange(6.).reshape(2, 3), np.ones((2, 3))
+    m = LazyMoments({"uj": np.zeros(2), "TC": 1.5}, {"rho": fetch("rho", rho), "Qij": fetch("Qij", qij)})
+    assert "rho" in m and "TC" in m and "nope" not in m and len(m) == 4 and m.pending() == ["Qij", "rho"]
+    assert m["TC"] == 1.5 and calls == []
+    assert m["rho"] is rho and m["rho"] is rho and calls == ["rho"] and m.pending() == ["Qij"]
+    assert m.get("additivity", 0) == 0 and m.get("Qij") is qij and calls == ["rho", "Qij"]
+    m2 = LazyMoments({"TC": 2.0}, {"rho": fetch("rho2", rho)})
+    assert sorted(m2) == ["TC", "rho"] and calls[-1] == "rho2"          # iteration materialises
+    m3 = LazyMoments({"TC": 2.0}, {"rho": fetch("rho3", rho)})
+    back = pickle.loads(pickle.dumps(m3))
+    assert type(back) is dict and set(back) == {"TC", "rho"} and np.array_equal(back["rho"], rho)
+    m4 = LazyMoments({"TC": 2.0}, {"rho": fetch("rho4", rho)})
+    m4["rho"] = qij                                                     # overwriting drops the pending fetch
+    assert m4["rho"] is qij and "rho4" not in calls and dict(m4.items()) == {"TC": 2.0, "rho": qij}
+    try:
+        m4["missing"]
+        raise AssertionError("KeyError expected")
+    except KeyError:
+        pass

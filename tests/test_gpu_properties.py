@@ -125,3 +125,27 @@ def test_run_to_run_bit_identical(precision):
         assert other.history["TC"] == fits[0].history["TC"]
         for key, val in fits[0].moments.items():
             assert np.array_equal(np.asarray(other.moments[key]), np.asarray(val)), key
+
+
+def test_lazy_moments_export_equals_eager(monkeypatch):
+    """Large models keep the m x n arrays of `moments` on the device until a key is read (Corex.LAZY_MOMENTS_BYTES); forced on
+    for a golden case, every key -- and what is derived from them -- must equal the eager export bit for bit."""
+    import pickle
+    from conftest import load_golden
+    from linearcorex_b200 import Corex
+    from linearcorex_b200.corex import LazyMoments
+    z, kw, x = load_golden("syn_400x300x10_f64")
+    eager = Corex(precision="fp64_split", **kw).fit(x)
+    monkeypatch.setattr(Corex, "LAZY_MOMENTS_BYTES", 0)
+    lazy = Corex(precision="fp64_split", **kw).fit(x)
+    assert isinstance(lazy.moments, LazyMoments) and not isinstance(eager.moments, LazyMoments)
+    assert {"rho", "Qij", "MI", "X_i Z_j"} <= set(lazy.moments.pending())
+    assert lazy.tc == eager.tc and np.array_equal(lazy.tcs, eager.tcs) and "rho" in lazy.moments.pending()
+    np.testing.assert_array_equal(lazy.get_covariance(), eager.get_covariance())   # reads rhoinvrho / Si only
+    assert "rho" in lazy.moments.pending() and "rhoinvrho" not in lazy.moments.pending()
+    Corex(precision="fp64_split", **kw).fit(x[::-1].copy())   # a later fit reuses device memory: the snapshots must not move
+    back = pickle.loads(pickle.dumps(lazy))
+    assert type(back.moments) is dict and list(back.moments) == list(eager.moments)
+    for key, val in eager.moments.items():
+        np.testing.assert_array_equal(np.asarray(lazy.moments[key]), np.asarray(val), err_msg=key)
+        np.testing.assert_array_equal(np.asarray(back.moments[key]), np.asarray(val), err_msg=key)
