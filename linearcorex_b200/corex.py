@@ -19,7 +19,8 @@ behaviour):
   precision           'fp64': all arithmetic binary64 (DMMA tensor-core contractions), parity target = the
                       reference's numpy float64 path.
                       'fp64_split' (default): the two X contractions run as exact int8 digit products on tcgen05
-                      (6 radix-254 digits = 48 bits below each row/column maximum -- truncation at the level of
+                      (6 radix-254 digits = 48 bits below max |X~| for the data -- one exponent for all of X~, which is
+                      standardised -- and below each row / column maximum for W, grad and Y; truncation at the level of
                       binary64 rounding, measured parity 1e-11), everything else binary64.
                       'fp64_split5': 5 digits (40 bits), 30 % faster, parity 1e-9 on fits up to ~700 iterations.
                       'fp64_split7': 7 digits (56 bits, finer than binary64's significand), ~1.4x the cost of the
@@ -28,7 +29,9 @@ behaviour):
                       'fast': 3 digits (24 bits, fp32-equivalent products; opt-in, 1e-4 tolerance).
                       'auto' (default): 'fp64_split', except for problems so small (N n m < 3e7: the README demo, big5,
                       adni) that an iteration is launch-bound -- there 'fp64' (DMMA) has fewer launches and is
-                      10-50 % quicker (tools/small_configs.py).  Both are FP64-faithful; `precision_used` tells which ran.
+                      10-50 % quicker (tools/small_configs.py) -- and except with gaussianize='none', where columns keep
+                      their own scales and the single exponent of X~ would short-change small ones (also 'fp64').
+                      Both are FP64-faithful; `precision_used` tells which ran.
   algorithm           'stream': every pass pair reads X~ (Y = X~ A^T, then X~^T Y), the reference's own formulation, which
                       it chose for n >> N (:197-198).  'gram': the fit only ever needs X~^T X~ / N, so that n x n matrix
                       is formed ONCE on the int8 tcgen05 engine (exact digit products) and every pass pair becomes one
@@ -293,10 +296,17 @@ class _DeviceSession(object):
 AUTO_SPLIT_MIN_WORK = 3e7  # N n m above which the split-integer tcgen05 contractions beat the DMMA ones (see 'auto')
 
 
-def resolve_precision(precision, n_rows_total, n_vars, n_factors):
-    """'auto' -> 'fp64_split' or, for launch-bound small problems, 'fp64'; anything else passes through."""
+def resolve_precision(precision, n_rows_total, n_vars, n_factors, gaussianize='standard'):
+    """'auto' -> 'fp64_split' or, for launch-bound small problems, 'fp64'; anything else passes through.
+
+    The split modes keep 48 bits below ONE exponent for all of X~ (max |X~|).  That is binary64-faithful for standardised data
+    ('standard', 'outliers': every column has unit scale), but with gaussianize='none' the columns keep the user's scales and a
+    small-magnitude column would silently hold far fewer than 48 significant bits -- so 'auto' stays on the all-binary64 DMMA
+    path there; the split modes remain available by name."""
     if precision != 'auto':
         return precision
+    if gaussianize == 'none':
+        return 'fp64'
     return 'fp64_split' if float(n_rows_total) * float(n_vars) * float(n_factors) >= AUTO_SPLIT_MIN_WORK else 'fp64'
 
 
@@ -592,7 +602,8 @@ class Corex(object):
             raise ValueError("n_hidden=None (pick_n_hidden) is not supported: the reference helper is broken (:458-480)")
         red = self._reducer()
         if self.precision == 'auto':  # every rank sees the same total, so every rank takes the same path
-            self.precision_used = resolve_precision('auto', red.sum_scalar(int(np.shape(x)[0])), int(np.shape(x)[1]), self.m)
+            self.precision_used = resolve_precision('auto', red.sum_scalar(int(np.shape(x)[0])), int(np.shape(x)[1]), self.m,
+                                                    self.gaussianize)
         sess = self._session()
         lib = sess.lib
         self._fitted_in_session = False
@@ -924,25 +935,35 @@ class Corex(object):
     LAZY_MOMENTS_BYTES = 256 << 20  # m x n arrays of moments stay on the device until read when together they exceed this
 
     def _export_moments(self, sess, tc):
+        """Every key of the reference's moments dict.  Large models (the seven m x n arrays together above LAZY_MOMENTS_BYTES)
+        get a LazyMoments: each m x n array is snapshotted on the device (the workspace is reused by the next fit) and crosses
+        to the host on first access -- at 1 000 x 50 000 x 500 the eager export is 1.6 GB over PCIe into pageable memory,
+        most of the time `fit` spends after its last iteration."""
         L = _lib
-        if 7 * 8 * self.m * self.nv > self.LAZY_MOMENTS_BYTES and getattr(sess, "allow_lazy", True):
-            return self._export_moments_lazy(sess, tc)
+        lazy = 7 * 8 * self.m * self.nv > self.LAZY_MOMENTS_BYTES
+
+        def big(array_id, transpose=False):
+            if not lazy:
+                return sess.host(array_id, transpose=transpose)
+            snap = sess.view(array_id).clone()
+            return lambda: (snap.t().contiguous() if transpose else snap).cpu().numpy()
+
         m = {}
         sc = sess.host(L.A_SCALARS, squeeze=True)
         if self.discourage_overlap:  # key set of _calculate_moments_ns (:236-288)
             m["uj"] = sess.host(L.A_UJ, squeeze=True)
-            m["rho"] = sess.host(L.A_RHO)
+            m["rho"] = big(L.A_RHO)
             m["ry"] = sess.host(L.A_RY)
             m["Y_j^2"] = sess.host(L.A_YJ2, squeeze=True)
-            m["invrho"] = sess.host(L.A_INVRHO)
-            m["rhoinvrho"] = sess.host(L.A_RHOINVRHO)
-            m["Qij"] = sess.host(L.A_QIJ)
+            m["invrho"] = big(L.A_INVRHO)
+            m["rhoinvrho"] = big(L.A_RHOINVRHO)
+            m["Qij"] = big(L.A_QIJ)
             m["Si"] = sess.host(L.A_SI, squeeze=True)
             m["Qi-Si^2"] = sess.host(L.A_QISI2, squeeze=True)
             m["TC"] = tc
-            m["MI"] = sess.host(L.A_MI)
-            m["X_i Y_j"] = sess.host(L.A_XY, transpose=True)
-            m["X_i Z_j"] = sess.host(L.A_XZ, transpose=True)
+            m["MI"] = big(L.A_MI)
+            m["X_i Y_j"] = big(L.A_XY, transpose=True)
+            m["X_i Z_j"] = big(L.A_XZ, transpose=True)
             m["X_i^2 | Y"] = sess.host(L.A_X2Y, squeeze=True)
             m["I(Y_j ; X)"] = sess.host(L.A_IYX, squeeze=True)
             m["I(X_i ; Y)"] = sess.host(L.A_IXY, squeeze=True)
@@ -951,51 +972,26 @@ class Corex(object):
             m["TC_direct"] = sess.host(L.A_TCDIRECT, squeeze=True)
             m["additivity"] = float(sc[6])
         else:  # key set of _calculate_moments_syn (:336-373)
-            m["X_i Y_j"] = sess.host(L.A_XY, transpose=True)
+            m["X_i Y_j"] = big(L.A_XY, transpose=True)
             m["cy"] = sess.host(L.A_CY)
             m["Y_j^2"] = sess.host(L.A_YJ2, squeeze=True)
             m["ry"] = sess.host(L.A_RY)
-            m["rho"] = sess.host(L.A_RHO)
-            m["invrho"] = sess.host(L.A_INVRHO)
-            m["rhoinvrho"] = sess.host(L.A_RHOINVRHO)
-            m["Qij"] = sess.host(L.A_QIJ)
+            m["rho"] = big(L.A_RHO)
+            m["invrho"] = big(L.A_INVRHO)
+            m["rhoinvrho"] = big(L.A_RHOINVRHO)
+            m["Qij"] = big(L.A_QIJ)
             m["Qi"] = sess.host(L.A_QISI2, squeeze=True)
             m["Si"] = sess.host(L.A_SI, squeeze=True)
-            m["MI"] = sess.host(L.A_MI)
-            m["X_i Z_j"] = sess.host(L.A_XZ, transpose=True)
+            m["MI"] = big(L.A_MI)
+            m["X_i Z_j"] = big(L.A_XZ, transpose=True)
             m["X_i^2 | Y"] = sess.host(L.A_X2Y, squeeze=True)
             m["TCs"] = sess.host(L.A_TCS, squeeze=True)
             m["additivity"] = float(sc[6])
             m["TC"] = tc
-        return m
-
-    def _export_moments_lazy(self, sess, tc):
-        """The same key set, with every m x n array snapshotted on the device (one device-to-device copy each, the workspace is
-        reused by the next fit) and fetched on first access -- at 1 000 x 50 000 x 500 the eager export is 1.6 GB over PCIe into
-        pageable memory, most of the time `fit` spends after its last iteration."""
-        L = _lib
-        sess.allow_lazy = False
-        small_ids = {L.A_UJ, L.A_RY, L.A_YJ2, L.A_SI, L.A_QISI2, L.A_X2Y, L.A_IYX, L.A_IXY, L.A_TCS, L.A_TCDIRECT, L.A_CY, L.A_SCALARS}
-        big = {}
-        orig_host = sess.host
-
-        def host(array_id, which=0, squeeze=False, transpose=False):
-            if array_id in small_ids:
-                return orig_host(array_id, which, squeeze=squeeze, transpose=transpose)
-            snap = sess.view(array_id, which).clone()
-
-            def fetch(snap=snap, transpose=transpose):
-                return (snap.t().contiguous() if transpose else snap).cpu().numpy()
-            return fetch
-        try:
-            sess.host = host
-            full = self._export_moments(sess, tc)
-        finally:
-            del sess.host
-            sess.allow_lazy = True
-        eager = {k: v for k, v in full.items() if not callable(v)}
-        big = {k: v for k, v in full.items() if callable(v)}
-        return LazyMoments(eager, big, order=list(full))
+        if not lazy:
+            return m
+        return LazyMoments({k: v for k, v in m.items() if not callable(v)}, {k: v for k, v in m.items() if callable(v)},
+                           order=list(m))
 
     # ------------------------------------------------------------------------------------------
     # transform / invert / predict / get_covariance (:386-395, :431-455)

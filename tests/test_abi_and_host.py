@@ -138,6 +138,8 @@ def test_auto_precision_resolution():
     assert resolve_precision("auto", 4000, 2000, 20) == "fp64_split"
     assert resolve_precision("auto", 100000, 10000, 100) == "fp64_split"   # config 3
     assert resolve_precision("auto", 1000000, 20000, 100) == "fp64_split"  # target (int overflow safe)
+    assert resolve_precision("auto", 100000, 10000, 100, "none") == "fp64"  # un-normalised columns: one exponent is not enough
+    assert resolve_precision("auto", 100000, 10000, 100, "outliers") == "fp64_split"
     assert AUTO_SPLIT_MIN_WORK == 3e7
     for mode in ("fp64", "fp64_split", "fp64_split5", "fp64_split7", "fast"):
         assert resolve_precision(mode, 10, 10, 1) == mode

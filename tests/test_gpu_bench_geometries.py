@@ -50,6 +50,19 @@ def test_config3_geometry_8192x10000x100():
     assert _rel(mdl.transform(x[:300]), ref.transform(x[:300])) <= RTOL
 
 
+def test_config3_geometry_gram_route_12288x10000x100():
+    """The Gram route at the benchmarked n = 10 000, m = 100: 79 row tiles of the matrix, its split-K product, the column-block
+    build with a partial last block, upper triangle + mirror -- N >= n so `algorithm='auto'` takes it."""
+    import corex_oracle as oc
+    from linearcorex_b200 import Corex
+    x = oc.latent_factor_data(12288, 10000, 100, seed=4, snr=1.0, snr_spread=0.02)
+    kw = dict(n_hidden=100, seed=0, max_iter=1, tol=1e-12)
+    mdl = Corex(precision="fp64_split", **kw).fit(x)
+    assert mdl.algorithm_used == "gram"
+    ref = oc.OracleCorex(work_dtype=np.float64, **kw).fit(x)
+    _compare(mdl, ref)
+
+
 def test_config4_geometry_1000x8192x500_outliers():
     import corex_oracle as oc
     from linearcorex_b200 import Corex
