@@ -141,6 +141,12 @@ int lcx_bind(lcx_session* s, const double* xt, long long n_rows_local, long long
  * scale: every product then comes out NaN, which is what the reference's float64 path does with such data. */
 int lcx_set_x_scale(lcx_session* s, double max_abs);
 int lcx_slice_block(lcx_session* s, const double* xt, long long row0, long long rows, long long ldx);
+/* The same for raw rows: lcx_standardize (:397-429, :483-487, :497-510) and lcx_slice_block fused into one pass -- the fp32 /
+ * fp64 source goes straight into the int8 digit planes of rows [row0, row0 + n_rows), X~ never exists in binary64 (4 or 8
+ * bytes read + S written per element).  Bit-identical planes to the two-call sequence. */
+int lcx_standardize_slice(lcx_session* s, const void* x, int dtype, long long row0, long long n_rows, long long ldx,
+                          int has_marker, double marker, int gauss_mode, const double* impute, const double* mean,
+                          const double* sd);
 /* ---- Gram route (N >= n) ------------------------------------------------------------------------------------------
  * Every quantity of the fit depends on the data only through X~^T X~ / N: _sig (linearcorex.py:196-213) is
  * u -> (X~^T X~ / N) u^T and sum_l Y_lj^2 / N = a_j^T (X~^T X~ / N) a_j (:248, :227).  The reference avoids the n x n matrix

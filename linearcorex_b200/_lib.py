@@ -56,6 +56,7 @@ SIGNATURES = {
     "lcx_colstats_sqdev": (_i, [_p, _p, _i, _ll, _i, _ll, _i, _d, _p, _p, _p, _p, _ll]),
     "lcx_set_x_scale": (_i, [_p, _d]),
     "lcx_slice_block": (_i, [_p, _p, _ll, _ll, _ll]),
+    "lcx_standardize_slice": (_i, [_p, _p, _i, _ll, _ll, _ll, _i, _d, _i, _p, _p, _p]),
     "lcx_colstats_std": (_i, [_p, _p, _p, _d, _i, _p, _i]),
     "lcx_standardize": (_i, [_p, _p, _i, _ll, _i, _ll, _i, _d, _i, _p, _p, _p, _p, _ll]),
     "lcx_colstats_scratch_doubles": (_ll, [_ll, _i]),

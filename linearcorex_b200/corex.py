@@ -607,9 +607,7 @@ class Corex(object):
         sess = self._session()
         lib = sess.lib
         self._fitted_in_session = False
-        rows = self._stream_rows_for(x)
-        if red.world > 1:  # the two preparation paths issue different collective sequences: every rank must take the same
-            rows = int(red.max_scalar(rows))
+        rows = self._stream_rows_for(x, red)
         if rows:
             self._prepare_streamed(x, rows, red)
         else:
@@ -705,19 +703,27 @@ class Corex(object):
         torch.cuda.synchronize(gs.device)
         self.timings["gram_bind_s"] = time.perf_counter() - t0
 
-    def _stream_rows_for(self, x):
-        """Row-block size for streamed preparation, or 0 for the one-shot path.  Streaming applies to the split modes
-        when the fp64 image of X~ would not fit beside its int8 digit planes (or when `stream_rows` forces it)."""
+    def _stream_rows_for(self, x, red=None):
+        """Row-block size of the split modes' preparation, or 0 for the fp64 path (DMMA mode, gaussianize='none').
+
+        The split modes never materialise X~ in binary64: column statistics, then ONE fused pass standardise + g() + impute +
+        digit slicing from the raw input (lcx_standardize_slice).  When the raw block fits on the device beside its digit
+        planes it is uploaded once and the block is the whole input; otherwise (or when `stream_rows` says so) the three passes
+        re-read the source in row blocks -- what lets the 1M x 20k target run on one GPU.  The choice is collective: if any
+        rank must stream, every rank does."""
         if self._active_precision() == 'fp64' or self.gaussianize == 'none':
             return 0
+        n_rows, n_vars = int(np.shape(x)[0]), int(np.shape(x)[1])
         if self.stream_rows:
             return int(self.stream_rows)
         torch = _torch()
-        n_rows, n_vars = int(np.shape(x)[0]), int(np.shape(x)[1])
         free, _total = torch.cuda.mem_get_info(self._session().device)
         digits = _lib.SPLIT_DIGITS.get(self._active_precision(), 6)
-        need = n_rows * self._session().lib.lcx_ld(n_vars) * (8 + digits + 4)
-        return 32768 if need > 0.8 * free else 0
+        need = n_rows * self._session().lib.lcx_ld(n_vars) * (digits + 8)   # planes + the raw block (as float64 at worst)
+        stream = 1 if need > 0.8 * free else 0
+        if red is not None and red.world > 1:
+            stream = int(red.max_scalar(stream))
+        return 32768 if stream else max(n_rows, 1)
 
     def _prepare_streamed(self, x, rows, red):
         """preprocess(fit=True) + bind without ever holding all of X~ in fp64 (SURVEY.md hard part 4): three passes over
@@ -737,9 +743,14 @@ class Corex(object):
         nscr = lib.lcx_colstats_scratch_doubles(rows, n)
         scratch = torch.empty(nscr, dtype=torch.float64, device=sess.device)
         blocks = [(lo, min(N, lo + rows)) for lo in range(0, N, rows)]
+        resident = None
+        if len(blocks) == 1:  # the raw block fits: one upload, three passes over the device copy
+            t_up = time.perf_counter()
+            resident = self._as_input(x[0:N])
+            self.timings["upload_s"] = time.perf_counter() - t_up
 
         def block(lo, hi):
-            xd = self._as_input(x[lo:hi])
+            xd = resident[lo:hi] if resident is not None else self._as_input(x[lo:hi])
             return xd, (_lib.F32 if xd.dtype == torch.float32 else _lib.F64)
 
         ssum, cnt, t1, t2 = vec(), vec(), vec(), vec()
@@ -775,13 +786,11 @@ class Corex(object):
         t0 = time.perf_counter()
         sess.bind(None, self.n_samples, n, self.m, red, n_local=N)
         _lib.check(lib.lcx_set_x_scale(sess.h, zmax), "lcx_set_x_scale")
-        xt = torch.empty((rows, ld), dtype=torch.float64, device=sess.device)
-        for lo, hi in blocks:  # pass 3
+        for lo, hi in blocks:  # pass 3: raw rows -> int8 digit planes, X~ never exists in binary64
             xd, dt = block(lo, hi)
-            _lib.check(lib.lcx_standardize(sess.h, xd.data_ptr(), dt, hi - lo, n, xd.stride(0), int(has_marker), marker, mode,
-                                           mean.data_ptr(), mean.data_ptr(), sd.data_ptr(), xt.data_ptr(), ld),
-                       "lcx_standardize")
-            _lib.check(lib.lcx_slice_block(sess.h, xt.data_ptr(), lo, hi - lo, ld), "lcx_slice_block")
+            _lib.check(lib.lcx_standardize_slice(sess.h, xd.data_ptr(), dt, lo, hi - lo, xd.stride(0), int(has_marker), marker, mode,
+                                                 mean.data_ptr(), mean.data_ptr(), sd.data_ptr()), "lcx_standardize_slice")
+        del resident
         torch.cuda.synchronize()
         self.timings["bind_s"] = time.perf_counter() - t0
 

@@ -419,6 +419,55 @@ extern "C" int lcx_standardize(lcx_session* s, const void* x, int dtype, long lo
     return 0;
 }
 
+template <typename T, int S>
+static int standardize_slice_t(lcx_session* s, const T* x, long long row0, long long rows, long long ldx, int has_marker,
+                               double marker, int mode, const double* impute, const double* mean, const double* sd) {
+    const Layout& L = s->L;
+    const dim3 grid((unsigned)rows, cdiv(L.ld8, 4 * 128));
+    int8_t* out = s->xs() + row0 * L.ld8;
+    const int nan_marker = marker != marker;
+    if (vec4_ok(x, ldx))
+        standardize_slice_kernel<T, S, 4><<<grid, 128, 0, s->stream>>>(x, rows, s->n, ldx, has_marker, marker, nan_marker, mode,
+                                                                     impute, mean, sd, s->oz_xscale(), out, L.ld8,
+                                                                     s->Nl * L.ld8, (double)L.radix);
+    else
+        standardize_slice_kernel<T, S, 1><<<grid, 128, 0, s->stream>>>(x, rows, s->n, ldx, has_marker, marker, nan_marker, mode,
+                                                                     impute, mean, sd, s->oz_xscale(), out, L.ld8,
+                                                                     s->Nl * L.ld8, (double)L.radix);
+    LAUNCHED(s);
+    LCX_CUDA(cudaGetLastError());
+    return 0;
+}
+
+template <typename T>
+static int standardize_slice_d(lcx_session* s, const T* x, long long row0, long long rows, long long ldx, int has_marker,
+                               double marker, int mode, const double* impute, const double* mean, const double* sd) {
+    switch (s->L.S) {
+        case 3: return standardize_slice_t<T, 3>(s, x, row0, rows, ldx, has_marker, marker, mode, impute, mean, sd);
+        case 4: return standardize_slice_t<T, 4>(s, x, row0, rows, ldx, has_marker, marker, mode, impute, mean, sd);
+        case 5: return standardize_slice_t<T, 5>(s, x, row0, rows, ldx, has_marker, marker, mode, impute, mean, sd);
+        case 6: return standardize_slice_t<T, 6>(s, x, row0, rows, ldx, has_marker, marker, mode, impute, mean, sd);
+        case 7: return standardize_slice_t<T, 7>(s, x, row0, rows, ldx, has_marker, marker, mode, impute, mean, sd);
+    }
+    return fail(LCX_ERR_STATE, "lcx_standardize_slice", "bad digit count");
+}
+
+// lcx_standardize + lcx_slice_block in one pass over the raw rows (split modes, after lcx_bind(xt = NULL) + lcx_set_x_scale)
+extern "C" int lcx_standardize_slice(lcx_session* s, const void* x, int dtype, long long row0, long long n_rows, long long ldx,
+                                     int has_marker, double marker, int gauss_mode, const double* impute, const double* mean,
+                                     const double* sd) {
+    S_REQUIRE_BOUND(s);
+    LCX_REQUIRE(s->L.S > 0 && !s->gram, "only meaningful in the split modes, on a session bound to X~");
+    LCX_REQUIRE(x != nullptr && row0 >= 0 && n_rows > 0 && row0 + n_rows <= s->Nl && ldx >= s->n, "bad row block");
+    LCX_REQUIRE(gauss_mode == LCX_GAUSS_NONE || (mean && sd), "mean/std required");
+    LCX_REQUIRE(has_marker == 0 || impute != nullptr, "imputation means required when a missing marker is set");
+    if (dtype == LCX_F32)
+        return standardize_slice_d<float>(s, (const float*)x, row0, n_rows, ldx, has_marker, marker, gauss_mode, impute, mean, sd);
+    if (dtype == LCX_F64)
+        return standardize_slice_d<double>(s, (const double*)x, row0, n_rows, ldx, has_marker, marker, gauss_mode, impute, mean, sd);
+    return fail(LCX_ERR_ARG, "lcx_standardize_slice", "unknown dtype");
+}
+
 // ---- exported steps ----------------------------------------------------------------------------
 extern "C" long long lcx_project_scratch_doubles(long long n_rows, int n_factors) {
     return (long long)cdiv(n_rows, 128) * round_up(n_factors, 8) + 16;

@@ -6,6 +6,7 @@
 // all-reduces the combined vectors between passes.
 #pragma once
 #include "common.cuh"
+#include "ozaki_i8.cuh"
 
 namespace lcx {
 
@@ -203,6 +204,63 @@ __global__ void standardize_kernel(const T* __restrict__ x, long long N, int n, 
     } else {  // ldo is a multiple of 16 doubles and i0 of 4: 16-byte stores
         *reinterpret_cast<double2*>(out + r * ldo + i0) = make_double2(o[0], o[1]);
         *reinterpret_cast<double2*>(out + r * ldo + i0 + 2) = make_double2(o[2], o[3]);
+    }
+}
+
+// Split modes: standardise + g() + impute + digit-slice in ONE pass over the raw input -- X~ goes straight from the fp32 / fp64
+// source into its S int8 planes (out[s][row0 + r][c]) and never exists in binary64: 4 (or 8) bytes read and S bytes written per
+// element instead of 12 + 8 + S + 8 through standardize_kernel, absmax and slice_rows.  The exponent of X~ must be known
+// beforehand (lcx_set_x_scale: max |x - mean| / std per column comes out of the squared-deviation pass).  The arithmetic of
+// each element is standardize_kernel's followed by split_digits's, operation for operation: the planes are bit-identical.
+template <typename T, int S, int V>
+__global__ void __launch_bounds__(128) standardize_slice_kernel(const T* __restrict__ x, long long N, int n, long long ldx,
+                                                                int has_marker, double marker, int marker_is_nan, int mode,
+                                                                const double* __restrict__ impute, const double* __restrict__ mean,
+                                                                const double* __restrict__ sd, double* x_scale,
+                                                                int8_t* __restrict__ out, long long ld_out,
+                                                                long long slice_stride, double radix) {
+    const int c4 = (blockIdx.y * blockDim.x + threadIdx.x) * 4;   // four columns per thread: one char4 store per plane
+    const long long r = blockIdx.x;
+    if (c4 >= ld_out || r >= N) return;
+    const double inv = 1.0 / x_scale[0];
+    double v[4] = {0.0, 0.0, 0.0, 0.0};
+    if (V == 4) {
+        if (c4 + 3 < n) {
+            load_row_vec<T, 4>(x + r * ldx + c4, v);
+        } else {
+            for (int j = 0; j < 4; ++j)
+                if (c4 + j < n) v[j] = (double)x[r * ldx + c4 + j];
+        }
+    } else {
+        for (int j = 0; j < 4; ++j)
+            if (c4 + j < n) v[j] = (double)x[r * ldx + c4 + j];
+    }
+    int8_t d[4][S];
+    bool poison = false;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int i = c4 + j;
+        double o = 0.0;
+        if (i < n) {
+            double e = v[j];
+            if (is_missing_d(e, has_marker, marker, marker_is_nan)) e = impute[i];
+            if (mode == 2) {
+                o = e;
+            } else {
+                o = (e - mean[i]) / sd[i];
+                if (mode == 1) o = squash_tails(o);
+            }
+            poison = poison || !(fabs(o) <= 1.7976931348623157e308);
+        }
+        oz::split_digits<S>(o, inv, radix, d[j]);
+    }
+    // A non-finite X~ entry (an inf in the data, a column with no observed value: mean = 0 / 0) has no digits.  The reference's
+    // float64 products turn NaN there; here the exponent of X~ is poisoned, and with it every product of the planes.
+    if (poison) x_scale[0] = __longlong_as_double(0x7ff8000000000000LL);
+#pragma unroll
+    for (int k = 0; k < S; ++k) {
+        char4 w = make_char4(d[0][k], d[1][k], d[2][k], d[3][k]);
+        *reinterpret_cast<char4*>(out + (long long)k * slice_stride + r * ld_out + c4) = w;
     }
 }
 
