@@ -103,16 +103,47 @@ static int gram_pair_t(lcx_session* s, const double* A, double* svec, cudaEvent_
     }
     oz::GemmParams p;
     memset(&p, 0, sizeof(p));
-    const bool split = L.oz1_splits > 1;
-    s->d_splits = 1;
-    p.C = split ? s->ptr(I_PART) : D;
     p.ldc = L.ld;
-    p.c_split_stride = split ? (long long)m * L.ld : 0;
     p.col_scale = s->oz_cscale();
     p.inv_radix = 1.0 / (double)L.radix;
-    p.rows = n; p.cols = m; p.k_total = n; p.k_chunk = L.oz1_chunk;
+    p.rows = n; p.cols = m; p.k_total = n;
     p.bn = s->oz_bn;
     p.trans_out = 1;
+    s->d_splits = 1;
+    const int n_tiles = cdiv(m, oz::bn_max(S));
+    // Whole waves of full-K row tiles straight into D, then the remaining r < #clusters row tiles split over K so that they
+    // fill one more (short) wave: 79 tiles on 74 pairs = 157 + 12 K blocks instead of 5 rounds of 40 + the per-unit drains.
+    const GramPlan gp = gram_plan(n, m, S, L.oz_kmax);
+    if (gp.full > 0) {
+        p.C = D;
+        p.c_split_stride = 0;
+        p.k_chunk = (int)round_up(n, oz::kBK);
+        LCX_TRY((oz::launch_oz_gemm<S, true>(s->map_x_k1, s->map_a_k1, p, dim3(n_tiles, gp.full, 1), s->stream, 2)));
+        LAUNCHED(s);
+        if (gp.rest > 0) {
+            const long long col0 = (long long)gp.full * oz::kBM;
+            p.m_tile0 = gp.full;
+            p.k_chunk = gp.chunk;
+            p.C = gp.splits > 1 ? s->ptr(I_PART) : D;
+            p.c_split_stride = gp.splits > 1 ? (long long)m * L.ld : 0;
+            LCX_TRY((oz::launch_oz_gemm<S, true>(s->map_x_k1, s->map_a_k1, p, dim3(n_tiles, gp.rest, gp.splits), s->stream, 2)));
+            LAUNCHED(s);
+            if (gp.splits > 1) {
+                LCX_TRY(launch_reduce_splits(s->ptr(I_PART) + col0, gp.splits, (long long)m * L.ld, D + col0, m, (int)(n - col0),
+                                             L.ld, s->stream));
+                LAUNCHED(s);
+            }
+        }
+        if (ev) {
+            LCX_CUDA(cudaEventRecord(ev[1], s->stream));
+            LCX_CUDA(cudaEventRecord(ev[3], s->stream));
+            LCX_CUDA(cudaEventRecord(ev[4], s->stream));
+        }
+    } else {
+    const bool split = L.oz1_splits > 1;
+    p.C = split ? s->ptr(I_PART) : D;
+    p.c_split_stride = split ? (long long)m * L.ld : 0;
+    p.k_chunk = L.oz1_chunk;
     LCX_TRY((oz::launch_oz_gemm<S, true>(s->map_x_k1, s->map_a_k1, p, dim3(cdiv(m, oz::bn_max(S)), cdiv(n, oz::kBM), L.oz1_splits),
                                          s->stream, oz_cluster())));
     LAUNCHED(s);
@@ -124,6 +155,7 @@ static int gram_pair_t(lcx_session* s, const double* A, double* svec, cudaEvent_
     } else if (split) {
         LCX_TRY(launch_reduce_splits(s->ptr(I_PART), L.oz1_splits, (long long)m * L.ld, D, m, n, L.ld, s->stream));
         LAUNCHED(s);
+    }
     }
     if (svec) {
         row_dot_kernel<<<m, 256, 0, s->stream>>>(A, D, svec, n, L.ld);

@@ -145,6 +145,27 @@ static double oz_unit_fixed_kb() {
     return (per && atoi(per) == 0) ? 16.0 : 4.0;
 }
 
+// Gram product plan (host_gram.cuh): `full` row tiles run as whole waves with the full contraction, the remaining ones split
+// over K `splits` ways so that they fill one more short wave.  full = 0: not applicable (the generic split-K plan is used).
+struct GramPlan {
+    int full, rest, splits, chunk;
+};
+static GramPlan gram_plan(int n, int m, int S, int oz_kmax) {
+    GramPlan g = {0, 0, 1, 0};
+    const int n_tiles = cdiv(m, oz::bn_max(S)), m_tiles = cdiv(n, oz::kBM);
+    const int clusters = kSMs / 2;
+    const char* env = getenv("LCX_OZ_CLUSTER");
+    if (n_tiles != 2 || (env && atoi(env) != 2) || n > oz_kmax) return g;
+    g.full = (m_tiles / clusters) * clusters;
+    g.rest = m_tiles - g.full;
+    if (g.full == 0 || g.rest == 0) return g;
+    const int kblocks = cdiv(n, oz::kBK);
+    const int sp = max(1, min(clusters / g.rest, kblocks / 4));
+    g.chunk = (int)round_up(cdiv(n, sp), oz::kBK);
+    g.splits = cdiv(n, g.chunk);
+    return g;
+}
+
 // gram: the bound "data" is the n x n matrix X~^T X~ / N (Nl = n rows); only the first contraction runs, with its output stored
 // factor-major (transposed), so its split-K partials are m x ld each.
 static Layout make_layout(long long Nl, int n, int m, int precision, bool gram = false) {
@@ -264,7 +285,10 @@ static Layout make_layout(long long Nl, int n, int m, int precision, bool gram =
             L.oz1_splits = cdiv(n, L.oz1_chunk);
         }
         long long part = max((long long)L.oz_splits * mn * L.ld, L.oz1_splits > 1 ? (long long)L.oz1_splits * Nl * L.ldy : 0LL);
-        if (gram) part = max(part, (long long)L.oz1_splits * mn * L.ld);
+        if (gram) {
+            part = max(part, (long long)L.oz1_splits * mn * L.ld);
+            part = max(part, (long long)gram_plan(n, m, L.S, L.oz_kmax).splits * mn * L.ld);
+        }
         if (part > L.slot[I_PART][0].cols) {  // grow the split-K partial buffer (it is the last big slot before these)
             put1(I_PART, 1, part, part);
         }

@@ -177,6 +177,7 @@ struct GemmParams {
     int n_tiles;                 // number of real N tiles of the product
     int n_groups, m_tiles, k_splits;  // work units of THIS launch: n_groups clusters' worth of N tiles x M tiles x K splits
     int n_tile0;                 // first N tile of this launch (a product may be split into launches of different cluster size)
+    int m_tile0;                 // first M tile of this launch (the Gram product runs whole waves of full-K tiles, then a split tail)
     int bn;                      // width of EVERY N tile (multiple of 8, 16 <= bn <= bn_max(S)): the factors are split into
                                  // equal tiles (m = 100, S = 6 -> 56 + 56, not 64 + 48) so the CTAs that share an X~ tile by
                                  // multicast -- and therefore run in lock-step -- carry the same work
@@ -299,7 +300,7 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     auto unit_of = [&](int u, int& n_tile, int& m_tile, int& z, int& kbeg, int& num_kb) {
         const int g = u % p.n_groups;
         const int r = u / p.n_groups;
-        m_tile = r % p.m_tiles;
+        m_tile = p.m_tile0 + r % p.m_tiles;
         z = r / p.m_tiles;
         n_tile = p.n_tile0 + g * CL + (int)crank;
         kbeg = z * p.k_chunk;
