@@ -503,8 +503,9 @@ def gram_record(res, shape, args, peaks, i8_peak, steps):
     n_total, n_vars, n_factors = shape
     digits = DIGITS[args.precision]
     planes = digits * (digits + 1) / 2
+    gdigits = digits   # the matrix and its operand carry the digits of the data (Corex.GRAM_PRECISION)
     peak = 2.0 * float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1400.0)))
-    prod_ops = 2.0 * n_vars * n_vars * n_factors * planes           # one n x n x m product as int8 digit-plane products
+    prod_ops = 2.0 * n_vars * n_vars * n_factors * gdigits * (gdigits + 1) / 2   # one n x n x m product as int8 digit-plane products
     prod_ms = res["k1_ms"]
     build_s = res["prep"].get("gram_build_s")
     # the build computes the upper triangle of X~^T X~ on this rank's rows: n (n + block) / 2 outputs, ~half of 2 N n^2
@@ -523,8 +524,9 @@ def gram_record(res, shape, args, peaks, i8_peak, steps):
            "roofline_product": {"bound": "tensor", "achieved": prod_ops / (prod_ms / 1e3) / 1e12 if prod_ms > 0 else None,
                                 "peak": peak, "unit": "TOP/s",
                                 "frac": prod_ops / (prod_ms / 1e3) / 1e12 / peak if prod_ms > 0 else None,
-                                "kernel": "oz_gemm_kernel<%d,true,2> (G planes K-major x digit planes of A, output stored "
-                                          "factor-major) incl. digit slicing of A" % digits},
+                                "kernel": "oz_gemm_kernel<%d,true,2> (G planes K-major x digit planes of A, %d digits each = %d plane "
+                                          "products, output stored factor-major) incl. digit slicing of A"
+                                          % (gdigits, gdigits, gdigits * (gdigits + 1) // 2)},
            "trials_per_iteration": res["trials"], "TC_after_timed_region": res["tc"], "clocks": res["clocks"],
            "ranks_bit_identical": res["ranks_bit_identical"], "gpu_launches": int(res["launches"])}
     if build_s:

@@ -400,6 +400,8 @@ class Corex(object):
 
     def _session(self):
         want = _lib.PRECISIONS[self._active_precision()]
+        if self._sess is not None and getattr(self._sess, "is_gram", False):
+            return self._sess  # the Gram route's session (bound to X~^T X~ / N: _to_gram)
         if self._sess is not None and self._sess.precision != want:  # 'auto' resolved differently for a new shape
             self._sess.close()
             self._sess = None
@@ -604,6 +606,9 @@ class Corex(object):
         if self.precision == 'auto':  # every rank sees the same total, so every rank takes the same path
             self.precision_used = resolve_precision('auto', red.sum_scalar(int(np.shape(x)[0])), int(np.shape(x)[1]), self.m,
                                                     self.gaussianize)
+        if self._sess is not None and getattr(self._sess, "is_gram", False):  # a refit starts from a fresh data session
+            self._sess.close()
+            self._sess = None
         sess = self._session()
         lib = sess.lib
         self._fitted_in_session = False
@@ -643,6 +648,16 @@ class Corex(object):
         return schedule
 
     GRAM_MIN_WORK = 1e9  # N n m from which an iteration is bound by the passes over X~ rather than by launches
+    # Digits of the matrix X~^T X~ / N and of the operand it meets, per data precision.  The build is exact for the digit planes
+    # of X~, so the route's own truncation is that of the matrix.  One digit more for the matrix (6 -> 7) was measured and
+    # does NOT buy parity: the ill-conditioned adni fixture (2 414 iterations, rho -> 1) sits at 8.5e-9 on invrho / Qij / Si
+    # either way and at 1.2e-11 only when the DATA planes carry 7 digits too (precision='fp64_split7') -- what it amplifies
+    # is the 48-bit truncation of X~, as on the streaming route -- while the product costs 28 / 21 more (config 3: 2 020 ->
+    # 1 845 it/s; profiles/r02_parity_report.txt, r02_gram_digits_ab.txt).  So: same digits as the data.
+    GRAM_PRECISION = {"fast": "fast", "fp64_split5": "fp64_split5", "fp64_split": "fp64_split", "fp64_split7": "fp64_split7"}
+
+    def _gram_precision(self):
+        return _lib.PRECISIONS[self.GRAM_PRECISION[self._active_precision()]]
 
     def _want_gram(self, red):
         """Resolve `algorithm` for the bound problem; every rank sees the same totals and takes the same route."""
@@ -658,7 +673,7 @@ class Corex(object):
         torch = _torch()
         sess = self._sess
         free, _total = torch.cuda.mem_get_info(sess.device)
-        need = 8 * (self.nv * sess.lib.lcx_ld(self.nv) + sess.lib.lcx_gram_workspace_doubles(self.nv, self.m, sess.precision)
+        need = 8 * (self.nv * sess.lib.lcx_ld(self.nv) + sess.lib.lcx_gram_workspace_doubles(self.nv, self.m, self._gram_precision())
                     + sess.lib.lcx_gram_scratch_doubles(sess.h, 128))
         fits = 1 if need < 0.8 * free else 0
         return bool(red.min_scalar(fits)) if red.world > 1 else bool(fits)
@@ -689,7 +704,7 @@ class Corex(object):
         t0 = time.perf_counter()
         del scratch
         launches = sess.launches()
-        precision, device = sess.precision, sess.device.index
+        precision, device = self._gram_precision(), sess.device.index
         sess.close()
         sess.ws = None
         self._sess = None
@@ -698,6 +713,7 @@ class Corex(object):
             torch.cuda.empty_cache()
         gs = _DeviceSession(precision, device)
         gs.bind_gram(g, n, self.m)
+        gs.is_gram = True
         gs.launches_before = launches
         self._sess = gs
         torch.cuda.synchronize(gs.device)

@@ -350,6 +350,15 @@ struct lcx_session {
     const double* xt;
     bool gram;        // the bound matrix is X~^T X~ / N (lcx_bind_gram): a "pass pair" is ONE product G A^T (host_gram.cuh)
     long long Nl, Nt, ldx;
+    // CUDA graphs of the loop body (lcx_run_stage_ns): direction + first trial + mailbox copy of one iteration, one graph per
+    // physical parity of the moment sets, re-captured when eps changes.  Captured and replayed on gstream (a blocking stream:
+    // capture is not allowed on the legacy default stream torch hands over).
+    cudaStream_t gstream;
+    cudaEvent_t gevent;
+    cudaGraphExec_t graph_exec[2];
+    double graph_eps;
+    long long graph_launches[2];
+    int graph_warm[2];  // iterations already run without capture on this parity (kernel attributes are configured there)
     int tg_phys;      // physical moment set whose T / G0 (I_T, LCX_A_GRAD) the fused tail has already written, -1 = none
     int row_parts;    // > 0: grad's row maxima / partial Bj wait in I_FROW as this many per-CTA partials (fused direction)
     int d_splits;     // > 1: the last Gram product left its split-K partials in I_PART for the consumer to add (host_gram.cuh)

@@ -84,8 +84,18 @@ extern "C" int lcx_profile_read_phases(lcx_session* s, double* k1_ms, double* k2
     return 0;
 }
 
+static void graphs_invalidate(lcx_session* s) {
+    for (int i = 0; i < 2; ++i) {
+        if (s->graph_exec[i]) cudaGraphExecDestroy(s->graph_exec[i]);
+        s->graph_exec[i] = nullptr;
+    }
+}
+
 extern "C" int lcx_session_destroy(lcx_session* s) {
     if (!s) return 0;
+    graphs_invalidate(s);
+    if (s->gstream) cudaStreamDestroy(s->gstream);
+    if (s->gevent) cudaEventDestroy(s->gevent);
     if (s->prof_ev) {
         for (int i = 0; i < kProfEv * s->prof_cap; ++i) cudaEventDestroy(s->prof_ev[i]);
         delete[] s->prof_ev;
@@ -172,6 +182,8 @@ static int bind_common(lcx_session* s, const double* xt, long long n_rows_local,
     s->ws = workspace;
     s->L = L;
     s->cur = 0;
+    graphs_invalidate(s);
+    s->graph_warm[0] = s->graph_warm[1] = 0;
     s->tg_phys = -1;
     s->row_parts = 0;
     s->d_splits = 1;
@@ -629,6 +641,82 @@ extern "C" int lcx_direction_trial_ns(lcx_session* s, double eps, double eta, do
     return (s->mailbox[1] >= 1.0) ? LCX_QUICK_FAIL : LCX_OK;
 }
 
+// Iteration graphs pay only where an iteration is bound by the host's launch rate: arrays of at most kGraphMaxElems elements
+// (README demo, big5: kernels of 2-3 us).  Measured on a B200 (tools/small_configs.py, profiles/r02_cuda_graph_ab.txt): README
+// demo 0.124 -> 0.075 ms per iteration; at config 3 a replay is 50 us SLOWER per iteration than stream launches (the host
+// waits for every iteration, so a graph's launch latency is exposed while stream launches run ahead of 5-30 us kernels), and a
+// capture costs ~1 ms, so a stage must run kGraphAfter iterations on a parity before it is captured.  LCX_GRAPH=0 / 1 forces
+// them off / on for every size.  Single-rank sessions only (the rank exchange is a cooperative kernel / a host hook).
+constexpr long long kGraphMaxElems = 1 << 17;
+constexpr int kGraphAfter = 8;
+static bool graphs_enabled(const lcx_session* s) {
+    static int mode = -2;
+    if (mode == -2) {
+        const char* env = getenv("LCX_GRAPH");
+        mode = env ? (atoi(env) != 0 ? 1 : 0) : -1;
+    }
+    if (mode == 0 || s->peers.world > 1 || s->hook != nullptr || s->prof_on || s->L.fused) return false;
+    return mode == 1 || (long long)s->m * s->n <= kGraphMaxElems;
+}
+
+// Direction (:292-305) + the eta = 1 trial (:320-321) + the mailbox copy of ONE iteration, replayed from a CUDA graph: ~17
+// launches become one cudaGraphLaunch.  Returns 1 when the iteration must be enqueued plainly instead (the first kGraphAfter
+// iterations of a stage on this parity: kernel attributes are configured outside a capture, and short stages never pay one).
+static int iteration_graph(lcx_session* s, double eps) {
+    const int par = s->cur;
+    if (s->graph_eps != eps) {
+        graphs_invalidate(s);
+        s->graph_eps = eps;
+        for (int i = 0; i < 2; ++i)
+            if (s->graph_warm[i] > 0) s->graph_warm[i] = 0;  // (a negative count = capture failed once: stay on plain launches)
+    }
+    if (s->graph_exec[par] == nullptr) {
+        if (s->graph_warm[par] < kGraphAfter) {
+            s->graph_warm[par]++;
+            return 1;
+        }
+        if (s->gstream == nullptr) {
+            LCX_CUDA(cudaStreamCreate(&s->gstream));
+            LCX_CUDA(cudaEventCreateWithFlags(&s->gevent, cudaEventDisableTiming));
+        }
+        cudaStream_t user = s->stream;
+        const long long l0 = s->launches;
+        LCX_CUDA(cudaStreamBeginCapture(s->gstream, cudaStreamCaptureModeRelaxed));
+        s->stream = s->gstream;
+        int rc = enqueue_direction(s, eps);
+        if (rc >= 0) rc = enqueue_trial(s, eps, 1.0, 0);
+        cudaError_t ce = cudaSuccess;
+        if (rc >= 0)
+            ce = cudaMemcpyAsync(s->mailbox, s->ptr(LCX_A_SCALARS), 16 * sizeof(double), cudaMemcpyDeviceToHost, s->gstream);
+        s->stream = user;
+        cudaGraph_t g = nullptr;
+        const cudaError_t ee = cudaStreamEndCapture(s->gstream, &g);
+        s->graph_launches[par] = s->launches - l0;
+        s->launches = l0;
+        if (rc < 0 || ce != cudaSuccess || ee != cudaSuccess || g == nullptr) {
+            if (g) cudaGraphDestroy(g);
+            cudaGetLastError();
+            s->graph_warm[par] = -1000000;  // capture is not possible here: stay on plain launches
+            return rc < 0 ? rc : 1;
+        }
+        const cudaError_t ie = cudaGraphInstantiate(&s->graph_exec[par], g, 0);
+        cudaGraphDestroy(g);
+        if (ie != cudaSuccess) {
+            cudaGetLastError();
+            s->graph_exec[par] = nullptr;
+            s->graph_warm[par] = -1000000;
+            return 1;
+        }
+    }
+    // everything queued on the caller's stream comes first; the host waits for the graph below, so what follows is ordered too
+    LCX_CUDA(cudaEventRecord(s->gevent, s->stream));
+    LCX_CUDA(cudaStreamWaitEvent(s->gstream, s->gevent, 0));
+    LCX_CUDA(cudaGraphLaunch(s->graph_exec[par], s->gstream));
+    s->launches += s->graph_launches[par];
+    LCX_CUDA(cudaStreamSynchronize(s->gstream));
+    return 0;
+}
+
 // The loop body of fit (:137-151) with _update_ns's backtracking (:290-334) for up to max_iter iterations of ONE annealing
 // stage, entirely on this side of the ABI: between two iterations the GPU waits only for the mailbox read and a few
 // branches, not for an interpreter.  Per iteration i < *n_done: tc[i] (the objective after it), tangent[i], eta[i] (accepted
@@ -650,11 +738,20 @@ extern "C" int lcx_run_stage_ns(lcx_session* s, double eps, double tol, int exac
         if (exact_trials) {
             LCX_TRY(enqueue_direction(s, eps));
         } else {  // direction and the eta = 1 trial share one host synchronisation (discarded if tangent >= 0)
-            LCX_TRY(enqueue_direction(s, eps));
-            LCX_TRY(enqueue_trial(s, eps, 1.0, 0));
+            int plain = 1;
+            if (graphs_enabled(s)) {
+                plain = iteration_graph(s, eps);
+                if (plain < 0) return plain;
+            }
+            if (plain) {
+                LCX_TRY(enqueue_direction(s, eps));
+                LCX_TRY(enqueue_trial(s, eps, 1.0, 0));
+            }
             have_first = true;
+            if (!plain) goto have_mailbox;  // the graph ends with the mailbox copy and the host already waited for it
         }
         LCX_TRY(read_mailbox(s));
+    have_mailbox:;
         const double tang = s->mailbox[2];
         tangent[it] = tang;
         eta[it] = 0.0;

@@ -124,3 +124,26 @@ def test_gram_run_to_run_bit_identical():
     b = Corex(precision="fp64_split", algorithm="gram", **kw).fit(x)
     np.testing.assert_array_equal(a.ws, b.ws)
     assert a.history["TC"] == b.history["TC"]
+
+
+def test_gram_warm_start_and_refit_on_the_same_object():
+    """A second fit on a fitted model (warm start, :114) re-binds the data session and builds a fresh matrix; both routes must
+    agree on the refit, and `transform` / `get_covariance` / pickling work from a Gram-route model like from any other."""
+    import pickle
+    from linearcorex_b200 import Corex
+    _, kw, x = load_golden("syn_400x300x10_f64")
+    kw = dict(kw, max_iter=5, tol=1e-12)
+    g = Corex(precision="fp64_split", algorithm="gram", **kw).fit(x)
+    s = Corex(precision="fp64_split", algorithm="stream", **kw).fit(x)
+    assert_close(g.ws, s.ws, RTOL, "first fit")
+    g.fit(x)
+    s.fit(x)
+    assert g.algorithm_used == "gram" and s.algorithm_used == "stream"
+    assert len(g.history["TC"]) == len(s.history["TC"])
+    assert_close(g.ws, s.ws, RTOL, "warm-started refit")
+    assert_close(g.transform(x[:50]), s.transform(x[:50]), RTOL, "transform")
+    assert_close(g.get_covariance(), s.get_covariance(), RTOL, "covariance")
+    back = pickle.loads(pickle.dumps(g))
+    assert back.algorithm_used == "gram"
+    assert_close(back.get_covariance(), s.get_covariance(), RTOL, "covariance after unpickle")
+    assert_close(back.transform(x[:50]), s.transform(x[:50]), RTOL, "transform after unpickle")
