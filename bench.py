@@ -275,7 +275,9 @@ def run_reference(args, shape):
     if rank != 0:
         return
     n_total, n_vars, n_factors = shape
-    base = time_reference_cpu(n_total, n_vars, n_factors, args.steps, args.warmup)
+    # at least 5 warm-up iterations, like the `cpu_baseline` leg of the CUDA arm: the first iterations of a stage backtrack 4-5
+    # times (each trial is a full pass pair on the CPU), steady state is 1.3-1.9 trials per iteration
+    base = time_reference_cpu(n_total, n_vars, n_factors, args.steps, max(args.warmup, 5))
     line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / base["value"], "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -709,7 +711,7 @@ def run_ours(args, shape):
     if world == 1 and not args.no_cpu_baseline:
         # same rows, warm-up and code path as `--impl reference` (5 warm-up iterations: the first iterations of a stage
         # backtrack 4-5 times; steady state is 1.3-1.9 trials per iteration), fewer timed steps
-        cpu = time_reference_cpu(n_total, n_vars, n_factors, steps=4, warmup=5)
+        cpu = time_reference_cpu(n_total, n_vars, n_factors, steps=max(4, min(args.steps, 8)), warmup=5)
         cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
     rl = roofline_of(res, shape, args, peaks, dgemm_peak, i8_peak)
     k1_ms, k2_ms = res["k1_ms"], res["k2_ms"]

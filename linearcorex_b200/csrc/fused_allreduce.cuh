@@ -24,6 +24,7 @@ namespace far {
 
 namespace cg = cooperative_groups;
 constexpr int kMaxRanks = 8;
+constexpr unsigned long long kBarrierTimeoutNs = 60ULL * 1000 * 1000 * 1000;  // 60 s
 
 struct Peers {
     double* base[kMaxRanks];  // symmetric buffer base of every rank (peer-mapped)
@@ -52,7 +53,17 @@ __device__ __forceinline__ void cross_gpu_barrier(const Peers& p, unsigned long 
         st_release_sys(flags_of(p.base[threadIdx.x], p.count) + p.rank, epoch);
     if (threadIdx.x < p.world) {
         const unsigned long long* mine = flags_of(p.base[p.rank], p.count) + threadIdx.x;
+        // A peer that died never arrives: after kBarrierTimeoutNs of polling the kernel traps, which surfaces as a CUDA error at
+        // the caller's next synchronisation instead of a hang (a live rank is at most one iteration -- milliseconds -- behind).
+        unsigned long long t0 = 0;
+        unsigned polls = 0;
         while (ld_acquire_sys(mine) < epoch) {
+            if ((++polls & 0x3ffu) == 0) {
+                unsigned long long now;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+                if (t0 == 0) t0 = now;
+                else if (now - t0 > kBarrierTimeoutNs) asm volatile("trap;");
+            }
         }
     }
     __syncthreads();

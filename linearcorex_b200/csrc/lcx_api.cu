@@ -734,7 +734,7 @@ extern "C" int lcx_run_stage_ns(lcx_session* s, double eps, double tol, int exac
     const double eta_min = tol < 1e-10 ? tol : 1e-10;
     for (int it = 0; it < max_iter; ++it) {
         const double last_tc = tc_cur;
-        bool have_first = false;
+        bool have_first = false, mailbox_ready = false;
         if (exact_trials) {
             LCX_TRY(enqueue_direction(s, eps));
         } else {  // direction and the eta = 1 trial share one host synchronisation (discarded if tangent >= 0)
@@ -748,10 +748,9 @@ extern "C" int lcx_run_stage_ns(lcx_session* s, double eps, double tol, int exac
                 LCX_TRY(enqueue_trial(s, eps, 1.0, 0));
             }
             have_first = true;
-            if (!plain) goto have_mailbox;  // the graph ends with the mailbox copy and the host already waited for it
+            mailbox_ready = !plain;  // a replayed graph ends with the mailbox copy and the host has already waited for it
         }
-        LCX_TRY(read_mailbox(s));
-    have_mailbox:;
+        if (!mailbox_ready) LCX_TRY(read_mailbox(s));
         const double tang = s->mailbox[2];
         tangent[it] = tang;
         eta[it] = 0.0;
