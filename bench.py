@@ -413,11 +413,14 @@ def resident_run(torch, dist, shape, args, steps, warmup, world, rank, local, de
     del x_dev
     mdl._begin_stage(schedule[0], rescale=False)
     sess = mdl._sess
-    def iterate(k):  # exactly k iterations of the current stage, the way fit() runs them (lcx_run_stage_ns)
+    def iterate(k):
+        """k iterations of the current stage, the way fit() runs them (lcx_run_stage_ns).  Returns how many ran: with
+        tol = 1e-12 the stage cannot converge inside a bench window on these workloads, but if it ever does the line reports
+        the iterations that were actually timed instead of dying."""
         n0 = len(mdl.trace)
         mdl.max_iter = k
-        ok = mdl._run_stage_native()
-        assert ok and len(mdl.trace) - n0 == k, "the timed region must run exactly %d iterations" % k
+        mdl._run_stage_native()
+        return len(mdl.trace) - n0
 
     iterate(warmup)
     sess.lib.lcx_profile_enable(sess.h, 1)
@@ -429,7 +432,7 @@ def resident_run(torch, dist, shape, args, steps, warmup, world, rank, local, de
     with ClockSampler(local) as clocks:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        iterate(steps)
+        steps_run = max(1, iterate(steps))
         e1.record()
         barrier()
     ms = e0.elapsed_time(e1)
@@ -449,7 +452,7 @@ def resident_run(torch, dist, shape, args, steps, warmup, world, rank, local, de
         dist.all_reduce(hi_, op=dist.ReduceOp.MAX)
         identical = bool((lo_ == hi_).item())
     trace = mdl.trace[n_trace0:]
-    res = {"ms": ms, "it_s": steps / (ms / 1e3), "k1_ms": k1.value / np_, "k2_ms": k2.value / np_, "exchange_ms": kx.value / np_,
+    res = {"ms": ms, "it_s": steps_run / (ms / 1e3), "steps_run": steps_run, "k1_ms": k1.value / np_, "k2_ms": k2.value / np_, "exchange_ms": kx.value / np_,
            "pairs": pairs.value, "launches": sess.launches() - launches0, "prep": prep,
            "trials": float(np.mean([t["trials"] for t in trace])) if trace else 0.0, "tc": float(mdl.tc),
            "clocks": clocks.summary(), "peer": sess._peer_buf is not None, "algorithm": mdl.algorithm_used, "ranks_bit_identical": identical,
@@ -778,6 +781,9 @@ def run_ours(args, shape):
     else:
         line["config"]["algorithm"] = "stream (every pass pair reads X~: the north star's formulation); see `gram` for the route "\
                                       "the public API picks at this shape"
+    if res.get("steps_run") != args.steps:  # (never seen: the stage converged inside the timed window)
+        line["steps_run"] = res.get("steps_run")
+        line["ms_per_step"] = ms / max(1, res.get("steps_run") or 1)
     if gram is not None:
         line["gram"] = gram
     if e2e_stream is not None:
