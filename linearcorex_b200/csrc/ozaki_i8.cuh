@@ -642,7 +642,7 @@ __global__ void row_scale_kernel(const double* __restrict__ a, long long ld, int
     const double* ra = a + (long long)blockIdx.x * ld;
     const double* rb = dot_b ? dot_b + (long long)blockIdx.x * ld : nullptr;
     double mx = 0.0, dot = 0.0;
-    if (skip_diag || rb != nullptr || ((uintptr_t)ra & 15) != 0) {
+    if (skip_diag || ((uintptr_t)ra & 15) != 0 || (rb != nullptr && ((uintptr_t)rb & 15) != 0)) {
         for (int i = threadIdx.x; i < cols; i += 256) {
             const double v = ra[i];
             if (!(skip_diag && i == (int)blockIdx.x)) mx = lcx::amax_acc(mx, v);
@@ -650,8 +650,9 @@ __global__ void row_scale_kernel(const double* __restrict__ a, long long ld, int
         }
     } else {  // 16-byte loads, eight values in flight per thread (a row of W is 400 KB at n = 50 000)
         const double2* ra2 = reinterpret_cast<const double2*>(ra);
+        const double2* rb2 = reinterpret_cast<const double2*>(rb);
         const int pairs = cols >> 1;
-        double m1 = 0.0, m2 = 0.0, m3 = 0.0;
+        double m1 = 0.0, m2 = 0.0, m3 = 0.0, d1 = 0.0, d2 = 0.0, d3 = 0.0;
         int i = threadIdx.x;
         for (; i + 768 < pairs; i += 1024) {
             const double2 v0 = ra2[i], v1 = ra2[i + 256], v2 = ra2[i + 512], v3 = ra2[i + 768];
@@ -659,13 +660,28 @@ __global__ void row_scale_kernel(const double* __restrict__ a, long long ld, int
             m1 = lcx::amax_acc(lcx::amax_acc(m1, v1.x), v1.y);
             m2 = lcx::amax_acc(lcx::amax_acc(m2, v2.x), v2.y);
             m3 = lcx::amax_acc(lcx::amax_acc(m3, v3.x), v3.y);
+            if (rb2) {
+                const double2 b0 = rb2[i], b1 = rb2[i + 256], b2 = rb2[i + 512], b3 = rb2[i + 768];
+                dot += v0.x * b0.x + v0.y * b0.y;
+                d1 += v1.x * b1.x + v1.y * b1.y;
+                d2 += v2.x * b2.x + v2.y * b2.y;
+                d3 += v3.x * b3.x + v3.y * b3.y;
+            }
         }
         for (; i < pairs; i += 256) {
             const double2 v = ra2[i];
             mx = lcx::amax_acc(lcx::amax_acc(mx, v.x), v.y);
+            if (rb2) {
+                const double2 b = rb2[i];
+                dot += v.x * b.x + v.y * b.y;
+            }
         }
-        if ((cols & 1) && threadIdx.x == 0) mx = lcx::amax_acc(mx, ra[cols - 1]);
+        if ((cols & 1) && threadIdx.x == 0) {
+            mx = lcx::amax_acc(mx, ra[cols - 1]);
+            if (rb) dot += ra[cols - 1] * rb[cols - 1];
+        }
         mx = fmax(fmax(mx, m1), fmax(m2, m3));
+        dot = (dot + d1) + (d2 + d3);
     }
     mx = block_max_256(mx, scratch);
     if (rb) dot = block_sum_256(dot, scratch);

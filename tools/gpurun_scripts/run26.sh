@@ -1,0 +1,6 @@
+set -x
+mkdir -p gpurun_out
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29531 tools/run_config5.py --max-iter 60 --algorithm auto > gpurun_out/r02_config5_8gpu_auto.json 2> gpurun_out/r02_config5_8gpu_auto.err; echo "auto rc=$?"
+cat gpurun_out/r02_config5_8gpu_auto.json | cut -c1-1200
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29532 tools/run_config5.py --max-iter 60 --algorithm stream > gpurun_out/r02_config5_8gpu_stream.json 2> gpurun_out/r02_config5_8gpu_stream.err; echo "stream rc=$?"
+cat gpurun_out/r02_config5_8gpu_stream.json | cut -c1-1200

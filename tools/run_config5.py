@@ -23,6 +23,7 @@ def main():
     ap.add_argument("--groups", type=int, default=30)
     ap.add_argument("--max-iter", type=int, default=3)
     ap.add_argument("--precision", default="fp64_split")
+    ap.add_argument("--algorithm", default="auto", choices=["auto", "stream", "gram"])
     args = ap.parse_args()
     world, rank, local = (int(os.environ.get(k, d)) for k, d in (("WORLD_SIZE", "1"), ("RANK", "0"), ("LOCAL_RANK", "0")))
     torch.cuda.set_device(local)
@@ -33,14 +34,15 @@ def main():
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     models = fit_layers(x, [30, 5, 1], seed=0, max_iter=args.max_iter, tol=1e-12, precision=args.precision,
-                        comm=True if world > 1 else None, stream_rows=32768)
+                        comm=True if world > 1 else None, stream_rows=32768, algorithm=args.algorithm)
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     if rank == 0:
-        out = {"config": "layers=30,5,1 on synthetic N=%d x n=%d (%d planted groups), %d ranks, precision=%s, max_iter=%d per stage"
-                         % (args.rows, args.vars, args.groups, world, args.precision, args.max_iter),
+        out = {"config": "layers=30,5,1 on synthetic N=%d x n=%d (%d planted groups), %d ranks, precision=%s, algorithm=%s, max_iter=%d per stage"
+                         % (args.rows, args.vars, args.groups, world, args.precision, args.algorithm, args.max_iter),
                "seconds_total": dt,
                "layers": [{"n": int(m.nv), "m": int(m.m), "iterations": len(m.history["TC"]), "TC": float(m.tc),
+                           "algorithm_used": m.algorithm_used, "precision_used": m.precision_used,
                            "timings": {k: round(v, 3) for k, v in m.timings.items()},
                            "pure_clusters": bool(all(len(set(m.clusters()[g::args.groups])) == 1 for g in range(args.groups)))
                            if m.nv == args.vars else None} for m in models]}
