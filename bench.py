@@ -525,7 +525,7 @@ def gram_record(res, shape, args, peaks, i8_peak, steps):
            "phases_ms_per_step": {"product_G_At": res["pairs"] / steps * prod_ms,
                                   "split_k_combine": res["pairs"] / steps * res["exchange_ms"],
                                   "m_x_n_phase_and_host_sync": ms_step - res["pairs"] / steps * (prod_ms + res["k2_ms"] + res["exchange_ms"])},
-           "one_off_s": {k: round(v, 4) for k, v in res["prep"].items()},
+           "one_off_s": {k: (round(v, 4) if isinstance(v, float) else v) for k, v in res["prep"].items()},
            "roofline_product": {"bound": "tensor", "achieved": prod_ops / (prod_ms / 1e3) / 1e12 if prod_ms > 0 else None,
                                 "peak": peak, "unit": "TOP/s",
                                 "frac": prod_ops / (prod_ms / 1e3) / 1e12 / peak if prod_ms > 0 else None,
@@ -623,7 +623,7 @@ def run_ours(args, shape):
         e2e_iters = len(e2e_mdl.history["TC"])
         e2e = {"value": e2e_iters / e2e_s, "unit": UNIT, "h2d_bytes_per_step": 0,
                "d2h_bytes_per_step": int(sum(np.asarray(v).nbytes for v in dict.values(e2e_mdl.moments)) / e2e_iters),
-               "iterations": e2e_iters, "seconds": e2e_s, "phases_s": {k: round(v, 4) for k, v in e2e_mdl.timings.items()},
+               "iterations": e2e_iters, "seconds": e2e_s, "phases_s": {k: (round(v, 4) if isinstance(v, float) else v) for k, v in e2e_mdl.timings.items()},
                "algorithm": e2e_mdl.algorithm_used,
                "what": "Corex.fit(device row generator), streamed preparation; not a host-buffer e2e (see config3)"}
         del e2e_mdl
@@ -657,7 +657,7 @@ def run_ours(args, shape):
             rec = {"value": iters / sec, "unit": UNIT, "h2d_bytes_per_step": int(x_host.nbytes * world / iters),
                    "d2h_bytes_per_step": int(d2h / iters), "iterations": iters, "seconds": sec,
                    "algorithm": "%s -> %s" % (algorithm, mdl.algorithm_used) if algorithm == "auto" else mdl.algorithm_used,
-                   "TC": float(mdl.tc), "phases_s": {k: round(v, 4) for k, v in mdl.timings.items()},
+                   "TC": float(mdl.tc), "phases_s": {k: (round(v, 4) if isinstance(v, float) else v) for k, v in mdl.timings.items()},
                    "moments_keys_left_on_device": pending,
                    "what": "second fit in the process: Corex(n_hidden=%d%s%s).fit(pinned host float32 X): H2D of X, preprocess, "
                            "digit slicing%s, 7 anneal stages%s, final sort + full moments, D2H of ws and every moments key"
@@ -698,7 +698,7 @@ def run_ours(args, shape):
                   "phases_ms": {"k1": tres["k1_ms"], "k2": tres["k2_ms"], "exchange": tres["exchange_ms"],
                                 "replicated_and_sync": tres["ms"] / tsteps - tres["pairs"] / tsteps *
                                 (tres["k1_ms"] + tres["k2_ms"] + tres["exchange_ms"])},
-                  "clocks": tres["clocks"], "TC_after_timed_region": tres["tc"], "prepare_s": {k: round(v, 3) for k, v in tres["prep"].items()},
+                  "clocks": tres["clocks"], "TC_after_timed_region": tres["tc"], "prepare_s": {k: (round(v, 3) if isinstance(v, float) else v) for k, v in tres["prep"].items()},
                   "trials_per_iteration": tres["trials"], "ranks_bit_identical": tres["ranks_bit_identical"],
                   "gpu_launches": int(tres["launches"])}
         if args.algorithm is None:
@@ -760,7 +760,7 @@ def run_ours(args, shape):
                    "parallelism": "sample-sharded x%d" % world, "exchange_per_pass_pair": exchange,
                    "l2": "inputs_exceed_l2 (X~ block is %.1f GB per GPU)"
                          % (n_local * n_vars * (8 if args.precision == "fp64" else digits) / 1e9),
-                   "prepare_s": {k: round(v, 3) for k, v in res["prep"].items()},
+                   "prepare_s": {k: (round(v, 3) if isinstance(v, float) else v) for k, v in res["prep"].items()},
                    "trials_per_iteration": res["trials"], "TC_after_timed_region": res["tc"]},
         "updates_per_sec": it_s * n_total * n_vars * n_factors,
         "phases_ms_per_step": {"k1": res["pairs"] / args.steps * k1_ms, "k2": res["pairs"] / args.steps * k2_ms,

@@ -680,7 +680,7 @@ class Corex(object):
 
     def _to_gram(self, red):
         """G = X~^T X~ / N from the bound digit planes (summed over ranks), then re-bind the fit loop to G: the digit planes
-        of X~ are released, and from here on no step touches the samples or exchanges anything between ranks."""
+        of X~ are released, and from here on no step touches the samples."""
         torch = _torch()
         sess = self._sess
         lib = sess.lib
@@ -702,6 +702,7 @@ class Corex(object):
         torch.cuda.synchronize(sess.device)
         self.timings["gram_build_s"] = time.perf_counter() - t0
         t0 = time.perf_counter()
+        marks = [("start", t0)]
         del scratch
         launches = sess.launches()
         precision, device = self._gram_precision(), sess.device.index
@@ -711,13 +712,23 @@ class Corex(object):
         need = 8 * lib.lcx_gram_workspace_doubles(n, self.m, precision)
         if need > 0.5 * torch.cuda.mem_get_info(g.device)[0]:  # hand the digit planes of X~ back before the next allocation
             torch.cuda.empty_cache()
+        marks.append(("release_data_session", time.perf_counter()))
         gs = _DeviceSession(precision, device)
+        marks.append(("create_session", time.perf_counter()))
         gs.bind_gram(g, n, self.m)
+        torch.cuda.synchronize(gs.device)
+        marks.append(("slice_matrix", time.perf_counter()))
         gs.is_gram = True
+        # With NVLink peers the per-iteration product G A^T is sharded over the ranks' row tiles of G and its column slabs are
+        # exchanged in place (far::gather_cols_kernel); without them every rank computes the whole product (no exchange).
+        if red.world > 1 and red.backend == "nccl" and os.environ.get("LCX_PEER_ALLREDUCE", "1") != "0":
+            gs._bind_peers(red, n, self.m)
+            marks.append(("map_peers", time.perf_counter()))
         gs.launches_before = launches
         self._sess = gs
         torch.cuda.synchronize(gs.device)
         self.timings["gram_bind_s"] = time.perf_counter() - t0
+        self.timings["gram_bind_parts_s"] = {b[0]: round(b[1] - a[1], 4) for a, b in zip(marks, marks[1:])}
 
     def _stream_rows_for(self, x, red=None):
         """Row-block size of the split modes' preparation, or 0 for the fp64 path (DMMA mode, gaussianize='none').

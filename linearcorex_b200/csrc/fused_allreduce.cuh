@@ -133,5 +133,29 @@ __global__ void __launch_bounds__(512) reduce_allreduce_kernel(Peers p, const do
     cross_gpu_barrier(p, epoch0 + 2, grid);
 }
 
+// Gram route across ranks: every rank has computed the columns [col0, col0 + ncols) of D = (G A^T)^T (its share of the rows of
+// G) into its own output region; this kernel hands that slab to every peer (P2P stores over NVLink) -- an all-gather in
+// place.  First barrier: every rank has finished reading the previous D and holds its new slab; second: all slabs landed.
+// Each element is produced by exactly one rank, so all ranks end with bit-identical D.
+__global__ void __launch_bounds__(512) gather_cols_kernel(Peers p, int rows, long long ld, int col0, int ncols,
+                                                          unsigned long long epoch0) {
+    cg::grid_group grid = cg::this_grid();
+    cross_gpu_barrier(p, epoch0 + 1, grid);
+    const long long out_off = 2 * p.count;   // the output region of the symmetric buffer (where D lives when sharded)
+    const double* mine = p.base[p.rank] + out_off;
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long nthr = (long long)gridDim.x * blockDim.x;
+    const int pairs = ncols >> 1;            // col0 and ncols are even (tiles of 128 variables; the last slab ends at ld)
+    for (long long i = tid; i < (long long)rows * pairs; i += nthr) {
+        const int j = (int)(i / pairs), c = (int)(i - (long long)j * pairs) * 2;
+        const long long o = (long long)j * ld + col0 + c;
+        const double2 v = *reinterpret_cast<const double2*>(mine + o);
+#pragma unroll
+        for (int r = 0; r < kMaxRanks; ++r)
+            if (r < p.world && r != p.rank) *reinterpret_cast<double2*>(p.base[r] + out_off + o) = v;
+    }
+    cross_gpu_barrier(p, epoch0 + 2, grid);
+}
+
 }  // namespace far
 }  // namespace lcx

@@ -111,6 +111,59 @@ static int gram_pair_t(lcx_session* s, const double* A, double* svec, cudaEvent_
     p.trans_out = 1;
     s->d_splits = 1;
     const int n_tiles = cdiv(m, oz::bn_max(S));
+    if (s->peers.world > 1) {
+        // Row tiles of G shard over the ranks: this rank computes the columns of D that belong to its tiles (split over K
+        // to fill its SMs), then the slabs are exchanged in place (far::gather_cols_kernel).  The m x n phase that follows
+        // is replicated on bit-identical D.
+        const int P = s->peers.world, m_tiles = cdiv(n, oz::kBM);
+        const int per = cdiv(m_tiles, P);
+        const int t0 = min(m_tiles, s->peers.rank * per), t1 = min(m_tiles, t0 + per);
+        const int mine = t1 - t0;
+        const int clusters = kSMs / 2, kblocks = cdiv(n, oz::kBK);
+        const long long col0 = (long long)t0 * oz::kBM;
+        const int ncols = (int)(min((long long)L.ld, (long long)t1 * oz::kBM) - col0);
+        if (mine > 0) {
+            // split count by the planner's cost model (rounds x (K blocks per unit + the per-unit fixed cost) + combine), never
+            // below the int32-exact minimum: 40 tiles x 157 K blocks on 74 pairs -> 3 splits (2 rounds of 53) instead of 1 x 157
+            const int smin = cdiv(n, L.oz_kmax), smax = max(smin, min(clusters, max(1, kblocks / 4)));
+            int sp = smin;
+            double best = 1e300;
+            for (int c = smin; c <= smax; ++c) {
+                const int rounds = cdiv((long long)mine * c, clusters);
+                const double cost = rounds * (ceil((double)kblocks / c) + oz_unit_fixed_kb()) + (c > 1 ? 1.5 * c : 0.0);
+                if (cost < best - 1e-9) { best = cost; sp = c; }
+            }
+            const int chunk = (int)round_up(cdiv(n, sp), oz::kBK);
+            const int splits = cdiv(n, chunk);
+            LCX_REQUIRE((long long)splits * m * L.ld <= L.slot[I_PART][0].cols, "split-K partial buffer too small");
+            p.m_tile0 = t0;
+            p.k_chunk = chunk;
+            p.C = splits > 1 ? s->ptr(I_PART) : D;
+            p.c_split_stride = splits > 1 ? (long long)m * L.ld : 0;
+            LCX_TRY((oz::launch_oz_gemm<S, true>(s->map_x_k1, s->map_a_k1, p, dim3(n_tiles, mine, splits), s->stream, oz_cluster())));
+            LAUNCHED(s);
+            if (splits > 1) {
+                LCX_TRY(launch_reduce_splits(s->ptr(I_PART) + col0, splits, (long long)m * L.ld, D + col0, m,
+                                             (int)min((long long)n - col0, (long long)mine * oz::kBM), L.ld, s->stream));
+                LAUNCHED(s);
+            }
+        }
+        if (ev) {
+            LCX_CUDA(cudaEventRecord(ev[1], s->stream));
+            LCX_CUDA(cudaEventRecord(ev[3], s->stream));
+            LCX_CUDA(cudaEventRecord(ev[4], s->stream));
+        }
+        {
+            unsigned long long epoch0 = 2ULL * s->ar_calls;
+            s->ar_calls++;
+            far::Peers pp = s->peers;
+            int rows = m, c0 = (int)col0, nc = max(0, ncols);
+            long long ldd = L.ld;
+            void* args[] = {&pp, &rows, &ldd, &c0, &nc, &epoch0};
+            LCX_CUDA(cudaLaunchCooperativeKernel((void*)far::gather_cols_kernel, dim3(kSMs), dim3(512), args, 0, s->stream));
+            LAUNCHED(s);
+        }
+    } else {
     // Whole waves of full-K row tiles straight into D, then the remaining r < #clusters row tiles split over K so that they
     // fill one more (short) wave: 79 tiles on 74 pairs = 157 + 12 K blocks instead of 5 rounds of 40 + the per-unit drains.
     const GramPlan gp = gram_plan(n, m, S, L.oz_kmax);
@@ -155,6 +208,7 @@ static int gram_pair_t(lcx_session* s, const double* A, double* svec, cudaEvent_
     } else if (split) {
         LCX_TRY(launch_reduce_splits(s->ptr(I_PART), L.oz1_splits, (long long)m * L.ld, D, m, n, L.ld, s->stream));
         LAUNCHED(s);
+    }
     }
     }
     if (svec) {

@@ -288,6 +288,9 @@ static Layout make_layout(long long Nl, int n, int m, int precision, bool gram =
         if (gram) {
             part = max(part, (long long)L.oz1_splits * mn * L.ld);
             part = max(part, (long long)gram_plan(n, m, L.S, L.oz_kmax).splits * mn * L.ld);
+            // sharded over ranks (host_gram.cuh) a rank's few row tiles are split up to kSMs / 2 / tiles ways: with at least
+            // two ranks and 128-variable tiles that is at most min(kSMs / 2, K blocks / 4) partials
+            part = max(part, (long long)min(kSMs / 2, max(1, cdiv(n, oz::kBK) / 4)) * mn * L.ld);
         }
         if (part > L.slot[I_PART][0].cols) {  // grow the split-K partial buffer (it is the last big slot before these)
             put1(I_PART, 1, part, part);
@@ -345,7 +348,8 @@ struct lcx_session {
     lcx_allreduce_fn hook;
     void* hook_user;
     long long launches;
-    double* mailbox;  // pinned host, 16 doubles
+    double* mailbox;  // pinned host, 16 doubles (a slot of the process-wide block, lcx_api.cu)
+    bool mailbox_pooled;
     bool bound;
     const double* xt;
     bool gram;        // the bound matrix is X~^T X~ / N (lcx_bind_gram): a "pass pair" is ONE product G A^T (host_gram.cuh)

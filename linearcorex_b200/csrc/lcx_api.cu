@@ -6,6 +6,49 @@
 #include "host_steps.cuh"
 
 // ---- lifecycle ---------------------------------------------------------------------------------
+// Mailboxes (16 pinned doubles per session) come from one process-wide page-locked block: cudaHostAlloc / cudaFreeHost cost
+// 10-80 ms each once the process maps 100+ GB of device memory (measured: the Gram route's re-bind spent 0.08-0.17 s in
+// them), and both synchronise the device.  64 slots; a 65th concurrent session falls back to its own allocation.
+#include <mutex>
+namespace {
+std::mutex g_mailbox_mutex;
+double* g_mailbox_pool = nullptr;
+unsigned long long g_mailbox_used = 0;
+constexpr int kMailboxSlots = 64, kMailboxDoubles = 16;
+
+double* mailbox_acquire(bool* pooled) {
+    std::lock_guard<std::mutex> lock(g_mailbox_mutex);
+    if (g_mailbox_pool == nullptr &&
+        cudaHostAlloc((void**)&g_mailbox_pool, kMailboxSlots * kMailboxDoubles * sizeof(double), cudaHostAllocPortable) != cudaSuccess) {
+        g_mailbox_pool = nullptr;
+        cudaGetLastError();
+    }
+    if (g_mailbox_pool != nullptr) {
+        for (int i = 0; i < kMailboxSlots; ++i) {
+            if (!(g_mailbox_used >> i & 1ULL)) {
+                g_mailbox_used |= 1ULL << i;
+                *pooled = true;
+                return g_mailbox_pool + i * kMailboxDoubles;
+            }
+        }
+    }
+    double* own = nullptr;
+    *pooled = false;
+    if (cudaHostAlloc((void**)&own, kMailboxDoubles * sizeof(double), cudaHostAllocPortable) != cudaSuccess) return nullptr;
+    return own;
+}
+
+void mailbox_release(double* box, bool pooled) {
+    if (box == nullptr) return;
+    if (!pooled) {
+        cudaFreeHost(box);
+        return;
+    }
+    std::lock_guard<std::mutex> lock(g_mailbox_mutex);
+    g_mailbox_used &= ~(1ULL << ((box - g_mailbox_pool) / kMailboxDoubles));
+}
+}  // namespace
+
 extern "C" int lcx_version(void) { return 100; }
 extern "C" const char* lcx_last_error(void) { return g_err; }
 
@@ -13,15 +56,19 @@ extern "C" int lcx_session_create(lcx_session** out, int device, int precision) 
     LCX_REQUIRE(out != nullptr, "out is null");
     LCX_REQUIRE(precision >= LCX_PRECISION_FP64 && precision <= LCX_PRECISION_FP64_SPLIT7, "unknown precision mode");
     LCX_CUDA(cudaSetDevice(device));
-    cudaDeviceProp prop;
-    LCX_CUDA(cudaGetDeviceProperties(&prop, device));
-    if (prop.major != 10) return fail(LCX_ERR_STATE, "lcx_session_create", "this library is built for sm_100a (B200) only");
+    int major = 0;  // (cudaGetDeviceProperties takes ~0.1 s once the process holds large page-locked / device mappings)
+    LCX_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
+    if (major != 10) return fail(LCX_ERR_STATE, "lcx_session_create", "this library is built for sm_100a (B200) only");
     lcx_session* s = new lcx_session();
     memset(s, 0, sizeof(*s));
     s->device = device;
     s->precision = precision;
     s->stream = 0;
-    LCX_CUDA(cudaHostAlloc((void**)&s->mailbox, 16 * sizeof(double), cudaHostAllocDefault));
+    s->mailbox = mailbox_acquire(&s->mailbox_pooled);
+    if (s->mailbox == nullptr) {
+        delete s;
+        return fail(LCX_ERR_CUDA, "lcx_session_create", "no page-locked memory for the mailbox");
+    }
     *out = s;
     return 0;
 }
@@ -100,7 +147,7 @@ extern "C" int lcx_session_destroy(lcx_session* s) {
         for (int i = 0; i < kProfEv * s->prof_cap; ++i) cudaEventDestroy(s->prof_ev[i]);
         delete[] s->prof_ev;
     }
-    if (s->mailbox) cudaFreeHost(s->mailbox);
+    mailbox_release(s->mailbox, s->mailbox_pooled);
     delete s;
     return 0;
 }
@@ -557,7 +604,8 @@ extern "C" int lcx_init_scale(lcx_session* s, double eps) {
         LCX_TRY(lcx_project(s, s->xt, s->Nl, n, s->ldx, W, L.ld, m, s->ptr(LCX_A_Y), L.ldy, svec, s->ptr(I_COLSQ),
                             lcx_project_scratch_doubles(s->Nl, m)));
     }
-    LCX_TRY(combine_and_allreduce(s, nullptr, 1, 0, 0, 0, L.ld, nullptr, svec, m));  // sum of Y^2 over ranks
+    if (!s->gram)  // (on the Gram route a_j^T G a_j is already the sum over all samples, identical on every rank)
+        LCX_TRY(combine_and_allreduce(s, nullptr, 1, 0, 0, 0, L.ld, nullptr, svec, m));  // sum of Y^2 over ranks
     row_dot_kernel<<<m, 256, 0, s->stream>>>(W, W, s->ptr(I_W2), n, L.ld);
     LAUNCHED(s);
     const double c1 = (1.0 - eps * eps) / (double)s->Nt, e2 = eps * eps;

@@ -27,14 +27,15 @@ def _worker(rank, world, port, ret, peer_mode):
         out = {}
         for name, prec, algo in (("syn_400x300x10_f64", "fp64", "stream"), ("standard_missing_f64", "fp64", "stream"),
                                  ("syn_400x300x10_f64", "fp64_split", "stream"), ("syn_400x300x10_f64", "fp64_split", "gram"),
-                                 ("standard_missing_f64", "fp64_split", "gram")):
+                                 ("standard_missing_f64", "fp64_split", "gram"), ("syn_4000x2000x20_f64", "fp64_split", "gram")):
             z, kw, x = load_golden(name)
             kw = dict(kw, precision=prec, algorithm=algo)
             lo, hi = shard_rows(x.shape[0], rank, world)
             mdl = Corex(comm=True, **kw).fit(x[lo:hi])
             assert mdl.n_samples == x.shape[0] and mdl.algorithm_used == algo
-            # Gram route: the ranks' partial X~^T X~ / N are summed once (NCCL); the loop itself exchanges nothing
-            assert (mdl._sess._peer_buf is not None) == (peer_mode == "require" and algo == "stream")
+            # Gram route: the ranks' partial X~^T X~ / N are summed once (NCCL); with NVLink peers the per-iteration product is
+            # sharded over the ranks' row tiles of the matrix and gathered in place, without them it is replicated
+            assert (mdl._sess._peer_buf is not None) == (peer_mode == "require")
             assert len(mdl.history["TC"]) == len(z["history_TC"])
             err = np.abs(mdl.ws - z["ws"]).max() / np.abs(z["ws"]).max()
             err_tc = np.abs(mdl.moments["TCs"] - z["m_TCs"]).max() / np.abs(z["m_TCs"]).max()

@@ -43,7 +43,7 @@ def main():
                "seconds_total": dt,
                "layers": [{"n": int(m.nv), "m": int(m.m), "iterations": len(m.history["TC"]), "TC": float(m.tc),
                            "algorithm_used": m.algorithm_used, "precision_used": m.precision_used,
-                           "timings": {k: round(v, 3) for k, v in m.timings.items()},
+                           "timings": {k: (round(v, 3) if isinstance(v, float) else v) for k, v in m.timings.items()},
                            "pure_clusters": bool(all(len(set(m.clusters()[g::args.groups])) == 1 for g in range(args.groups)))
                            if m.nv == args.vars else None} for m in models]}
         os.write(1, (json.dumps(out) + "\n").encode())
