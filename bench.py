@@ -451,8 +451,17 @@ def resident_run(torch, dist, shape, args, steps, warmup, world, rank, local, de
         dist.all_reduce(lo_, op=dist.ReduceOp.MIN)
         dist.all_reduce(hi_, op=dist.ReduceOp.MAX)
         identical = bool((lo_ == hi_).item())
+    # per-rank phase times: shows how much of rank 0's `exchange` is waiting for the slowest rank's contractions
+    per_rank = None
+    if world > 1:
+        mine = torch.tensor([k1.value / np_, k2.value / np_, kx.value / np_, e0.elapsed_time(e1) / max(1, steps_run)],
+                            dtype=torch.float64, device="cuda")
+        allr = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        per_rank = {"columns": ["k1_ms", "k2_ms", "exchange_ms", "step_ms"],
+                    "ranks": [[round(float(v), 4) for v in t.tolist()] for t in allr]}
     trace = mdl.trace[n_trace0:]
-    res = {"ms": ms, "it_s": steps_run / (ms / 1e3), "steps_run": steps_run, "k1_ms": k1.value / np_, "k2_ms": k2.value / np_, "exchange_ms": kx.value / np_,
+    res = {"ms": ms, "per_rank": per_rank, "it_s": steps_run / (ms / 1e3), "steps_run": steps_run, "k1_ms": k1.value / np_, "k2_ms": k2.value / np_, "exchange_ms": kx.value / np_,
            "pairs": pairs.value, "launches": sess.launches() - launches0, "prep": prep,
            "trials": float(np.mean([t["trials"] for t in trace])) if trace else 0.0, "tc": float(mdl.tc),
            "clocks": clocks.summary(), "peer": sess._peer_buf is not None, "algorithm": mdl.algorithm_used, "ranks_bit_identical": identical,
@@ -767,6 +776,7 @@ def run_ours(args, shape):
                                "exchange_incl_split_k_combine": res["pairs"] / args.steps * res["exchange_ms"],
                                "replicated_mxn_phase_and_host_sync": ms / args.steps - pair_total},
         "ranks_bit_identical": res["ranks_bit_identical"],
+        "phases_ms_per_rank": res.get("per_rank"),
         "roofline": rl,
         "clocks": res["clocks"],
         "e2e": e2e,

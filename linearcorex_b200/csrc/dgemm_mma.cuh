@@ -130,9 +130,13 @@ __global__ void __launch_bounds__(256, 1) dgemm_mma_kernel(const GemmArgs p) {
 #pragma unroll
         for (int nt = 0; nt < NT; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
 
+    // Row groups of 8 that lie wholly beyond M issue no DMMA (warp-uniform): with m = 100 factors on the M side only 13 of the
+    // 16 groups of a tile do work, and the FP64 tensor pipe -- one per SM, shared by the 8 warps -- is what bounds these loops.
+    const bool act0 = m0 + warp * 16 < p.M, act1 = m0 + warp * 16 + 8 < p.M;
     auto compute = [&](int stage) {
         const double* as = As + stage * A_TILE;
         const double* bs = Bs + stage * B_TILE;
+        if (!act0) return;
 #pragma unroll
         for (int ks = 0; ks < BK / 4; ++ks) {
             const int kk = ks * 4 + t;
@@ -144,11 +148,19 @@ __global__ void __launch_bounds__(256, 1) dgemm_mma_kernel(const GemmArgs p) {
                 a0 = as[kk * A_STRIDE + warp * 16 + g];
                 a1 = as[kk * A_STRIDE + warp * 16 + 8 + g];
             }
+            if (act1) {
 #pragma unroll
-            for (int nt = 0; nt < NT; ++nt) {
-                const double b = B_KC ? bs[(nt * 8 + g) * B_STRIDE + kk] : bs[kk * B_STRIDE + nt * 8 + g];
-                dmma884(acc[0][nt][0], acc[0][nt][1], a0, b);
-                dmma884(acc[1][nt][0], acc[1][nt][1], a1, b);
+                for (int nt = 0; nt < NT; ++nt) {
+                    const double b = B_KC ? bs[(nt * 8 + g) * B_STRIDE + kk] : bs[kk * B_STRIDE + nt * 8 + g];
+                    dmma884(acc[0][nt][0], acc[0][nt][1], a0, b);
+                    dmma884(acc[1][nt][0], acc[1][nt][1], a1, b);
+                }
+            } else {
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt) {
+                    const double b = B_KC ? bs[(nt * 8 + g) * B_STRIDE + kk] : bs[kk * B_STRIDE + nt * 8 + g];
+                    dmma884(acc[0][nt][0], acc[0][nt][1], a0, b);
+                }
             }
         }
     };
@@ -346,6 +358,26 @@ inline GemmPlan plan_gemm(int M, int N, int K, int sms, int max_splits, bool all
     return pl;
 }
 
+// (m x n) = (m x m)(m x n) products (Qij = ry rhoinvrho, grad = G0 + H W): K = m is a handful of k tiles and the variables run
+// along N, so the tile width decides how many SMs work at all -- 104-wide tiles of n = 10 000 are 97 CTAs on 148 SMs.  Pick
+// the width whose waves x (width + a per-CTA fixed cost of ~3 n8 tiles) is smallest: 72 wide -> 139 CTAs at that shape.
+inline GemmPlan plan_gemm_kn(int M, int N, int K, int sms) {
+    GemmPlan pl = plan_gemm(M, N, K, sms, 1, false);
+    const int opts[9] = {2, 4, 6, 8, 9, 11, 13, 16, 17};
+    double best = 1e300;
+    const int gm = cdiv(M, 128);
+    for (int i = 0; i < 9; ++i) {
+        const int nt = opts[i];
+        if (nt * 8 > round_up(N, 8) && nt != pick_nt(N)) continue;
+        const long long tiles = (long long)gm * cdiv(N, nt * 8);
+        const long long waves = (tiles + sms - 1) / sms;
+        const double cost = (double)waves * (nt + 3.0);
+        if (cost < best - 1e-9) { best = cost; pl.nt = nt; }
+    }
+    pl.grid = dim3(gm, cdiv(N, pl.nt * 8), 1);
+    return pl;
+}
+
 template <int NT, bool A_KC, bool B_KC>
 inline int launch_gemm_inst(const GemmArgs& a, dim3 grid, cudaStream_t st) {
     constexpr int STAGES = 4;
@@ -367,6 +399,14 @@ inline int launch_gemm_nt(int nt, const GemmArgs& a, dim3 grid, cudaStream_t st)
         case 8: return launch_gemm_inst<8, A_KC, B_KC>(a, grid, st);
         case 13: return launch_gemm_inst<13, A_KC, B_KC>(a, grid, st);
         case 16: return launch_gemm_inst<16, A_KC, B_KC>(a, grid, st);
+    }
+    if (A_KC && !B_KC) {  // the extra widths of plan_gemm_kn exist for the (K, N)-contiguous layout only
+        switch (nt) {
+            case 6: return launch_gemm_inst<6, true, false>(a, grid, st);
+            case 9: return launch_gemm_inst<9, true, false>(a, grid, st);
+            case 11: return launch_gemm_inst<11, true, false>(a, grid, st);
+            case 17: return launch_gemm_inst<17, true, false>(a, grid, st);
+        }
     }
     return fail(-1, "launch_gemm", "unsupported tile width");
 }

@@ -186,7 +186,7 @@ static Layout make_layout(long long Nl, int n, int m, int precision, bool gram =
     L.plan_k1 = plan_gemm((int)Nl, m, n, kSMs, k1_split ? 16 : 1, k1_split);
     L.plan_k2 = plan_gemm(n, m, (int)Nl, kSMs, kMaxSplitsX, true);
     L.plan_mm = plan_gemm(m, m, n, kSMs, kMaxSplitsSmall, true);
-    L.plan_mn = plan_gemm(m, n, m, kSMs, 1, false);
+    L.plan_mn = plan_gemm_kn(m, n, m, kSMs);
     L.nstrips = cdiv(n, kStripCols);
     long long cur = 0;
     auto put = [&](int id, int set, long long rows, long long cols, long long ld) {
