@@ -32,7 +32,6 @@ import json
 import os
 import statistics
 import sys
-import threading
 import time
 
 import numpy as np
@@ -109,48 +108,100 @@ class DeviceRows(object):
         return out
 
 
+_CLOCK_HELPER = r"""
+import sys, time
+import pynvml
+pynvml.nvmlInit()
+idx = int(sys.argv[1]); period = float(sys.argv[2])
+h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+mx = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+sys.stdout.write("ready %d\n" % mx); sys.stdout.flush()
+while True:
+    t = time.time()
+    try:
+        c = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+        r = int(pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+        sys.stdout.write("%.6f %d %d\n" % (t, c, r)); sys.stdout.flush()
+    except Exception:
+        pass
+    time.sleep(period)
+"""
+
+
 class ClockSampler(object):
+    """SM clock and throttle reasons of this rank's GPU, sampled through NVML DURING the timed region -- from a helper
+    PROCESS.  An NVML query made inside the benchmarking process takes a driver lock that stalls that process's kernel
+    launches for ~0.4 ms, and the queries of the ranks of one box serialise: with in-process sampling the first sample of
+    every rank landed at the start of the timed region and cost the 8-GPU run 2-3 ms of its 20 ms window (exchange
+    0.23 ms per step over 20 steps against 0.10 over 100).  The helper is started (and NVML initialised) before the timed
+    region; its samples are matched to the region by wall-clock time stamps."""
     REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
                0x80: "hw_power_brake", 0x2: "applications_clocks_setting", 0x100: "display_clock_setting"}
+    PERIOD_S = 0.004
 
     def __init__(self, index):
-        self.samples, self.mask, self.max_mhz, self._stop, self._th = [], 0, None, threading.Event(), None
+        import subprocess
+        self.samples, self.mask, self.max_mhz, self.proc, self.t0, self.t1 = [], 0, None, None, None, None
+        cvd = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+        ids = [v.strip() for v in cvd.split(",") if v.strip()]
+        if ids and all(v.isdigit() for v in ids) and index < len(ids):
+            index = int(ids[index])  # NVML counts physical devices
         try:
-            import pynvml
-            pynvml.nvmlInit()
-            self.nv = pynvml
-            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
-            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
-            # first queries outside the timed region: NVML's first call per handle can take ~0.1 s, and it holds a
-            # driver lock that stalls kernel launches of this process for that long
-            pynvml.nvmlDeviceGetClockInfo(self.h, pynvml.NVML_CLOCK_SM)
-            pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+            self.proc = subprocess.Popen([sys.executable, "-c", _CLOCK_HELPER, str(index), str(self.PERIOD_S)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            first = self.proc.stdout.readline().split()  # blocks until NVML is initialised in the helper
+            if len(first) == 2 and first[0] == "ready":
+                self.max_mhz = int(first[1])
+            else:
+                self._kill()
         except Exception:
-            self.nv = None
+            self._kill()
 
-    def _run(self):
-        while not self._stop.is_set():
+    def _kill(self):
+        if self.proc is not None:
             try:
-                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
-                self.mask |= int(self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                self.proc.kill()
+                self.proc.wait(timeout=5)
             except Exception:
                 pass
-            time.sleep(0.05)
+        self.proc = None
 
     def __enter__(self):
-        if self.nv is not None:
-            self._th = threading.Thread(target=self._run, daemon=True)
-            self._th.start()
+        self.t0 = time.time()
         return self
 
     def __exit__(self, *exc):
-        self._stop.set()
-        if self._th is not None:
-            self._th.join()
+        self.t1 = time.time()
+        if self.proc is None:
+            return
+        time.sleep(2 * self.PERIOD_S)
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self._kill()
+            return
+        rows = []
+        for line in out.splitlines():
+            f = line.split()
+            if len(f) == 3:
+                try:
+                    rows.append((float(f[0]), int(f[1]), int(f[2])))
+                except ValueError:
+                    pass
+        inside = [r for r in rows if self.t0 <= r[0] <= self.t1]
+        if not inside and rows:  # a window shorter than one period: the sample closest to it
+            mid = 0.5 * (self.t0 + self.t1)
+            inside = [min(rows, key=lambda r: abs(r[0] - mid))]
+        self.samples = [r[1] for r in inside]
+        for r in inside:
+            self.mask |= r[2]
 
     def summary(self):
         return {"sm_mhz": statistics.median(self.samples) if self.samples else None, "sm_max_mhz": self.max_mhz,
-                "samples": len(self.samples),
+                "samples": len(self.samples), "sampler": "NVML in a helper process, every %d ms" % round(self.PERIOD_S * 1e3),
                 "reasons": sorted(name for bit, name in self.REASONS.items() if self.mask & bit)}
 
 
@@ -428,8 +479,9 @@ def resident_run(torch, dist, shape, args, steps, warmup, world, rank, local, de
     sess.lib.lcx_profile_read_phases(sess.h, C.byref(k1), C.byref(k2), C.byref(kx), C.byref(pairs), 1)
     launches0 = sess.launches()
     n_trace0 = len(mdl.trace)
+    clocks = ClockSampler(local)  # helper process up and NVML initialised before the ranks line up
     barrier()
-    with ClockSampler(local) as clocks:
+    with clocks:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         steps_run = max(1, iterate(steps))
