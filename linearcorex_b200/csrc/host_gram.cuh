@@ -17,7 +17,7 @@ static long long gram_tbuf_doubles(const lcx_session* s, int block_cols) {
 
 static long long gram_scratch_doubles(const lcx_session* s, int block_cols, long long ldg) {
     return round_up(block_cols, 16) + align16(gram_tbuf_doubles(s, block_cols)) +
-           (s->L.oz_splits > 1 ? (long long)s->L.oz_splits * block_cols * ldg : 0LL) + 64;
+           (s->L.oz_build_splits > 1 ? (long long)s->L.oz_build_splits * block_cols * ldg : 0LL) + 64;
 }
 
 template <int S>
@@ -28,7 +28,7 @@ static int gram_build_t(lcx_session* s, double* g, long long ldg, int B, double*
     int8_t* tbuf = (int8_t*)(scratch + round_up(B, 16));
     double* part = scratch + round_up(B, 16) + align16(gram_tbuf_doubles(s, B));
     const long long t_stride = (long long)B * L.ldk8;
-    const int splits = L.oz_splits;
+    const int splits = L.oz_build_splits;
     oz::gram_scale_kernel<<<cdiv(B, 256), 256, 0, s->stream>>>(s->oz_xscale(), 1.0 / (double)s->Nt, scale, B);
     LAUNCHED(s);
     for (int c0 = 0; c0 < n; c0 += B) {
@@ -52,7 +52,7 @@ static int gram_build_t(lcx_session* s, double* g, long long ldg, int B, double*
         p.c_split_stride = splits > 1 ? (long long)B * ldg : 0;
         p.col_scale = scale;
         p.inv_radix = 1.0 / (double)L.radix;
-        p.rows = n - c0; p.cols = nb; p.k_total = (int)s->Nl; p.k_chunk = L.oz_chunk;
+        p.rows = n - c0; p.cols = nb; p.k_total = (int)s->Nl; p.k_chunk = L.oz_build_chunk;
         p.bn = bn;
         p.trans_out = 1;
         LCX_TRY((oz::launch_oz_gemm<S, false>(map_a, map_b, p, dim3(n_tiles, cdiv(n - c0, oz::kBM), splits), s->stream, oz_cluster())));

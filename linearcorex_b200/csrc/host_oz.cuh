@@ -92,9 +92,26 @@ static int oz_pair_t(lcx_session* s, const double* A, double* svec, cudaEvent_t*
         p.inv_radix = 1.0 / (double)L.radix;
         p.rows = (int)s->Nl; p.cols = m; p.k_total = n; p.k_chunk = L.oz1_chunk;
         p.bn = s->oz_bn;
+        const int row0 = (cdiv(s->Nl, oz::kBM) - L.oz1_tail_tiles) * oz::kBM;
+        if (L.oz1_tail_tiles > 0) {  // two-level split (host_session.cuh: plan_two_level): the last row tiles' last K chunk, cut finer
+            const int groups = cdiv(cdiv(m, oz::bn_max(S)), 2), m_tiles = cdiv(s->Nl, oz::kBM);
+            p.main_units = groups * (m_tiles * L.oz1_splits - L.oz1_tail_tiles);
+            p.tail_units = groups * L.oz1_tail_tiles * L.oz1_tail_splits;
+            p.tail_m_tile0 = m_tiles - L.oz1_tail_tiles; p.tail_m_tiles = L.oz1_tail_tiles;
+            p.tail_kbase = (L.oz1_splits - 1) * L.oz1_chunk; p.tail_kchunk = L.oz1_tail_chunk;
+            p.tail_C = s->ptr(I_TAIL1) - (long long)row0 * L.ldy;
+            p.tail_ldc = L.ldy; p.tail_split_stride = (long long)L.oz1_tail_tiles * oz::kBM * L.ldy;
+        }
         LCX_TRY((oz::launch_oz_gemm<S, true>(s->map_x_k1, s->map_a_k1, p,
                                              dim3(cdiv(m, oz::bn_max(S)), cdiv(s->Nl, oz::kBM), L.oz1_splits), s->stream, oz_cluster())));
         LAUNCHED(s);
+        if (L.oz1_tail_tiles > 0) {
+            double* dst = (split1 ? s->ptr(I_PART) + (long long)(L.oz1_splits - 1) * s->Nl * L.ldy : Y) + (long long)row0 * L.ldy;
+            const int rows = (int)(s->Nl - row0);
+            oz::tail_fold_kernel<<<cdiv((long long)rows * m, 256), 256, 0, s->stream>>>(
+                s->ptr(I_TAIL1), L.oz1_tail_splits, (long long)L.oz1_tail_tiles * oz::kBM * L.ldy, L.ldy, dst, L.ldy, rows, m);
+            LAUNCHED(s);
+        }
         if (split1) {
             LCX_TRY(launch_reduce_splits(s->ptr(I_PART), L.oz1_splits, s->Nl * L.ldy, Y, (int)s->Nl, m, L.ldy, s->stream));
             LAUNCHED(s);
@@ -128,9 +145,26 @@ static int oz_pair_t(lcx_session* s, const double* A, double* svec, cudaEvent_t*
         p.rows = n; p.cols = m; p.k_total = (int)s->Nl; p.k_chunk = L.oz_chunk;
         p.bn = s->oz_bn;
         p.trans_out = 1;
+        const int var0 = (cdiv(n, oz::kBM) - L.oz_tail_tiles) * oz::kBM;
+        const long long tld = (long long)L.oz_tail_tiles * oz::kBM;
+        if (L.oz_tail_tiles > 0) {  // two-level split: the last variable tiles' last sample chunk, cut finer
+            const int groups = cdiv(cdiv(m, oz::bn_max(S)), 2), m_tiles = cdiv(n, oz::kBM);
+            p.main_units = groups * (m_tiles * L.oz_splits - L.oz_tail_tiles);
+            p.tail_units = groups * L.oz_tail_tiles * L.oz_tail_splits;
+            p.tail_m_tile0 = m_tiles - L.oz_tail_tiles; p.tail_m_tiles = L.oz_tail_tiles;
+            p.tail_kbase = (L.oz_splits - 1) * L.oz_chunk; p.tail_kchunk = L.oz_tail_chunk;
+            p.tail_C = s->ptr(I_TAIL2) - var0;
+            p.tail_ldc = tld; p.tail_split_stride = (long long)m * tld;
+        }
         LCX_TRY((oz::launch_oz_gemm<S, false>(s->map_x_k2, s->map_y_k2, p,
                                               dim3(cdiv(m, oz::bn_max(S)), cdiv(n, oz::kBM), L.oz_splits), s->stream, oz_cluster())));
         LAUNCHED(s);
+        if (L.oz_tail_tiles > 0) {
+            double* dst = (split ? s->ptr(I_PART) + (long long)(L.oz_splits - 1) * m * L.ld : D) + var0;
+            oz::tail_fold_kernel<<<cdiv((long long)m * (n - var0), 256), 256, 0, s->stream>>>(
+                s->ptr(I_TAIL2), L.oz_tail_splits, (long long)m * tld, tld, dst, L.ld, m, n - var0);
+            LAUNCHED(s);
+        }
         if (ev) LCX_CUDA(cudaEventRecord(ev[4], s->stream));
         LCX_TRY(combine_and_allreduce(s, split ? s->ptr(I_PART) : D, split ? L.oz_splits : 1, (long long)m * L.ld, m, n, L.ld, D, svec,
                                       want_tail ? m : 0));

@@ -68,6 +68,8 @@ enum {
     I_FPART,            // fused m x n phase (m <= 128, fused_strip_kernels.cuh): per-CTA partials of ry / H  [kSMs][m][ldm]
     I_FROW,             //              per-CTA row maxima and partial Bj of grad  [2][kSMs][ldm]
     I_TICKET,           //              arrival counters of the last-CTA reductions (self-resetting)
+    I_TAIL1,            // two-level split of the first contraction: partials of the tail units  [splits][tail rows][ldy]
+    I_TAIL2,            //              of the second contraction  [splits][m][tail variables]
     I_COUNT
 };
 
@@ -86,6 +88,10 @@ struct Layout {
     long long ld8, ldk8;         // byte leading dimensions of the X~/A slices and of the transposed Y slices (samples)
     int oz_splits, oz_chunk;     // split-K of the second contraction (over samples)
     int oz1_splits, oz1_chunk;   // split-K of the first contraction (over variables), only when row tiles are scarce
+    // two-level split (TwoLevel below): the last tail_tiles M tiles run their last K chunk cut tail_splits ways
+    int oz_tail_tiles, oz_tail_splits, oz_tail_chunk;     // second contraction (M tiles = 128 variables)
+    int oz_build_splits, oz_build_chunk;                  // the uniform split over samples (what lcx_gram_build walks)
+    int oz1_tail_tiles, oz1_tail_splits, oz1_tail_chunk;  // first contraction (M tiles = 128 samples)
     int ystat_slabs;
     int radix;                   // 128: 7-bit signed digits (|d| <= 64); 254: full int8 range (|d| <= 127)
     int oz_kmax;                 // longest contraction one int32 accumulator group may see: 2^31 / ((R/2)^2 S)
@@ -143,6 +149,51 @@ static double oz_unit_fixed_kb() {
     if (const char* env = getenv("LCX_OZ_FIXED_KB")) return atof(env);
     const char* per = getenv("LCX_OZ_PERSISTENT");
     return (per && atoi(per) == 0) ? 16.0 : 4.0;
+}
+
+// Two-level split of a contraction whose uniform units (M tiles x K splits, one cluster per unit and N group) do not fill whole
+// rounds of the resident clusters: R full rounds of the uniform units, and the r units left over -- the last K chunk of the
+// last few M tiles -- cut t = #clusters / r ways so that they fill ONE more short round instead of a long, mostly idle one.
+// 12 500 samples per rank (config 3 on 8 GPUs), second contraction: 79 tiles on 74 cluster pairs = 1 round of 196 K blocks + 5
+// tiles x 14 splits of 14 K blocks (cost 218 in K-block units) instead of 7 uniform splits in 8 rounds of 28 + 4 (266).
+// Cost model as everywhere: rounds x (K blocks per unit + the per-unit fixed cost) + what the combine of the partials costs.
+struct TwoLevel {
+    int splits, chunk;                       // uniform level
+    int tail_tiles, tail_splits, tail_chunk; // 0 tiles: plain uniform split
+    double cost;
+};
+static TwoLevel plan_two_level(long long K, int m_tiles, int n_groups, int smin, int smax, double combine_per_split) {
+    const int clusters = kSMs / 2;
+    TwoLevel best = {0, 0, 0, 0, 0, 1e300};  // (only plans WITH a tail are returned; cost 1e300 = none exists)
+    for (int s0 = smin; s0 <= max(smin, smax); ++s0) {
+        const int chunk = (int)round_up(cdiv(K, s0), oz::kBK);
+        const int sp = cdiv(K, chunk);
+        if (sp < smin) continue;
+        const long long U = (long long)n_groups * m_tiles * sp;
+        const long long R = U / clusters, r = U - R * clusters;
+        const int rt = cdiv(r, n_groups);
+        if (r == 0 || R == 0 || rt > m_tiles) continue;
+        const long long klast = K - (long long)(sp - 1) * chunk;
+        int t = (int)min((long long)(clusters / (rt * n_groups)), max(1LL, (long long)cdiv(klast, oz::kBK) / 2));
+        if (t <= 1) continue;
+        const int tchunk = (int)round_up(cdiv(klast, t), oz::kBK);
+        t = cdiv(klast, tchunk);
+        if (t <= 1) continue;
+        const double cost = (double)R * (chunk / oz::kBK + oz_unit_fixed_kb()) + (tchunk / oz::kBK + oz_unit_fixed_kb()) +
+                            (sp > 1 ? combine_per_split * sp : 0.0) + 4.0;  // + the fold launch
+        if (cost < best.cost - 1e-9) best = TwoLevel{sp, chunk, rt, t, tchunk, cost};
+    }
+    return best;
+}
+// LCX_OZ_TAIL=0 switches the two-level split off; it needs the persistent unit walk and pairs of N tiles in one launch.
+static bool oz_tail_allowed(int m, int S) {
+    const char* env = getenv("LCX_OZ_TAIL");
+    if (env && atoi(env) == 0) return false;
+    const char* per = getenv("LCX_OZ_PERSISTENT");
+    if (per && atoi(per) == 0) return false;
+    const char* cl = getenv("LCX_OZ_CLUSTER");
+    if (cl && atoi(cl) != 2) return false;
+    return cdiv(m, oz::bn_max(S)) % 2 == 0;
 }
 
 // Gram product plan (host_gram.cuh): `full` row tiles run as whole waves with the full contraction, the remaining ones split
@@ -270,6 +321,16 @@ static Layout make_layout(long long Nl, int n, int m, int precision, bool gram =
         }
         L.oz_chunk = (int)round_up(cdiv(Nl, best), oz::kBK);
         L.oz_splits = cdiv(Nl, L.oz_chunk);
+        L.oz_build_splits = L.oz_splits;
+        L.oz_build_chunk = L.oz_chunk;
+        const bool tail_ok = !gram && oz_tail_allowed(m, L.S);
+        if (tail_ok && getenv("LCX_OZ_SPLITS") == nullptr) {
+            const TwoLevel t2 = plan_two_level(Nl, cdiv(n, oz::kBM), cdiv(cdiv(m, oz::bn_max(L.S)), 2), smin, max(smin, smax), 1.5);
+            if (t2.tail_tiles > 0 && t2.cost < best_cost) {
+                L.oz_chunk = t2.chunk; L.oz_splits = t2.splits;
+                L.oz_tail_tiles = t2.tail_tiles; L.oz_tail_splits = t2.tail_splits; L.oz_tail_chunk = t2.tail_chunk;
+            }
+        }
         {   // first contraction: same cost model over its (row tile x factor tile) grid
             const long long tiles1 = (long long)cdiv(Nl, oz::kBM) * cdiv(m, oz::bn_max(L.S));
             const int kblocks1 = cdiv(n, oz::kBK);
@@ -283,6 +344,14 @@ static Layout make_layout(long long Nl, int n, int m, int precision, bool gram =
             }
             L.oz1_chunk = (int)round_up(cdiv(n, b1), oz::kBK);
             L.oz1_splits = cdiv(n, L.oz1_chunk);
+            if (tail_ok) {
+                const TwoLevel t1 = plan_two_level(n, cdiv(Nl, oz::kBM), cdiv(cdiv(m, oz::bn_max(L.S)), 2), s1min,
+                                                   max(s1min, min(8, kblocks1 / 16)), 4.0);
+                if (t1.tail_tiles > 0 && t1.cost < c1best) {
+                    L.oz1_chunk = t1.chunk; L.oz1_splits = t1.splits;
+                    L.oz1_tail_tiles = t1.tail_tiles; L.oz1_tail_splits = t1.tail_splits; L.oz1_tail_chunk = t1.tail_chunk;
+                }
+            }
         }
         long long part = max((long long)L.oz_splits * mn * L.ld, L.oz1_splits > 1 ? (long long)L.oz1_splits * Nl * L.ldy : 0LL);
         if (gram) {
@@ -302,6 +371,12 @@ static Layout make_layout(long long Nl, int n, int m, int precision, bool gram =
         put1(I_AS, 1, as8, as8);
         put1(I_YS, 1, ys8, ys8);
         put1(I_AMAX, 1, kAmaxCtas, kAmaxCtas);
+        {
+            const long long t1 = max(16LL, (long long)L.oz1_tail_splits * L.oz1_tail_tiles * oz::kBM * L.ldy);
+            const long long t2 = max(16LL, (long long)L.oz_tail_splits * mn * L.oz_tail_tiles * oz::kBM);
+            put1(I_TAIL1, 1, t1, t1);
+            put1(I_TAIL2, 1, t2, t2);
+        }
         L.mm_i8 = mm_i8_for(L.S, n, m);
         if (L.mm_i8) {
             L.ldm8 = round_up(m, 128);
@@ -339,6 +414,10 @@ static Layout make_layout(long long Nl, int n, int m, int precision, bool gram =
     }
     put1(I_TICKET, 1, 16, 16);
     L.total = cur;
+    if (getenv("LCX_PLAN_DEBUG") && L.S > 0)
+        fprintf(stderr, "[lcx plan] Nl=%lld n=%d m=%d gram=%d | K1: splits %d chunk %d tail %d tiles x %d splits (chunk %d) | K2: splits %d "
+                "chunk %d tail %d tiles x %d splits (chunk %d)\n", Nl, n, m, (int)gram, L.oz1_splits, L.oz1_chunk, L.oz1_tail_tiles,
+                L.oz1_tail_splits, L.oz1_tail_chunk, L.oz_splits, L.oz_chunk, L.oz_tail_tiles, L.oz_tail_splits, L.oz_tail_chunk);
     return L;
 }
 

@@ -186,6 +186,16 @@ struct GemmParams {
                                  // N-side loads -- results are garbage, timings isolate the operand feed from the tensor work
     const double* c_add;         // optional (with trans_out, no split): C = c_add + product, c_add laid out like C (may be C
                                  // itself: grad = G0 + H W, linearcorex.py:300; Qij = rinv + (ry - I) rinv, :266)
+    // Two-level split (short contractions, e.g. 12 500 samples per rank): the uniform units fill whole rounds of the resident
+    // clusters; the units that would start a mostly idle last round -- K chunk k_splits - 1 of the last tail_m_tiles M tiles --
+    // are left out of the uniform walk (main_units of them remain) and run instead as tail_units finer units: that K chunk cut
+    // tail_splits ways, partials in their own compact buffer (folded into the uniform layout by tail_fold_kernel).
+    int main_units;              // 0: every uniform unit; else the uniform walk stops here
+    int tail_units;              // n_groups * tail_m_tiles * tail_splits
+    int tail_m_tile0, tail_m_tiles;
+    int tail_kbase, tail_kchunk; // K range of tail split z: [tail_kbase + z * tail_kchunk, + tail_kchunk) clipped to k_total
+    double* tail_C;              // indexed with ABSOLUTE rows / cols like C (+ z * tail_split_stride)
+    long long tail_ldc, tail_split_stride;
 };
 
 // The N-side (factor) operand is always K-major: B tile = [64 rows][64 B of K] (SW64), tensor map (K, rows, slice),
@@ -276,7 +286,8 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     const int b_bytes = bn * kBK;
     // work units of this launch: u -> (N group, M tile, K split), N groups fastest
     const int cluster_id = (int)blockIdx.x / CL, n_clusters = (int)gridDim.x / CL;
-    const int units = p.n_groups * p.m_tiles * p.k_splits;
+    const int units_main = p.main_units > 0 ? p.main_units : p.n_groups * p.m_tiles * p.k_splits;
+    const int units = units_main + p.tail_units;
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
@@ -297,14 +308,28 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     const uint32_t tmem_base = tmem_base_smem;
 
     // decode of unit u for this CTA (its own N tile of the cluster's group)
+    // (z < 0 encodes tail split -1 - z)
     auto unit_of = [&](int u, int& n_tile, int& m_tile, int& z, int& kbeg, int& num_kb) {
-        const int g = u % p.n_groups;
-        const int r = u / p.n_groups;
-        m_tile = p.m_tile0 + r % p.m_tiles;
-        z = r / p.m_tiles;
-        n_tile = p.n_tile0 + g * CL + (int)crank;
-        kbeg = z * p.k_chunk;
-        const int kend = min(p.k_total, kbeg + p.k_chunk);
+        int kend;
+        if (u < units_main) {
+            const int g = u % p.n_groups;
+            const int r = u / p.n_groups;
+            m_tile = p.m_tile0 + r % p.m_tiles;
+            z = r / p.m_tiles;
+            n_tile = p.n_tile0 + g * CL + (int)crank;
+            kbeg = z * p.k_chunk;
+            kend = min(p.k_total, kbeg + p.k_chunk);
+        } else {
+            const int v = u - units_main;
+            const int g = v % p.n_groups;
+            const int r = v / p.n_groups;
+            m_tile = p.tail_m_tile0 + r % p.tail_m_tiles;
+            const int zt = r / p.tail_m_tiles;
+            z = -1 - zt;
+            n_tile = p.n_tile0 + g * CL + (int)crank;
+            kbeg = p.tail_kbase + zt * p.tail_kchunk;
+            kend = min(p.k_total, kbeg + p.tail_kchunk);
+        }
         num_kb = (kend > kbeg) ? (kend - kbeg + kBK - 1) / kBK : 0;
     };
 
@@ -420,7 +445,8 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 tc_fence_after();
                 ++it;
             }
-            double* C = p.C + (long long)z * p.c_split_stride;
+            double* C = z >= 0 ? p.C + (long long)z * p.c_split_stride : p.tail_C + (long long)(-1 - z) * p.tail_split_stride;
+            const long long ldc = z >= 0 ? p.ldc : p.tail_ldc;
             const double rs = (p.row_scale != nullptr && row < p.rows) ? p.row_scale[row] : 1.0;
 #pragma unroll 1
             for (int c0 = 0; c0 < bn; c0 += 16) {
@@ -471,12 +497,12 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                                 v0 += cur[j];
                                 v1 += cur[j + 1];
                             }
-                            if (col < cend) C[(long long)col * p.ldc + row] = v0;
-                            if (col + 1 < cend) C[(long long)(col + 1) * p.ldc + row] = v1;
+                            if (col < cend) C[(long long)col * ldc + row] = v0;
+                            if (col + 1 < cend) C[(long long)(col + 1) * ldc + row] = v1;
                         } else if (col + 1 < cend) {
-                            *reinterpret_cast<double2*>(C + (long long)row * p.ldc + col) = make_double2(v0, v1);
+                            *reinterpret_cast<double2*>(C + (long long)row * ldc + col) = make_double2(v0, v1);
                         } else if (col < cend) {
-                            C[(long long)row * p.ldc + col] = v0;
+                            C[(long long)row * ldc + col] = v0;
                         }
                     }
                 }
@@ -807,6 +833,26 @@ __global__ void y_stats_finish_kernel(const double* __restrict__ part, int slabs
     }
 }
 
+// dst[r][c] = sum_t src[t][r][c], t in index order (rows x cols; leading dimensions ld_src / ld_dst; split t at t * stride):
+// folds the tail partials of the two-level split (GemmParams::tail_*) into the slot the uniform walk left unwritten.
+__global__ void __launch_bounds__(256) tail_fold_kernel(const double* __restrict__ src, int splits, long long stride,
+                                                        long long ld_src, double* __restrict__ dst, long long ld_dst, int rows,
+                                                        int cols) {
+    const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (i >= (long long)rows * cols) return;
+    const int r = (int)(i / cols), c = (int)(i - (long long)r * cols);
+    const double* p0 = src + (long long)r * ld_src + c;
+    double acc = p0[0];
+    int t = 1;
+    for (; t + 3 < splits; t += 4) {  // four loads in flight, added in index order
+        const double v0 = p0[(long long)t * stride], v1 = p0[(long long)(t + 1) * stride];
+        const double v2 = p0[(long long)(t + 2) * stride], v3 = p0[(long long)(t + 3) * stride];
+        acc += v0; acc += v1; acc += v2; acc += v3;
+    }
+    for (; t < splits; ++t) acc += p0[(long long)t * stride];
+    dst[(long long)r * ld_dst + c] = acc;
+}
+
 // cscale[j] = x_scale * a_scale[j]   (output scale of Y = X~ A^T)
 __global__ void mul_scale_kernel(const double* __restrict__ x_scale, const double* __restrict__ a_scale, double* __restrict__ out,
                                  int m) {
@@ -956,7 +1002,7 @@ inline int launch_oz_gemm_cl(const CUtensorMap& mapA, const CUtensorMap& mapB, G
     p.n_groups = (int)round_up(grid.x, CL) / CL;
     p.m_tiles = (int)grid.y;
     p.k_splits = (int)grid.z;
-    const long long units = (long long)p.n_groups * p.m_tiles * p.k_splits;
+    const long long units = (p.main_units > 0 ? (long long)p.main_units : (long long)p.n_groups * p.m_tiles * p.k_splits) + p.tail_units;
     {
         static int dbg = -1;
         if (dbg < 0) {
