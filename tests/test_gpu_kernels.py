@@ -286,6 +286,22 @@ def test_pass_pair_random_shapes_fp64_split(N, n, m):
     test_pass_pair_over_tile_edges("fp64_split", 5e-11, N, n, m)
 
 
+@pytest.mark.parametrize("N,n,m", [(12500, 10000, 100), (9600, 9500, 120), (4000, 20000, 70), (25000, 10000, 100)])
+def test_pass_pair_two_level_split(N, n, m, monkeypatch, capfd):
+    """Shapes whose units do not fill whole rounds of the 74 resident cluster pairs (config 3's 12 500 samples per rank on 8
+    GPUs first): the planner's two-level split (host_session.cuh: plan_two_level; tail units inside the persistent launch,
+    ozaki_i8.cuh; tail_fold_kernel) must engage and give the same `_sig` as numpy."""
+    from linearcorex_b200 import _lib as L
+    monkeypatch.setenv("LCX_PLAN_DEBUG", "1")
+    L.load().lcx_workspace_doubles(N, n, m, L.PRECISIONS["fp64_split"])
+    plan = capfd.readouterr().err
+    assert "[lcx plan]" in plan and plan.count("tail 0 tiles") < 2, plan  # at least one of the two contractions has a tail
+    monkeypatch.delenv("LCX_PLAN_DEBUG")
+    test_pass_pair_over_tile_edges("fp64_split", 5e-11, N, n, m)
+    monkeypatch.setenv("LCX_OZ_TAIL", "0")   # and the uniform plan still works when the tail is switched off
+    test_pass_pair_over_tile_edges("fp64_split", 5e-11, N, n, m)
+
+
 @pytest.mark.parametrize("name,algorithm", [("syn_400x300x10_f64", "stream"), ("big5_l0_f64", "stream"),
                                             ("standard_missing_f64", "gram"), ("syn_4000x2000x20_f64", "gram")])
 def test_fused_mxn_phase_matches_golden(name, algorithm, monkeypatch):
