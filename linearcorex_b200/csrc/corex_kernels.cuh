@@ -265,6 +265,16 @@ __global__ void __launch_bounds__(256) direction_stage2_kernel(
     }
 }
 
+// The 16 scalars of an iteration (TC, max uj, tangent, ..., the solve status) stored straight into the session's page-locked
+// mailbox -- host memory, device-addressable under UVA -- followed by a sequence number the host polls: no copy engine, no
+// stream synchronisation between the last kernel of a trial and the host's accept / backtrack decision.  One warp.
+__global__ void post_mailbox_kernel(const double* __restrict__ scalars, volatile double* box, unsigned long long seq) {
+    if (threadIdx.x < 16) box[threadIdx.x] = scalars[threadIdx.x];
+    __threadfence_system();
+    __syncwarp();
+    if (threadIdx.x == 0) *reinterpret_cast<volatile unsigned long long*>(box + 16) = seq;
+}
+
 // out[0] = sum of partials (fixed order).  Single CTA.
 __global__ void sum_partials_kernel(const double* __restrict__ part, int nparts, double* __restrict__ out) {
     __shared__ double scratch[8];

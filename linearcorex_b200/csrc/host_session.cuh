@@ -429,6 +429,7 @@ struct lcx_session {
     long long launches;
     double* mailbox;  // pinned host, 16 doubles (a slot of the process-wide block, lcx_api.cu)
     bool mailbox_pooled;
+    unsigned long long mailbox_seq;   // sequence number of the last post_mailbox_kernel (slot 16 of the mailbox)
     bool bound;
     const double* xt;
     bool gram;        // the bound matrix is X~^T X~ / N (lcx_bind_gram): a "pass pair" is ONE product G A^T (host_gram.cuh)

@@ -1,6 +1,8 @@
 // The steps of one fit iteration as sequences of launches on the session stream (no host synchronisation here):
 // the X pass pair + exchange, the moment tail, direction and trial.  Included by lcx_api.cu after host_oz.cuh.
 #pragma once
+#include <atomic>
+
 #include "host_oz.cuh"
 #include "host_gram.cuh"
 
@@ -178,9 +180,39 @@ static int xpair(lcx_session* s, const double* A, bool want_colsq, const double*
     return 0;
 }
 
+// LCX_MAILBOX=copy: cudaMemcpyAsync + cudaStreamSynchronize (the round-1 path); default: post_mailbox_kernel + polling.
+static bool mailbox_posted() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("LCX_MAILBOX");
+        v = (e && strcmp(e, "copy") == 0) ? 0 : 1;
+    }
+    return v != 0;
+}
 static int read_mailbox(lcx_session* s) {
-    LCX_CUDA(cudaMemcpyAsync(s->mailbox, s->ptr(LCX_A_SCALARS), 16 * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
-    LCX_CUDA(cudaStreamSynchronize(s->stream));
+    if (!mailbox_posted()) {
+        LCX_CUDA(cudaMemcpyAsync(s->mailbox, s->ptr(LCX_A_SCALARS), 16 * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+        LCX_CUDA(cudaStreamSynchronize(s->stream));
+        return 0;
+    }
+    const unsigned long long seq = ++s->mailbox_seq;
+    post_mailbox_kernel<<<1, 32, 0, s->stream>>>(s->ptr(LCX_A_SCALARS), s->mailbox, seq);
+    LAUNCHED(s);
+    volatile unsigned long long* flag = reinterpret_cast<volatile unsigned long long*>(s->mailbox + 16);
+    unsigned polls = 0;
+    while (*flag != seq) {
+        if ((++polls & 0x3fffu) == 0) {  // every ~16k polls: has the stream failed, or drained without the flag landing?
+            const cudaError_t q = cudaStreamQuery(s->stream);
+            if (q == cudaSuccess) {
+                if (*flag == seq) break;
+                LCX_CUDA(cudaStreamSynchronize(s->stream));
+                if (*flag != seq) return fail(LCX_ERR_CUDA, "read_mailbox", "the mailbox post never arrived");
+                break;
+            }
+            if (q != cudaErrorNotReady) return fail(LCX_ERR_CUDA, "read_mailbox", cudaGetErrorString(q));
+        }
+    }
+    std::atomic_thread_fence(std::memory_order_acquire);
     return 0;
 }
 

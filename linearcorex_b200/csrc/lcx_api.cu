@@ -6,7 +6,7 @@
 #include "host_steps.cuh"
 
 // ---- lifecycle ---------------------------------------------------------------------------------
-// Mailboxes (16 pinned doubles per session) come from one process-wide page-locked block: cudaHostAlloc / cudaFreeHost cost
+// Mailboxes (32 pinned doubles per session) come from one process-wide page-locked block: cudaHostAlloc / cudaFreeHost cost
 // 10-80 ms each once the process maps 100+ GB of device memory (measured: the Gram route's re-bind spent 0.08-0.17 s in
 // them), and both synchronise the device.  64 slots; a 65th concurrent session falls back to its own allocation.
 #include <mutex>
@@ -14,7 +14,7 @@ namespace {
 std::mutex g_mailbox_mutex;
 double* g_mailbox_pool = nullptr;
 unsigned long long g_mailbox_used = 0;
-constexpr int kMailboxSlots = 64, kMailboxDoubles = 16;
+constexpr int kMailboxSlots = 64, kMailboxDoubles = 32;  // 16 scalars + the sequence number of post_mailbox_kernel (+ padding)
 
 double* mailbox_acquire(bool* pooled) {
     std::lock_guard<std::mutex> lock(g_mailbox_mutex);
@@ -69,6 +69,7 @@ extern "C" int lcx_session_create(lcx_session** out, int device, int precision) 
         delete s;
         return fail(LCX_ERR_CUDA, "lcx_session_create", "no page-locked memory for the mailbox");
     }
+    for (int i = 0; i < kMailboxDoubles; ++i) s->mailbox[i] = 0.0;  // (a recycled slot still holds its last owner's sequence number)
     *out = s;
     return 0;
 }
