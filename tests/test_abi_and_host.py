@@ -71,6 +71,53 @@ def test_layout_of_the_int8_product_route(monkeypatch):
                                                       lib.lcx_workspace_doubles(N, n, m, 0))      # DMMA mode ignores it
 
 
+def _plan(lib, capfd, N, n, m, precision=2):
+    """(K1, K2) plans of the split-integer contractions as printed by LCX_PLAN_DEBUG: dicts of splits / chunk / tail."""
+    import re
+    capfd.readouterr()
+    assert lib.lcx_workspace_doubles(N, n, m, precision) > 0
+    text = capfd.readouterr().err
+    out = []
+    for part in re.findall(r"splits (\d+) chunk (\d+) tail (\d+) tiles x (\d+) splits \(chunk (\d+)\)", text):
+        out.append(dict(zip(("splits", "chunk", "tail_tiles", "tail_splits", "tail_chunk"), map(int, part))))
+    assert len(out) == 2, text
+    return out
+
+
+def test_two_level_split_plan(monkeypatch, capfd):
+    """host_session.cuh: plan_two_level.  With 12 500 samples per rank (config 3 on 8 GPUs) the 79 variable tiles of the
+    second contraction run one full-length round on the 74 resident cluster pairs and the 5 left-over tiles are cut 14 ways;
+    every chunk is a whole number of 64-deep K blocks, stays within the int32-exact contraction length, and the tail units
+    fit one round.  No tail with an odd number of factor tiles (m = 30), in the DMMA mode, or when switched off."""
+    from linearcorex_b200 import _lib
+    lib = _lib.load()
+    monkeypatch.setenv("LCX_PLAN_DEBUG", "1")
+    monkeypatch.delenv("LCX_OZ_TAIL", raising=False)
+    k1, k2 = _plan(lib, capfd, 12500, 10000, 100)
+    assert (k2["splits"], k2["tail_tiles"], k2["tail_splits"]) == (1, 5, 14)
+    assert (k1["splits"], k1["tail_tiles"], k1["tail_splits"]) == (1, 24, 3)
+    kmax = (2 ** 31 // (127 * 127 * 6)) // 64 * 64
+    for N, n, m in [(12500, 10000, 100), (25000, 10000, 100), (50000, 10000, 100), (100000, 10000, 100), (125000, 20000, 100),
+                    (1000000, 20000, 100), (1000, 50000, 500), (9600, 9500, 120), (4000, 20000, 70), (777, 333, 65)]:
+        for plan, K, m_tiles in zip(_plan(lib, capfd, N, n, m), (n, N), ((N + 127) // 128, (n + 127) // 128)):
+            assert plan["chunk"] % 64 == 0 and plan["chunk"] <= kmax and plan["splits"] * plan["chunk"] >= K
+            assert (plan["splits"] - 1) * plan["chunk"] < K
+            if plan["tail_tiles"]:
+                groups = (-(-m // 64) + 1) // 2
+                assert plan["tail_chunk"] % 64 == 0 and plan["tail_splits"] >= 2
+                assert plan["tail_tiles"] <= m_tiles
+                assert groups * plan["tail_tiles"] * plan["tail_splits"] <= 74          # one round of the cluster pairs
+                last = K - (plan["splits"] - 1) * plan["chunk"]                          # the K chunk the tail re-cuts
+                assert (plan["tail_splits"] - 1) * plan["tail_chunk"] < last <= plan["tail_splits"] * plan["tail_chunk"]
+                units = groups * m_tiles * plan["splits"]
+                assert units - groups * plan["tail_tiles"] <= units // 74 * 74           # what is left fills whole rounds
+    assert all(p["tail_tiles"] == 0 for p in _plan(lib, capfd, 125000, 20000, 30))       # one factor tile: no pairs
+    monkeypatch.setenv("LCX_OZ_TAIL", "0")
+    assert all(p["tail_tiles"] == 0 for p in _plan(lib, capfd, 12500, 10000, 100))
+    uniform = _plan(lib, capfd, 12500, 10000, 100)
+    assert uniform[1]["splits"] == 7 and uniform[0]["splits"] == 3                        # what round 1 ran at this shape
+
+
 def test_no_cpu_fallback():
     import torch
     if torch.cuda.is_available():
