@@ -151,7 +151,9 @@ class ClockSampler(object):
         try:
             self.proc = subprocess.Popen([sys.executable, "-c", _CLOCK_HELPER, str(index), str(self.PERIOD_S)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            first = self.proc.stdout.readline().split()  # blocks until NVML is initialised in the helper
+            import select
+            ready, _, _ = select.select([self.proc.stdout], [], [], 30.0)  # NVML initialised in the helper (or it died)
+            first = self.proc.stdout.readline().split() if ready else []
             if len(first) == 2 and first[0] == "ready":
                 self.max_mhz = int(first[1])
             else:
