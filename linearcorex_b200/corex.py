@@ -145,6 +145,34 @@ class LazyMoments(dict):
         return (dict, (dict(self.materialize()),))
 
 
+class _HostDraw(object):
+    """np.random.randn(m, n) from the global legacy generator, on a background thread."""
+
+    def __init__(self, m, n):
+        import threading
+        self.out, self.err, self._th = None, None, None
+        if os.environ.get("LCX_HOST_DRAW", "thread") != "thread":  # (A/B switch: draw inline, where the reference does)
+            self._args = (m, n)
+            return
+        self._th = threading.Thread(target=self._run, args=(m, n), daemon=True)
+        self._th.start()
+
+    def _run(self, m, n):
+        try:
+            self.out = np.random.randn(m, n)
+        except BaseException as e:  # surfaced by result()
+            self.err = e
+
+    def result(self):
+        if self._th is None:
+            self._run(*self._args)
+        else:
+            self._th.join()
+        if self.err is not None:
+            raise self.err
+        return self.out
+
+
 class _DeviceSession(object):
     """Owns the lcx_session handle, the bound X~ block and the torch workspace."""
 
@@ -603,6 +631,10 @@ class Corex(object):
         if self.m is None:
             raise ValueError("n_hidden=None (pick_n_hidden) is not supported: the reference helper is broken (:458-480)")
         red = self._reducer()
+        # W0 (:114-121) comes from numpy's legacy global generator exactly as in the reference -- a serial MT19937 + polar-method
+        # stream (55 ms for 100 x 10 000 on one core).  Nothing else of fit draws from it, so it is drawn first, on a thread
+        # (RandomState releases the GIL), while the device work of the preparation runs; joined where the reference draws it.
+        w0_draw = _HostDraw(self.m, int(np.shape(x)[1])) if self.ws.size == 0 else None
         if self.precision == 'auto':  # every rank sees the same total, so every rank takes the same path
             self.precision_used = resolve_precision('auto', red.sum_scalar(int(np.shape(x)[0])), int(np.shape(x)[1]), self.m,
                                                     self.gaussianize)
@@ -633,7 +665,7 @@ class Corex(object):
         schedule = [0.]
         if self.ws.size == 0:  # :114-121
             if self.discourage_overlap:
-                w0 = np.random.randn(self.m, self.nv)
+                w0 = w0_draw.result()
                 if self.input_dtype == 'float32':
                     w0 = w0.astype(np.float32)
                 self._set_w(w0)
@@ -641,7 +673,7 @@ class Corex(object):
                 if self.anneal:
                     schedule = list(ANNEAL_SCHEDULE)
             else:
-                self._set_w(np.random.randn(self.m, self.nv) * self.yscale ** 2 / np.sqrt(self.nv))
+                self._set_w(w0_draw.result() * self.yscale ** 2 / np.sqrt(self.nv))
         else:
             self._set_w(self.ws)
         self.moments = {"TC": self._moments_from_x()}  # :122
